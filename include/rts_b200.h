@@ -1,0 +1,141 @@
+/* rts_b200.h — C-ABI of librts_b200.so, the B200-native (sm_100a) ray-tracing radar path.
+ *
+ * Drop-in boundary for the reference's OptiX pipeline.  Each entry point names the reference
+ * interface it replaces (file:line in /root/reference).  All pointers passed in are caller-owned
+ * HOST memory unless a name ends in _device; the library owns every device allocation behind the
+ * opaque handle.  Every function returns RTS_OK (0) or a negative error code and never exits the
+ * process (the reference aborts: RT_CHECK_ERROR, aggregation.cu:17-27, ray_tracer.cpp:455-458);
+ * rts_last_error() returns the thread-local message of the last failure.
+ *
+ * There is no CPU fallback: every compute entry point fails with RTS_ERR_NO_DEVICE when no
+ * sm_100-class CUDA device is usable.
+ */
+#ifndef RTS_B200_H
+#define RTS_B200_H
+
+#include "rts_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTS_OK               0
+#define RTS_ERR_ARG         -1
+#define RTS_ERR_NO_DEVICE   -2
+#define RTS_ERR_CUDA        -3
+#define RTS_ERR_STATE       -4
+#define RTS_ERR_CAPACITY    -5
+
+/* rts_trace_pulse flags */
+#define RTS_OUT_BINS      1u  /* fused post-process + aggregation into (receiver, path) bins         */
+#define RTS_OUT_RECORDS   2u  /* reference-shaped per-ray arrays (dbuf_results / _targ_intersect / _rcs_angle) + tri_path */
+#define RTS_COUNT_NODES   4u  /* fill rts_stats.nodes_visited / tris_tested (slower)                 */
+#define RTS_NO_FINALISE   8u  /* leave bins un-finalised (caller reduces across GPUs, then rts_finalise_bins) */
+#define RTS_NO_RCS_ANGLES 16u /* records mode: skip the four atan2 per bounce, leave rcs_angle at -1e6 */
+
+typedef struct rts_engine rts_engine;
+
+/* Rigid pose of one target for one pulse: world = (has_rotation ? R * base : base) + t, evaluated
+ * exactly as ray_tracer.cpp:156-170 + :1006-1014 do ((0 + R[i][0]*v0) + R[i][1]*v1) + R[i][2]*v2, then + t[i]).
+ * `base` is the mesh given to rts_scene_set_targets (already carrying the t = 0 rotation,
+ * ray_tracer.cpp:956-987).  Normals get the rotation only. */
+typedef struct rts_pose {
+    double  R[9];          /* row-major */
+    double  t[3];
+    int32_t has_rotation;
+    int32_t _pad;
+} rts_pose;
+
+typedef struct rts_sizes {
+    uint64_t rays;        /* nx*ny*nz                                        */
+    uint64_t ray_total;   /* M * rays      (ray_tracer.cpp:608-626)          */
+    uint32_t depth_total; /* D = max_refl + (max_refr ? 2 : 0)   (:655)      */
+    uint32_t slots;       /* M                                               */
+    uint32_t tri_cols;    /* W = max_refl + 3, columns of tri_path           */
+    uint32_t _pad;
+} rts_sizes;
+
+typedef struct rts_bvh_info {
+    uint32_t n_tris, n_nodes, root_is_leaf, max_leaf;
+    float    scene_lo[3], scene_hi[3];
+    float    ms_build, ms_refit;
+    double   sah_cost;     /* surface-area-heuristic cost of the current tree (diagnostic) */
+} rts_bvh_info;
+
+/* ---- life cycle (replaces rtContextCreate / rtContextDestroy, ray_tracer.cpp:532-534,1358) ---- */
+int         rts_create(int device, rts_engine **out);
+void        rts_destroy(rts_engine *e);
+const char *rts_last_error(void);
+const char *rts_version(void);
+/* sizeof() of the POD structs as compiled, for binding self-checks:
+ * [0] rts_ray_record [1] rts_target_mesh [2] rts_rx_sphere [3] rts_rx_desc [4] rts_pulse
+ * [5] rts_bin [6] rts_stats [7] rts_pose */
+int         rts_abi_sizes(uint32_t sizes[8]);
+/* Run subsequent work of this engine on a caller-provided cudaStream_t (NULL = engine's own). */
+int         rts_set_stream(rts_engine *e, void *cuda_stream);
+
+/* ---- host helpers (pure host code, usable without a GPU) ---- */
+/* Receiver sphere centre and angular window: ray_tracer.cpp:894-918. */
+void rts_rx_sphere_from_desc(const rts_rx_desc *desc, rts_rx_sphere *out);
+/* Result-array sizes: ray_tracer.cpp:600-626, 655. */
+int  rts_result_sizes(const rts_pulse *pulse, rts_sizes *out);
+/* Mesh generators and rigid rotation: ray_tracer.cpp:156-170, 226-297, 300-426, 429-504.
+ * Two-call protocol: NULL output arrays → counts only. */
+int  rts_rect_mesh(float w, float h, float d, float yaw, float pitch, float roll,
+                   double *verts, uint32_t *n_verts, uint32_t *tris, uint32_t *n_tris,
+                   double *normals, uint32_t *n_normals);
+int  rts_sphere_mesh(uint32_t subdivs, float radius, float yaw, float pitch, float roll,
+                     double *verts, uint32_t *n_verts, uint32_t *tris, uint32_t *n_tris,
+                     double *normals, uint32_t *n_normals);
+int  rts_file_mesh(const char *v_file, const char *n_file, float yaw, float pitch, float roll,
+                   double *verts, uint32_t *n_verts, uint32_t *tris, uint32_t *n_tris,
+                   double *normals, uint32_t *n_normals);
+/* Rotation matrix Rz(yaw)*Ry(pitch)*Rx(roll) with the reference's float angles (ray_tracer.cpp:156-162). */
+void rts_rotation_matrix(float yaw, float pitch, float roll, double R[9]);
+
+/* ---- scene (replaces the per-pulse rtGeometry/rtBuffer/rtAcceleration set-up,
+ *      ray_tracer.cpp:1017-1133, and OptiX's "Bvh" builder) ---- */
+/* Upload all targets in their base pose and build the BVH (Morton LBVH) on the device. */
+int rts_scene_set_targets(rts_engine *e, const rts_target_mesh *targets, uint32_t n_targets);
+/* Per-pulse target motion (ray_tracer.cpp:936-1014): transform on the device, refit the BVH. */
+int rts_scene_set_poses(rts_engine *e, const rts_pose *poses, uint32_t n_targets);
+/* Full rebuild at the current poses (what the reference does every pulse, ray_tracer.cpp:1126-1130). */
+int rts_scene_rebuild(rts_engine *e);
+int rts_scene_bvh_info(rts_engine *e, rts_bvh_info *out);
+/* Parity/diagnostic read-backs: world-space vertices of one target [n_verts*3]; leaf boxes in
+ * global-triangle order [n_tris*6] (the `bound` program, triangle_mesh.cu:204-233). */
+int rts_scene_get_world_vertices(rts_engine *e, uint32_t target, double *out);
+int rts_scene_get_tri_bounds(rts_engine *e, float *out6);
+/* Returns 0 when every triangle's box is contained in all its ancestors' boxes, else the number of violations. */
+int rts_scene_check_bvh(rts_engine *e, uint64_t *violations);
+
+/* ---- one pulse (replaces rtContextLaunch3D + the result hand-off, ray_tracer.cpp:1165-1258) ---- */
+int rts_trace_pulse(rts_engine *e, const rts_pulse *pulse, uint32_t flags);
+int rts_get_stats(rts_engine *e, rts_stats *out);
+/* RTS_OUT_BINS: non-empty bins sorted by (rx, path). *n is the total even when cap is smaller. */
+int rts_get_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n);
+/* RTS_OUT_RECORDS: copy out the reference-shaped arrays; any pointer may be NULL.
+ *   results [ray_total] · targ_intersect [ray_total*D] · rcs_angle [ray_total*D*2] · tri_path [ray_total*W] */
+int rts_get_records(rts_engine *e, rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle,
+                    int32_t *tri_path);
+
+/* ---- multi-GPU plumbing: raw bin accumulators for an external reduction (NCCL all-reduce) ----
+ * sums_device: double[n_bins_dense*5] {npath, Σ√P, Σdelay, Σphase, ΣDoppler}  (reduce with SUM)
+ * mins_device: uint64[n_bins_dense]   smallest result-slot index               (reduce with MIN) */
+int rts_bins_device(rts_engine *e, void **sums_device, uint64_t *n_sum_doubles, void **mins_device,
+                    uint64_t *n_mins);
+int rts_finalise_bins(rts_engine *e);
+
+/* ---- aggregation of caller-supplied received rays: the C form of rs::kernel_wrapper
+ *      (aggregation.cuh:18-23, aggregation.cu:103-184).  Same array contract: accumulators
+ *      pre-zeroed, path_match pre-filled (ray_tracer.cpp:1266-1271); on return rx_results[i].power,
+ *      rx_results[i].doppler, delay[i], phase[i], path_match[i] are written (npath/power/doppler
+ *      arrays are also written back, which the reference omits). ---- */
+int rts_aggregate(rts_engine *e, rts_ray_record *rx_results, const int32_t *rx_intersects, uint32_t received,
+                  uint32_t depth_total, double cspeed, double carrier, double *npath, double *power,
+                  double *doppler, double *delay, double *phase, int32_t *path_match);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTS_B200_H */

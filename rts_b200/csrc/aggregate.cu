@@ -1,0 +1,351 @@
+// aggregate.cu — receiver-bin finalisation and the drop-in ray aggregator (sm_100a).
+//
+// Replaces the reference's aggregation.cu:
+//   myKernel1 (aggregation.cu:32-74)   O(R^2 * D) all-pairs path match      -> O(R * D) hash grouping
+//   myKernel2 (aggregation.cu:79-97)   mean voltage squared, mean delay/phase/Doppler
+//   rs::kernel_wrapper (:103-184)      same signature, same array contract (api.cu exports it)
+// and the unique-path step of ray_tracer.cpp:1289-1294 for the fused bins.
+#include "engine.h"
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+#include <algorithm>
+#include <math_constants.h>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+inline unsigned blocks_for(uint64_t n, unsigned bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// ---- record-mode defaults (ray_tracer.cu:227-240, ray_tracer.cpp:854-868) ----
+__global__ void k_fill_records(rts_ray_record *res, unsigned long long n)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    // 144 bytes = 9 x 16: zero everything, then the two non-zero defaults
+    double2 *p = reinterpret_cast<double2 *>(res + i);
+#pragma unroll
+    for (int k = 0; k < 9; k++) p[k] = make_double2(0.0, 0.0);
+    res[i].refrIndex[0] = 1; res[i].refrIndex[1] = 1;
+    res[i].received = -1;
+}
+__global__ void k_fill_i32(int32_t *p, unsigned long long n, int32_t v)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+__global__ void k_fill_f64(double *p, unsigned long long n, double v)
+{
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// ---- fused bins: finalise + compact ----
+// One thread per dense bin.  Direct-ray rule (aggregation.cu:56): a direct ray sums over every
+// ray of its receiver, so the direct bin (key 0 = all columns -1) reports the receiver totals.
+__global__ void k_rx_totals(const double *__restrict__ sums, const unsigned long long *__restrict__ mins,
+                            unsigned long long bins_per_rx, uint32_t n_rx, double *__restrict__ rx_sums,
+                            unsigned long long *__restrict__ rx_mins)
+{
+    // grid.y = receiver; block-stride over its bins; fp64 block reduction then one atomic set per block
+    const uint32_t rx = blockIdx.y;
+    if (rx >= n_rx) return;
+    double acc[5] = {0, 0, 0, 0, 0};
+    unsigned long long mn = ~0ull;
+    for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < bins_per_rx;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long g = rx * bins_per_rx + b;
+        const double n = sums[g * 5];
+        if (n > 0) {
+#pragma unroll
+            for (int k = 0; k < 5; k++) acc[k] += sums[g * 5 + k];
+            mn = min(mn, mins[g]);
+        }
+    }
+    cg::thread_block_tile<32> w = cg::tiled_partition<32>(cg::this_thread_block());
+#pragma unroll
+    for (int k = 0; k < 5; k++) acc[k] = cg::reduce(w, acc[k], cg::plus<double>());
+    mn = cg::reduce(w, mn, cg::less<unsigned long long>());
+    if (w.thread_rank() == 0 && acc[0] > 0) {
+#pragma unroll
+        for (int k = 0; k < 5; k++) atomicAdd(rx_sums + rx * 5 + k, acc[k]);
+        atomicMin(rx_mins + rx, mn);
+    }
+}
+
+__global__ void k_emit_bins(const double *__restrict__ sums, const unsigned long long *__restrict__ mins,
+                            unsigned long long n_bins, unsigned long long bins_per_rx, uint32_t B, uint32_t D,
+                            const double *__restrict__ rx_sums, const unsigned long long *__restrict__ rx_mins,
+                            rts_bin *__restrict__ out, uint32_t *__restrict__ out_count, uint32_t cap)
+{
+    const unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_bins) return;
+    if (!(sums[g * 5] > 0)) return;
+    const uint32_t rx = (uint32_t)(g / bins_per_rx);
+    unsigned long long key = g % bins_per_rx;
+    rts_bin b;
+    b.rx = (int32_t)rx;
+    const bool direct = key == 0;
+    for (uint32_t c = 0; c < RTS_MAX_DEPTH; c++) {
+        b.path[c] = c < D ? (int32_t)(key % B) - 1 : -1;
+        if (c < D) key /= B;
+    }
+    b.direct = direct ? 1 : 0;
+    const double *s = direct ? rx_sums + rx * 5 : sums + g * 5;
+    b.npath = s[0]; b.sum_sqrt_power = s[1]; b.sum_delay = s[2]; b.sum_phase = s[3]; b.sum_doppler = s[4];
+    b.min_slot = direct ? rx_mins[rx] : mins[g];
+    // myKernel2 (aggregation.cu:86-92)
+    b.power = pow(b.sum_sqrt_power / b.npath, 2);
+    b.delay = b.sum_delay / b.npath;
+    b.phase = b.sum_phase / b.npath;
+    b.doppler = b.sum_doppler / b.npath;
+    const uint32_t at = atomicAdd(out_count, 1u);
+    if (at < cap) out[at] = b;
+}
+
+// ---- drop-in aggregator (rs::kernel_wrapper) ----
+// Open-addressing table keyed by (receiver, path row); a slot stores the index of the ray that
+// claimed it and later arrivals compare rows against that representative.
+__device__ __forceinline__ unsigned long long row_hash(const rts_ray_record *res, const int32_t *rows, uint32_t i, uint32_t D)
+{
+    unsigned long long h = 0x9E3779B97F4A7C15ull ^ (unsigned long long)(uint32_t)res[i].received;
+    for (uint32_t k = 0; k < D; k++) {
+        h ^= (unsigned long long)(uint32_t)rows[(size_t)i * D + k] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    }
+    h ^= h >> 31; h *= 0x7fb5d329728ea185ull; h ^= h >> 27;
+    return h;
+}
+__device__ __forceinline__ bool same_group(const rts_ray_record *res, const int32_t *rows, uint32_t a, uint32_t b, uint32_t D)
+{
+    if (res[a].received != res[b].received) return false;
+    for (uint32_t k = 0; k < D; k++)
+        if (rows[(size_t)a * D + k] != rows[(size_t)b * D + k]) return false;
+    return true;
+}
+
+__global__ void k_group(const rts_ray_record *__restrict__ res, const int32_t *__restrict__ rows, uint32_t R, uint32_t D,
+                        uint32_t *table, uint32_t table_mask, uint32_t *__restrict__ slot_of)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    uint32_t s = (uint32_t)row_hash(res, rows, i, D) & table_mask;
+    for (;;) {
+        uint32_t cur = table[s];
+        if (cur == 0xffffffffu) {
+            const uint32_t prev = atomicCAS(table + s, 0xffffffffu, i);
+            cur = prev == 0xffffffffu ? i : prev;
+        }
+        if (cur == i || same_group(res, rows, cur, i, D)) { slot_of[i] = s; return; }
+        s = (s + 1) & table_mask;
+    }
+}
+
+// per-ray terms of myKernel1 (aggregation.cu:59-69) summed per group and per receiver
+__global__ void k_accumulate(const rts_ray_record *__restrict__ res, uint32_t R, const uint32_t *__restrict__ slot_of,
+                             double cspeed, double carrier, double *grp_sums, uint32_t *grp_min, double *rx_sums,
+                             uint32_t *rx_min, uint32_t n_rx_slots)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const double delay = (res[i].rayLength) / cspeed;
+    const double phase = -fmod(delay * 2 * M_PI * carrier, 2 * M_PI);
+    const double amp = sqrt(res[i].power);
+    const double dop = res[i].doppler;
+    const uint32_t s = slot_of[i];
+    const uint32_t rx = (uint32_t)res[i].received;
+    cg::coalesced_group g = cg::coalesced_threads();
+    {
+        auto part = cg::labeled_partition(g, s);
+        const double a0 = cg::reduce(part, 1.0, cg::plus<double>());
+        const double a1 = cg::reduce(part, amp, cg::plus<double>());
+        const double a2 = cg::reduce(part, delay, cg::plus<double>());
+        const double a3 = cg::reduce(part, phase, cg::plus<double>());
+        const double a4 = cg::reduce(part, dop, cg::plus<double>());
+        const uint32_t mn = cg::reduce(part, i, cg::less<uint32_t>());
+        if (part.thread_rank() == 0) {
+            double *b = grp_sums + (size_t)s * 5;
+            atomicAdd(b, a0); atomicAdd(b + 1, a1); atomicAdd(b + 2, a2); atomicAdd(b + 3, a3); atomicAdd(b + 4, a4);
+            atomicMin(grp_min + s, mn);
+        }
+    }
+    if (rx < n_rx_slots) {
+        auto part = cg::labeled_partition(g, rx);
+        const double a0 = cg::reduce(part, 1.0, cg::plus<double>());
+        const double a1 = cg::reduce(part, amp, cg::plus<double>());
+        const double a2 = cg::reduce(part, delay, cg::plus<double>());
+        const double a3 = cg::reduce(part, phase, cg::plus<double>());
+        const double a4 = cg::reduce(part, dop, cg::plus<double>());
+        const uint32_t mn = cg::reduce(part, i, cg::less<uint32_t>());
+        if (part.thread_rank() == 0) {
+            double *b = rx_sums + (size_t)rx * 5;
+            atomicAdd(b, a0); atomicAdd(b + 1, a1); atomicAdd(b + 2, a2); atomicAdd(b + 3, a3); atomicAdd(b + 4, a4);
+            atomicMin(rx_min + rx, mn);
+        }
+    }
+}
+
+// write-out in the reference's array contract + myKernel2
+__global__ void k_scatter(rts_ray_record *res, uint32_t R, const uint32_t *__restrict__ slot_of,
+                          const double *__restrict__ grp_sums, const uint32_t *__restrict__ grp_min,
+                          const double *__restrict__ rx_sums, const uint32_t *__restrict__ rx_min, uint32_t n_rx_slots,
+                          double *npath, double *power, double *doppler, double *delay, double *phase, int32_t *pathMatch)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const bool direct = (res[i].reflDepth == 0) && (res[i].refrDepth == 0);
+    const uint32_t rx = (uint32_t)res[i].received;
+    const double *s = (direct && rx < n_rx_slots) ? rx_sums + (size_t)rx * 5 : grp_sums + (size_t)slot_of[i] * 5;
+    const uint32_t mn = (direct && rx < n_rx_slots) ? rx_min[rx] : grp_min[slot_of[i]];
+    npath[i] += s[0];
+    power[i] += s[1];
+    delay[i] += s[2];
+    phase[i] += s[3];
+    doppler[i] += s[4];
+    if ((int32_t)mn < pathMatch[i]) pathMatch[i] = (int32_t)mn;
+    if (npath[i] > 0) {
+        res[i].power = pow(power[i] / npath[i], 2);
+        delay[i] /= npath[i];
+        phase[i] /= npath[i];
+        res[i].doppler = doppler[i] / npath[i];
+    }
+}
+
+} // namespace
+
+int agg_fill_records(rts_engine *e, uint64_t ray_total, uint32_t D, uint32_t W)
+{
+    const unsigned bs = 256;
+    k_fill_records<<<blocks_for(ray_total, bs), bs, 0, e->stream>>>(e->d_results, ray_total);
+    if (D) {
+        k_fill_i32<<<blocks_for(ray_total * D, bs), bs, 0, e->stream>>>(e->d_targ_intersect, ray_total * D, -1);
+        k_fill_f64<<<blocks_for(ray_total * D * 2, bs), bs, 0, e->stream>>>(e->d_rcs_angle, ray_total * D * 2, -1000000.0);
+    }
+    k_fill_i32<<<blocks_for(ray_total * W, bs), bs, 0, e->stream>>>(e->d_tri_path, ray_total * W, -1);
+    RTS_CUDA(cudaGetLastError());
+    return RTS_OK;
+}
+
+int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
+{
+    const uint64_t nb = e->n_bins_dense;
+    const uint32_t n_rx = e->last_nrx, B = e->last_B, D = e->last_D;
+    if (!nb || !n_rx) { if (n) *n = 0; return RTS_OK; }
+    const uint64_t per_rx = nb / n_rx;
+    // receiver totals
+    double *rx_sums = nullptr;
+    unsigned long long *rx_mins = nullptr;
+    RTS_CUDA(cudaMalloc(&rx_sums, sizeof(double) * 5 * n_rx));
+    RTS_CUDA(cudaMalloc(&rx_mins, sizeof(unsigned long long) * n_rx));
+    RTS_CUDA(cudaMemsetAsync(rx_sums, 0, sizeof(double) * 5 * n_rx, e->stream));
+    RTS_CUDA(cudaMemsetAsync(rx_mins, 0xff, sizeof(unsigned long long) * n_rx, e->stream));
+    dim3 grid((unsigned)std::min<uint64_t>(64, (per_rx + 255) / 256), n_rx);
+    k_rx_totals<<<grid, 256, 0, e->stream>>>(e->d_bin_sums, e->d_bin_mins, per_rx, n_rx, rx_sums, rx_mins);
+    // compact non-empty bins
+    const uint64_t want = std::max<uint64_t>(cap, 1);
+    if (e->bins_out_alloc < want) {
+        if (e->d_bins_out) cudaFree(e->d_bins_out);
+        e->d_bins_out = nullptr;
+        RTS_CUDA(cudaMalloc(&e->d_bins_out, sizeof(rts_bin) * want));
+        e->bins_out_alloc = want;
+    }
+    if (!e->d_bins_out_count) RTS_CUDA(cudaMalloc(&e->d_bins_out_count, sizeof(uint32_t)));
+    RTS_CUDA(cudaMemsetAsync(e->d_bins_out_count, 0, sizeof(uint32_t), e->stream));
+    k_emit_bins<<<blocks_for(nb, 256), 256, 0, e->stream>>>(e->d_bin_sums, e->d_bin_mins, nb, per_rx, B, D, rx_sums, rx_mins,
+                                                           e->d_bins_out, e->d_bins_out_count, cap);
+    RTS_CUDA(cudaGetLastError());
+    uint32_t count = 0;
+    RTS_CUDA(cudaMemcpyAsync(&count, e->d_bins_out_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    RTS_CUDA(cudaStreamSynchronize(e->stream));
+    const uint32_t got = std::min(count, cap);
+    if (out && got) {
+        RTS_CUDA(cudaMemcpy(out, e->d_bins_out, sizeof(rts_bin) * got, cudaMemcpyDeviceToHost));
+        std::sort(out, out + got, [](const rts_bin &a, const rts_bin &b) {
+            if (a.rx != b.rx) return a.rx < b.rx;
+            for (uint32_t c = 0; c < RTS_MAX_DEPTH; c++)
+                if (a.path[c] != b.path[c]) return a.path[c] < b.path[c];
+            return false;
+        });
+    }
+    cudaFree(rx_sums);
+    cudaFree(rx_mins);
+    if (n) *n = count;
+    e->stats.n_bins = count;
+    return RTS_OK;
+}
+
+int agg_kernel_wrapper(rts_engine *e, rts_ray_record *rx_results, const int32_t *rx_intersects, uint32_t R, uint32_t D,
+                       double cspeed, double carrier, double *npath, double *power, double *doppler, double *delay,
+                       double *phase, int32_t *path_match)
+{
+    if (R == 0) return RTS_OK;
+    cudaStream_t st = e->stream;
+    uint32_t table_size = 64;
+    while (table_size < 2ull * R) table_size <<= 1;
+    // receivers are small non-negative ints; size the per-receiver table from the data
+    int32_t max_rx = 0;
+    for (uint32_t i = 0; i < R; i++) max_rx = std::max(max_rx, rx_results[i].received);
+    const uint32_t n_rx_slots = (uint32_t)max_rx + 1;
+
+    rts_ray_record *d_res = nullptr;
+    int32_t *d_rows = nullptr, *d_pm = nullptr;
+    uint32_t *d_table = nullptr, *d_slot = nullptr, *d_gmin = nullptr, *d_rmin = nullptr;
+    double *d_gs = nullptr, *d_rs = nullptr, *d_acc = nullptr; // d_acc: npath,power,doppler,delay,phase [5*R]
+    int rc = RTS_OK;
+#define AGG_CUDA(call)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t _e = (call);                                                                                \
+        if (_e != cudaSuccess) {                                                                                \
+            rc = rts_fail(RTS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            goto done;                                                                                          \
+        }                                                                                                       \
+    } while (0)
+    AGG_CUDA(cudaMalloc(&d_res, sizeof(rts_ray_record) * (size_t)R));
+    AGG_CUDA(cudaMalloc(&d_rows, sizeof(int32_t) * std::max<size_t>(1, (size_t)R * D)));
+    AGG_CUDA(cudaMalloc(&d_pm, sizeof(int32_t) * (size_t)R));
+    AGG_CUDA(cudaMalloc(&d_table, sizeof(uint32_t) * (size_t)table_size));
+    AGG_CUDA(cudaMalloc(&d_slot, sizeof(uint32_t) * (size_t)R));
+    AGG_CUDA(cudaMalloc(&d_gmin, sizeof(uint32_t) * (size_t)table_size));
+    AGG_CUDA(cudaMalloc(&d_rmin, sizeof(uint32_t) * (size_t)n_rx_slots));
+    AGG_CUDA(cudaMalloc(&d_gs, sizeof(double) * 5 * (size_t)table_size));
+    AGG_CUDA(cudaMalloc(&d_rs, sizeof(double) * 5 * (size_t)n_rx_slots));
+    AGG_CUDA(cudaMalloc(&d_acc, sizeof(double) * 5 * (size_t)R));
+    AGG_CUDA(cudaMemcpyAsync(d_res, rx_results, sizeof(rts_ray_record) * (size_t)R, cudaMemcpyHostToDevice, st));
+    if (D) AGG_CUDA(cudaMemcpyAsync(d_rows, rx_intersects, sizeof(int32_t) * (size_t)R * D, cudaMemcpyHostToDevice, st));
+    AGG_CUDA(cudaMemcpyAsync(d_pm, path_match, sizeof(int32_t) * (size_t)R, cudaMemcpyHostToDevice, st));
+    AGG_CUDA(cudaMemcpyAsync(d_acc + 0 * (size_t)R, npath, sizeof(double) * R, cudaMemcpyHostToDevice, st));
+    AGG_CUDA(cudaMemcpyAsync(d_acc + 1 * (size_t)R, power, sizeof(double) * R, cudaMemcpyHostToDevice, st));
+    AGG_CUDA(cudaMemcpyAsync(d_acc + 2 * (size_t)R, doppler, sizeof(double) * R, cudaMemcpyHostToDevice, st));
+    AGG_CUDA(cudaMemcpyAsync(d_acc + 3 * (size_t)R, delay, sizeof(double) * R, cudaMemcpyHostToDevice, st));
+    AGG_CUDA(cudaMemcpyAsync(d_acc + 4 * (size_t)R, phase, sizeof(double) * R, cudaMemcpyHostToDevice, st));
+    AGG_CUDA(cudaMemsetAsync(d_table, 0xff, sizeof(uint32_t) * (size_t)table_size, st));
+    AGG_CUDA(cudaMemsetAsync(d_gmin, 0xff, sizeof(uint32_t) * (size_t)table_size, st));
+    AGG_CUDA(cudaMemsetAsync(d_rmin, 0xff, sizeof(uint32_t) * (size_t)n_rx_slots, st));
+    AGG_CUDA(cudaMemsetAsync(d_gs, 0, sizeof(double) * 5 * (size_t)table_size, st));
+    AGG_CUDA(cudaMemsetAsync(d_rs, 0, sizeof(double) * 5 * (size_t)n_rx_slots, st));
+    {
+        const unsigned bs = 256, gb = blocks_for(R, bs);
+        k_group<<<gb, bs, 0, st>>>(d_res, d_rows, R, D, d_table, table_size - 1, d_slot);
+        k_accumulate<<<gb, bs, 0, st>>>(d_res, R, d_slot, cspeed, carrier, d_gs, d_gmin, d_rs, d_rmin, n_rx_slots);
+        k_scatter<<<gb, bs, 0, st>>>(d_res, R, d_slot, d_gs, d_gmin, d_rs, d_rmin, n_rx_slots, d_acc + 0 * (size_t)R,
+                                     d_acc + 1 * (size_t)R, d_acc + 2 * (size_t)R, d_acc + 3 * (size_t)R,
+                                     d_acc + 4 * (size_t)R, d_pm);
+        AGG_CUDA(cudaGetLastError());
+    }
+    AGG_CUDA(cudaMemcpyAsync(rx_results, d_res, sizeof(rts_ray_record) * (size_t)R, cudaMemcpyDeviceToHost, st));
+    AGG_CUDA(cudaMemcpyAsync(npath, d_acc + 0 * (size_t)R, sizeof(double) * R, cudaMemcpyDeviceToHost, st));
+    AGG_CUDA(cudaMemcpyAsync(power, d_acc + 1 * (size_t)R, sizeof(double) * R, cudaMemcpyDeviceToHost, st));
+    AGG_CUDA(cudaMemcpyAsync(doppler, d_acc + 2 * (size_t)R, sizeof(double) * R, cudaMemcpyDeviceToHost, st));
+    AGG_CUDA(cudaMemcpyAsync(delay, d_acc + 3 * (size_t)R, sizeof(double) * R, cudaMemcpyDeviceToHost, st));
+    AGG_CUDA(cudaMemcpyAsync(phase, d_acc + 4 * (size_t)R, sizeof(double) * R, cudaMemcpyDeviceToHost, st));
+    AGG_CUDA(cudaMemcpyAsync(path_match, d_pm, sizeof(int32_t) * (size_t)R, cudaMemcpyDeviceToHost, st));
+    AGG_CUDA(cudaStreamSynchronize(st));
+done:
+#undef AGG_CUDA
+    cudaFree(d_res); cudaFree(d_rows); cudaFree(d_pm); cudaFree(d_table); cudaFree(d_slot); cudaFree(d_gmin);
+    cudaFree(d_rmin); cudaFree(d_gs); cudaFree(d_rs); cudaFree(d_acc);
+    return rc;
+}

@@ -1,0 +1,558 @@
+// api.cu — the C-ABI of librts_b200.so (include/rts_b200.h) and the per-pulse orchestration.
+//
+// Host-side counterpart of the reference's ray_tracer.cpp pulse loop (ray_tracer.cpp:843-1333),
+// minus everything that talks to SOARS or OptiX: scene upload, per-pulse pose update + BVH refit,
+// the wavefront launch sequence, result hand-off.  Also exports the C++ symbol
+// rs::kernel_wrapper with the reference's exact signature (aggregation.cuh:18-23).
+#include "engine.h"
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+
+static thread_local char g_err[512] = "";
+
+int rts_fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *rts_last_error(void) { return g_err; }
+extern "C" const char *rts_version(void) { return "rts_b200 0.1 (sm_100a; wavefront LBVH tracer; no CPU fallback)"; }
+
+extern "C" int rts_abi_sizes(uint32_t s[8])
+{
+    if (!s) return rts_fail(RTS_ERR_ARG, "sizes is NULL");
+    s[0] = sizeof(rts_ray_record); s[1] = sizeof(rts_target_mesh); s[2] = sizeof(rts_rx_sphere); s[3] = sizeof(rts_rx_desc);
+    s[4] = sizeof(rts_pulse); s[5] = sizeof(rts_bin); s[6] = sizeof(rts_stats); s[7] = sizeof(rts_pose);
+    return RTS_OK;
+}
+
+static_assert(sizeof(rts_ray_record) == 144, "PerRayData contract: 144 bytes");
+static_assert(offsetof(rts_ray_record, refrIndex) == 16 && offsetof(rts_ray_record, reflDepth) == 32 &&
+              offsetof(rts_ray_record, rayDirection) == 48 && offsetof(rts_ray_record, firstHitPoint) == 72 &&
+              offsetof(rts_ray_record, prevHitPoint) == 96 && offsetof(rts_ray_record, power) == 120 &&
+              offsetof(rts_ray_record, doppler) == 128 && offsetof(rts_ray_record, received) == 136 &&
+              offsetof(rts_ray_record, end) == 140, "PerRayData contract: offsets");
+
+extern "C" int rts_result_sizes(const rts_pulse *p, rts_sizes *out)
+{
+    if (!p || !out) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    const uint32_t rMax = p->max_refr > 0 ? 2u : 0u;               // ray_tracer.cpp:604-605
+    out->rays = (uint64_t)p->nx * p->ny * p->nz;
+    out->slots = rMax == 2 ? 1 + (p->max_refl + 1) + 1 : 1;         // ray_tracer.cpp:608-613
+    out->ray_total = out->rays * out->slots;                        // ray_tracer.cpp:626
+    out->depth_total = p->max_refl + rMax;                          // ray_tracer.cpp:655
+    out->tri_cols = p->max_refl + 3;
+    out->_pad = 0;
+    return RTS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int rts_create(int device, rts_engine **out)
+{
+    if (!out) return rts_fail(RTS_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+        return rts_fail(RTS_ERR_NO_DEVICE, "no CUDA device available (%s); librts_b200 has no CPU fallback",
+                        err == cudaSuccess ? "device count 0" : cudaGetErrorString(err));
+    if (device < 0 || device >= count) return rts_fail(RTS_ERR_ARG, "device %d out of range (0..%d)", device, count - 1);
+    cudaDeviceProp prop;
+    RTS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return rts_fail(RTS_ERR_NO_DEVICE, "device %d is sm_%d%d; librts_b200 is built for sm_100a only", device, prop.major,
+                        prop.minor);
+    RTS_CUDA(cudaSetDevice(device));
+    rts_engine *e = new rts_engine();
+    e->device = device;
+    e->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete e;
+        return rts_fail(RTS_ERR_CUDA, "cudaStreamCreate failed");
+    }
+    e->stream = e->own_stream;
+    for (auto &ev : e->ev) cudaEventCreate(&ev);
+    cudaMalloc(&e->d_counts, sizeof(unsigned long long) * 64);
+    cudaMalloc(&e->d_counters, sizeof(Counters));
+    cudaMalloc(&e->d_rx, sizeof(RxDev) * RTS_MAX_RX);
+    *out = e;
+    return RTS_OK;
+}
+
+static void free_scene(rts_engine *e)
+{
+    void **ptrs[] = {(void **)&e->d_base_verts, (void **)&e->d_base_normals, (void **)&e->d_world_verts,
+                     (void **)&e->d_world_normals, (void **)&e->d_tris, (void **)&e->d_tri_target, (void **)&e->d_vert_target,
+                     (void **)&e->d_norm_target, (void **)&e->d_t_vert_off, (void **)&e->d_t_norm_off, (void **)&e->d_t_tri_off,
+                     (void **)&e->d_t_per_face, (void **)&e->d_t_refl, (void **)&e->d_t_refr, (void **)&e->d_t_vel,
+                     (void **)&e->d_poses};
+    for (void **p : ptrs) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    bvh_free(e);
+    e->scene_ready = false;
+}
+
+extern "C" void rts_destroy(rts_engine *e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    free_scene(e);
+    for (int k = 0; k < 2; k++) if (e->q_slab[k]) cudaFree(e->q_slab[k]);
+    void *ptrs[] = {e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count,
+                    e->d_results, e->d_targ_intersect, e->d_tri_path, e->d_rcs_angle};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+extern "C" int rts_set_stream(rts_engine *e, void *cuda_stream)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    cudaStreamSynchronize(e->stream);
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return RTS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class T> static int upload(T **dst, const std::vector<T> &src)
+{
+    if (*dst) { cudaFree(*dst); *dst = nullptr; }
+    RTS_CUDA(cudaMalloc((void **)dst, sizeof(T) * std::max<size_t>(1, src.size())));
+    if (!src.empty()) RTS_CUDA(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+    return RTS_OK;
+}
+
+extern "C" int rts_scene_set_targets(rts_engine *e, const rts_target_mesh *targets, uint32_t n_targets)
+{
+    if (!e || (!targets && n_targets)) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    RTS_CUDA(cudaSetDevice(e->device));
+    RTS_CUDA(cudaStreamSynchronize(e->stream));
+    free_scene(e);
+    e->n_targets = n_targets;
+    e->tri_off.assign(n_targets, 0); e->vert_off.assign(n_targets, 0); e->norm_off.assign(n_targets, 0);
+    e->t_nverts.assign(n_targets, 0); e->t_ntris.assign(n_targets, 0); e->t_nnormals.assign(n_targets, 0);
+    uint64_t T = 0, V = 0, N = 0;
+    for (uint32_t k = 0; k < n_targets; k++) {
+        const rts_target_mesh &m = targets[k];
+        if ((m.n_verts && !m.verts) || (m.n_tris && !m.tris) || (m.n_normals && !m.normals))
+            return rts_fail(RTS_ERR_ARG, "target %u has NULL arrays", k);
+        e->tri_off[k] = (uint32_t)T; e->vert_off[k] = (uint32_t)V; e->norm_off[k] = (uint32_t)N;
+        e->t_nverts[k] = m.n_verts; e->t_ntris[k] = m.n_tris; e->t_nnormals[k] = m.n_normals;
+        T += m.n_tris; V += m.n_verts; N += m.n_normals;
+    }
+    if (T >= (1ull << 28)) return rts_fail(RTS_ERR_CAPACITY, "%llu triangles exceed the 2^28 leaf-reference limit", (unsigned long long)T);
+    e->n_tris = (uint32_t)T; e->n_verts = (uint32_t)V; e->n_normals = (uint32_t)N;
+
+    std::vector<double> verts(3 * V), normals(3 * N), refl(n_targets), refr(n_targets), vel(3 * (size_t)n_targets, 0.0);
+    std::vector<uint32_t> tris(3 * T), tri_target(T), vert_target(V), norm_target(N), per_face(n_targets);
+    std::vector<rts_pose> poses(n_targets);
+    for (uint32_t k = 0; k < n_targets; k++) {
+        const rts_target_mesh &m = targets[k];
+        for (uint32_t t = 0; t < m.n_tris; t++)
+            for (int c = 0; c < 3; c++) {
+                const uint32_t vi = m.tris[3 * (size_t)t + c];
+                if (vi >= m.n_verts) return rts_fail(RTS_ERR_ARG, "target %u triangle %u references vertex %u of %u", k, t, vi, m.n_verts);
+                tris[3 * ((size_t)e->tri_off[k] + t) + c] = vi;
+            }
+        if (m.n_verts) memcpy(&verts[3 * (size_t)e->vert_off[k]], m.verts, sizeof(double) * 3 * m.n_verts);
+        if (m.n_normals) memcpy(&normals[3 * (size_t)e->norm_off[k]], m.normals, sizeof(double) * 3 * m.n_normals);
+        std::fill(tri_target.begin() + e->tri_off[k], tri_target.begin() + e->tri_off[k] + m.n_tris, k);
+        std::fill(vert_target.begin() + e->vert_off[k], vert_target.begin() + e->vert_off[k] + m.n_verts, k);
+        std::fill(norm_target.begin() + e->norm_off[k], norm_target.begin() + e->norm_off[k] + m.n_normals, k);
+        per_face[k] = m.n_normals > m.n_verts ? 1u : 0u;   // triangle_mesh.cu:180
+        refl[k] = m.refl_coeff; refr[k] = m.refr_index;
+        memset(&poses[k], 0, sizeof(rts_pose));
+        poses[k].R[0] = poses[k].R[4] = poses[k].R[8] = 1.0;
+    }
+    int rc;
+    if ((rc = upload(&e->d_base_verts, verts))) return rc;
+    if ((rc = upload(&e->d_base_normals, normals))) return rc;
+    if ((rc = upload(&e->d_world_verts, verts))) return rc;
+    if ((rc = upload(&e->d_world_normals, normals))) return rc;
+    if ((rc = upload(&e->d_tris, tris))) return rc;
+    if ((rc = upload(&e->d_tri_target, tri_target))) return rc;
+    if ((rc = upload(&e->d_vert_target, vert_target))) return rc;
+    if ((rc = upload(&e->d_norm_target, norm_target))) return rc;
+    if ((rc = upload(&e->d_t_vert_off, e->vert_off))) return rc;
+    if ((rc = upload(&e->d_t_norm_off, e->norm_off))) return rc;
+    if ((rc = upload(&e->d_t_tri_off, e->tri_off))) return rc;
+    if ((rc = upload(&e->d_t_per_face, per_face))) return rc;
+    if ((rc = upload(&e->d_t_refl, refl))) return rc;
+    if ((rc = upload(&e->d_t_refr, refr))) return rc;
+    if ((rc = upload(&e->d_t_vel, vel))) return rc;
+    if ((rc = upload(&e->d_poses, poses))) return rc;
+    if ((rc = bvh_alloc(e))) return rc;
+    if ((rc = bvh_build(e))) return rc;
+    e->scene_ready = true;
+    return RTS_OK;
+}
+
+extern "C" int rts_scene_set_poses(rts_engine *e, const rts_pose *poses, uint32_t n_targets)
+{
+    if (!e || !poses) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    if (!e->scene_ready) return rts_fail(RTS_ERR_STATE, "no scene committed");
+    if (n_targets != e->n_targets) return rts_fail(RTS_ERR_ARG, "%u poses for %u targets", n_targets, e->n_targets);
+    RTS_CUDA(cudaSetDevice(e->device));
+    cudaEventRecord(e->ev[4], e->stream);
+    RTS_CUDA(cudaMemcpyAsync(e->d_poses, poses, sizeof(rts_pose) * n_targets, cudaMemcpyHostToDevice, e->stream));
+    int rc = bvh_refit(e);
+    if (rc) return rc;
+    cudaEventRecord(e->ev[5], e->stream);
+    // the pose array is caller-owned pageable memory: make the copy complete before returning
+    RTS_CUDA(cudaStreamSynchronize(e->stream));
+    cudaEventElapsedTime(&e->bvh_info.ms_refit, e->ev[4], e->ev[5]);
+    return RTS_OK;
+}
+
+extern "C" int rts_scene_rebuild(rts_engine *e)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    if (!e->scene_ready) return rts_fail(RTS_ERR_STATE, "no scene committed");
+    RTS_CUDA(cudaSetDevice(e->device));
+    return bvh_build(e);
+}
+
+extern "C" int rts_scene_bvh_info(rts_engine *e, rts_bvh_info *out)
+{
+    if (!e || !out) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    *out = e->bvh_info;
+    return RTS_OK;
+}
+
+extern "C" int rts_scene_get_world_vertices(rts_engine *e, uint32_t target, double *out)
+{
+    if (!e || !out) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    if (!e->scene_ready || target >= e->n_targets) return rts_fail(RTS_ERR_ARG, "bad target %u", target);
+    RTS_CUDA(cudaStreamSynchronize(e->stream));
+    RTS_CUDA(cudaMemcpy(out, e->d_world_verts + 3 * (size_t)e->vert_off[target], sizeof(double) * 3 * e->t_nverts[target],
+                        cudaMemcpyDeviceToHost));
+    return RTS_OK;
+}
+
+extern "C" int rts_scene_get_tri_bounds(rts_engine *e, float *out6)
+{
+    if (!e || !out6) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    if (!e->scene_ready) return rts_fail(RTS_ERR_STATE, "no scene committed");
+    RTS_CUDA(cudaStreamSynchronize(e->stream));
+    RTS_CUDA(cudaMemcpy(out6, e->d_tri_box, sizeof(float) * 6 * (size_t)e->n_tris, cudaMemcpyDeviceToHost));
+    return RTS_OK;
+}
+
+extern "C" int rts_scene_check_bvh(rts_engine *e, uint64_t *violations)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    if (!e->scene_ready) return rts_fail(RTS_ERR_STATE, "no scene committed");
+    return bvh_check(e, violations);
+}
+
+// ---------------------------------------------------------------------------------------------
+static void sph_to_cart(double azi, double ele, double out[3]) // ray_tracer.cu:132-139
+{
+    out[0] = cos(azi) * cos(ele);
+    out[1] = sin(azi) * cos(ele);
+    out[2] = sin(ele);
+}
+
+// Launch-invariant part of ray_generation (ray_tracer.cu:155-196), evaluated once per pulse on the
+// host in the source's operation order; the kernels then use only +,-,*,/ and sqrt per ray.
+static void fill_launch_constants(WaveParams &P, const rts_pulse *p)
+{
+    const double az = p->tx_dir[0], el = p->tx_dir[1];
+    double beamEnd[3];
+    sph_to_cart(-p->tx_span[0] / 2, -p->tx_span[1] / 2, P.beamStart);
+    sph_to_cart(p->tx_span[0] / 2, p->tx_span[1] / 2, beamEnd);
+    P.slope[0] = p->nx > 1 ? (((beamEnd[0] * (1 + p->tx_span[2])) - P.beamStart[0]) / (p->nx - 1)) : 0.0;
+    P.slope[1] = p->ny > 1 ? ((beamEnd[1] - P.beamStart[1]) / (p->ny - 1)) : 0.0;
+    P.slope[2] = p->nz > 1 ? ((beamEnd[2] - P.beamStart[2]) / (p->nz - 1)) : 0.0;
+    const double Rot[9] = {cos(az), -sin(az), 0, sin(az), cos(az), 0, 0, 0, 1};
+    memcpy(P.Rot, Rot, sizeof(Rot));
+    double rx = 0, ry = 0, rz = 0;
+    rx += Rot[1]; ry += Rot[4]; rz += Rot[7];
+    const double norm = sqrt(rx * rx + ry * ry + rz * rz);
+    const double ox = rx / norm, oy = ry / norm, oz = rz / norm;
+    const double c = cos(el), s = sin(el);
+    const double Rot1[9] = {c + ox * ox * (1 - c), ox * oy * (1 - c) + oz * s, ox * oz * (1 - c) - oy * s,
+                            oy * ox * (1 - c) - oz * s, c + oy * oy * (1 - c), oy * oz * (1 - c) + ox * s,
+                            oz * ox * (1 - c) + oy * s, oz * oy * (1 - c) - ox * s, c + oz * oz * (1 - c)};
+    memcpy(P.Rot1, Rot1, sizeof(Rot1));
+    sph_to_cart(az, el, P.boresight);
+    P.single_ray = (p->nx == 1 && p->ny == 1 && p->nz == 1) ? 1 : 0;
+}
+
+static int ensure_records(rts_engine *e, const rts_sizes &sz)
+{
+    if (e->rec_alloc_rays >= sz.ray_total && e->rec_alloc_D >= sz.depth_total && e->rec_alloc_W >= sz.tri_cols) return RTS_OK;
+    void **ptrs[] = {(void **)&e->d_results, (void **)&e->d_targ_intersect, (void **)&e->d_rcs_angle, (void **)&e->d_tri_path};
+    for (void **p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+    e->rec_alloc_rays = 0;
+    const size_t n = sz.ray_total, D = std::max<uint32_t>(1, sz.depth_total), W = sz.tri_cols;
+    RTS_CUDA(cudaMalloc(&e->d_results, sizeof(rts_ray_record) * n));
+    RTS_CUDA(cudaMalloc(&e->d_targ_intersect, sizeof(int32_t) * n * D));
+    RTS_CUDA(cudaMalloc(&e->d_rcs_angle, sizeof(double) * 2 * n * D));
+    RTS_CUDA(cudaMalloc(&e->d_tri_path, sizeof(int32_t) * n * W));
+    e->rec_alloc_rays = n; e->rec_alloc_D = sz.depth_total; e->rec_alloc_W = W;
+    return RTS_OK;
+}
+
+extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags)
+{
+    if (!e || !p) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    if (!e->scene_ready) return rts_fail(RTS_ERR_STATE, "no scene committed (rts_scene_set_targets)");
+    if (!(flags & (RTS_OUT_BINS | RTS_OUT_RECORDS))) return rts_fail(RTS_ERR_ARG, "flags must request RTS_OUT_BINS and/or RTS_OUT_RECORDS");
+    if (p->n_targets != e->n_targets) return rts_fail(RTS_ERR_ARG, "pulse carries %u target velocities, scene has %u targets", p->n_targets, e->n_targets);
+    if (p->n_rx > RTS_MAX_RX) return rts_fail(RTS_ERR_CAPACITY, "%u receivers > %u", p->n_rx, RTS_MAX_RX);
+    if (p->n_rx && !p->rx) return rts_fail(RTS_ERR_ARG, "rx is NULL");
+    if (p->n_targets && !p->targ_vel) return rts_fail(RTS_ERR_ARG, "targ_vel is NULL");
+    if (!p->nx || !p->ny || !p->nz) return rts_fail(RTS_ERR_ARG, "empty launch grid");
+    rts_sizes sz;
+    rts_result_sizes(p, &sz);
+    if (sz.depth_total > RTS_MAX_DEPTH) return rts_fail(RTS_ERR_CAPACITY, "depth_total %u > %u", sz.depth_total, RTS_MAX_DEPTH);
+    if (sz.rays >= (1ull << 32)) return rts_fail(RTS_ERR_CAPACITY, "%llu primary rays per launch exceed 2^32", (unsigned long long)sz.rays);
+    if (p->max_refl + 3 > 15) return rts_fail(RTS_ERR_CAPACITY, "max_refl %u too deep for the ray-state encoding", p->max_refl);
+    RTS_CUDA(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+
+    const uint32_t rMax = p->max_refr > 0 ? 2u : 0u;
+    const uint64_t stride = p->ray_stride ? p->ray_stride : 1;
+    uint64_t begin = std::min<uint64_t>(p->ray_begin, sz.rays);
+    uint64_t end = p->ray_count ? std::min<uint64_t>(sz.rays, p->ray_begin + p->ray_count) : sz.rays;
+    if (end < begin) end = begin;
+    const uint64_t n_primary_total = (end - begin + stride - 1) / stride;
+
+    WaveParams P;
+    memset(&P, 0, sizeof(P));
+    P.nodes = e->d_nodes; P.trirec = e->d_trirec; P.root_ref = e->root_ref; P.n_tris = e->n_tris;
+    P.world_normals = e->d_world_normals; P.tris = e->d_tris;
+    P.t_norm_off = e->d_t_norm_off; P.t_tri_off = e->d_t_tri_off; P.t_per_face = e->d_t_per_face;
+    P.t_refl = e->d_t_refl; P.t_refr = e->d_t_refr; P.t_vel = e->d_t_vel;
+    P.nx = p->nx; P.ny = p->ny; P.nz = p->nz; P.R3 = sz.rays;
+    P.dMax = p->max_refl + 1;                                     // ray_tracer.cpp:776
+    P.rMax = rMax; P.D = sz.depth_total; P.M = sz.slots; P.W = sz.tri_cols;
+    P.interpolate = p->interpolate_smooth ? 1 : 0;
+    memcpy(P.origin, p->tx_origin, sizeof(P.origin));
+    fill_launch_constants(P, p);
+    P.n_rx = p->n_rx; P.rx = e->d_rx;
+    P.cspeed = p->cspeed; P.carrier = p->carrier;
+    {
+        const double Wl = p->cspeed / p->carrier;                 // ray_tracer.cpp:815
+        const double Gt = 1.0, Gr = 1.0;
+        P.wl2gain = (Wl * Wl * Gt * Gr);                          // ray_tracer.cpp:1247
+    }
+    // path key: digits base B = n_targets + 1 (digit 0 <=> -1)
+    const uint64_t B = (uint64_t)e->n_targets + 1;
+    P.powB[0] = 1;
+    bool key_overflow = false;
+    for (uint32_t c = 1; c <= RTS_MAX_DEPTH; c++) {
+        if (c <= sz.depth_total && P.powB[c - 1] > (~0ull) / B / 2) key_overflow = true;
+        P.powB[c] = P.powB[c - 1] * B;
+    }
+    if (key_overflow) return rts_fail(RTS_ERR_CAPACITY, "path key (targets+1)^depth does not fit 63 bits");
+    P.key_all = 0;
+    for (uint32_t c = 0; c < sz.depth_total; c++) P.key_all += P.powB[c];
+    P.flags = flags;
+
+    // receivers, target velocities
+    {
+        RxDev rx[RTS_MAX_RX];
+        for (uint32_t j = 0; j < p->n_rx; j++) {
+            rx[j].cx = p->rx[j].centre[0]; rx[j].cy = p->rx[j].centre[1]; rx[j].cz = p->rx[j].centre[2];
+            rx[j].radius = p->rx[j].radius;
+            rx[j].min_theta = p->rx[j].min_theta; rx[j].max_theta = p->rx[j].max_theta;
+            rx[j].min_phi = p->rx[j].min_phi; rx[j].max_phi = p->rx[j].max_phi;
+        }
+        if (p->n_rx) RTS_CUDA(cudaMemcpyAsync(e->d_rx, rx, sizeof(RxDev) * p->n_rx, cudaMemcpyHostToDevice, st));
+        if (p->n_targets)
+            RTS_CUDA(cudaMemcpyAsync(e->d_t_vel, p->targ_vel, sizeof(double) * 3 * p->n_targets, cudaMemcpyHostToDevice, st));
+        RTS_CUDA(cudaStreamSynchronize(st)); // rx[] is a stack array, targ_vel is caller-owned
+    }
+
+    // bins
+    if (flags & RTS_OUT_BINS) {
+        const uint64_t per_rx = P.powB[sz.depth_total];
+        const uint64_t nb = per_rx * std::max<uint32_t>(1, p->n_rx);
+        if (per_rx > (1ull << 24) || nb > (1ull << 24))
+            return rts_fail(RTS_ERR_CAPACITY, "dense bin table (%u targets+1)^%u x %u receivers = %llu bins exceeds 2^24",
+                            e->n_targets, sz.depth_total, p->n_rx, (unsigned long long)nb);
+        if (e->bins_alloc < nb) {
+            if (e->d_bin_sums) cudaFree(e->d_bin_sums);
+            if (e->d_bin_mins) cudaFree(e->d_bin_mins);
+            e->d_bin_sums = nullptr; e->d_bin_mins = nullptr; e->bins_alloc = 0;
+            RTS_CUDA(cudaMalloc(&e->d_bin_sums, sizeof(double) * 5 * nb));
+            RTS_CUDA(cudaMalloc(&e->d_bin_mins, sizeof(unsigned long long) * nb));
+            e->bins_alloc = nb;
+        }
+        e->n_bins_dense = p->n_rx ? nb : 0;
+        RTS_CUDA(cudaMemsetAsync(e->d_bin_sums, 0, sizeof(double) * 5 * nb, st));
+        RTS_CUDA(cudaMemsetAsync(e->d_bin_mins, 0xff, sizeof(unsigned long long) * nb, st));
+        P.bin_sums = e->d_bin_sums; P.bin_mins = e->d_bin_mins; P.n_bins = e->n_bins_dense;
+    } else {
+        e->n_bins_dense = 0;
+    }
+
+    // records
+    const bool records = (flags & RTS_OUT_RECORDS) != 0;
+    if (records) {
+        int rc = ensure_records(e, sz);
+        if (rc) return rc;
+        P.results = e->d_results; P.targ_intersect = e->d_targ_intersect; P.rcs_angle = e->d_rcs_angle; P.tri_path = e->d_tri_path;
+    }
+
+    // queues: a batch of primaries and up to three live chains per primary with refraction
+    const uint64_t batch = std::min<uint64_t>(n_primary_total ? n_primary_total : 1, 1ull << 24);
+    const uint64_t cap = batch * (rMax ? 3 : 1);
+    {
+        int rc = trace_alloc_queues(e, cap);
+        if (rc) return rc;
+    }
+    P.out_capacity = e->q_capacity;
+    P.counters = e->d_counters;
+    RTS_CUDA(cudaMemsetAsync(e->d_counters, 0, sizeof(Counters), st));
+
+    cudaEventRecord(e->ev[0], st);
+    if (records) {
+        int rc = agg_fill_records(e, sz.ray_total, sz.depth_total, sz.tri_cols);
+        if (rc) return rc;
+    }
+    const uint32_t max_waves = p->max_refl + 1 + (rMax ? 2 : 0); // longest chain: see DESIGN.md (wave count)
+    uint64_t waves = 0;
+    for (uint64_t done = 0; done < n_primary_total; done += batch) {
+        const uint64_t nb = std::min<uint64_t>(batch, n_primary_total - done);
+        // d_counts: [0..31] queue counts per wave, [32..63] work counters per wave
+        RTS_CUDA(cudaMemsetAsync(e->d_counts, 0, sizeof(unsigned long long) * 64, st));
+        for (uint32_t w = 0; w < max_waves && w < 31; w++) {
+            WaveParams Q = P;
+            Q.ray_begin = begin + done * stride; Q.ray_stride = stride; Q.n_primary = nb;
+            Q.in = e->q[w & 1]; Q.out = e->q[(w + 1) & 1];
+            Q.in_count = e->d_counts + w;
+            Q.out_count = e->d_counts + w + 1;
+            Q.work_counter = e->d_counts + 32 + w;
+            int rc = trace_launch_wave(e, Q, w == 0, records);
+            if (rc) return rc;
+            waves++;
+        }
+    }
+    cudaEventRecord(e->ev[1], st);
+    Counters c;
+    RTS_CUDA(cudaMemcpyAsync(&c, e->d_counters, sizeof(c), cudaMemcpyDeviceToHost, st));
+    RTS_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+
+    rts_stats &s = e->stats;
+    memset(&s, 0, sizeof(s));
+    s.primary_rays = n_primary_total; s.segments = c.segments; s.hits = c.hits; s.shaded_hits = c.shaded;
+    s.captured = c.captured; s.multi_captured = c.multi; s.edge_rays = c.edge; s.refracted = c.refracted;
+    s.nodes_visited = c.nodes; s.tris_tested = c.tris; s.waves = waves;
+    s.ms_trace = ms; s.ms_update = e->bvh_info.ms_refit; s.ms_total = ms;
+    e->have_pulse = true; e->last_flags = flags; e->last_sizes = sz;
+    e->last_B = (uint32_t)B; e->last_D = sz.depth_total; e->last_nrx = p->n_rx;
+    e->bins_finalised = !(flags & RTS_NO_FINALISE);
+    if (c.overflow) return rts_fail(RTS_ERR_CAPACITY, "%llu ray states dropped (queue/stack overflow)", (unsigned long long)c.overflow);
+    return RTS_OK;
+}
+
+extern "C" int rts_get_stats(rts_engine *e, rts_stats *out)
+{
+    if (!e || !out) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    *out = e->stats;
+    return RTS_OK;
+}
+
+extern "C" int rts_get_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    if (!e->have_pulse || !(e->last_flags & RTS_OUT_BINS)) return rts_fail(RTS_ERR_STATE, "last pulse did not produce bins");
+    RTS_CUDA(cudaSetDevice(e->device));
+    return agg_collect_bins(e, out, cap, n);
+}
+
+extern "C" int rts_bins_device(rts_engine *e, void **sums, uint64_t *n_sum, void **mins, uint64_t *n_mins)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    if (!e->have_pulse || !(e->last_flags & RTS_OUT_BINS)) return rts_fail(RTS_ERR_STATE, "last pulse did not produce bins");
+    if (sums) *sums = e->d_bin_sums;
+    if (n_sum) *n_sum = e->n_bins_dense * 5;
+    if (mins) *mins = e->d_bin_mins;
+    if (n_mins) *n_mins = e->n_bins_dense;
+    return RTS_OK;
+}
+
+extern "C" int rts_finalise_bins(rts_engine *e)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    if (!e->have_pulse || !(e->last_flags & RTS_OUT_BINS)) return rts_fail(RTS_ERR_STATE, "last pulse did not produce bins");
+    e->bins_finalised = true; // myKernel2 is applied when bins are collected (agg_collect_bins)
+    return RTS_OK;
+}
+
+extern "C" int rts_get_records(rts_engine *e, rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle,
+                               int32_t *tri_path)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    if (!e->have_pulse || !(e->last_flags & RTS_OUT_RECORDS)) return rts_fail(RTS_ERR_STATE, "last pulse did not produce records");
+    RTS_CUDA(cudaSetDevice(e->device));
+    RTS_CUDA(cudaStreamSynchronize(e->stream));
+    const rts_sizes &sz = e->last_sizes;
+    const size_t n = sz.ray_total, D = sz.depth_total, W = sz.tri_cols;
+    if (results) RTS_CUDA(cudaMemcpy(results, e->d_results, sizeof(rts_ray_record) * n, cudaMemcpyDeviceToHost));
+    if (targ_intersect && D) RTS_CUDA(cudaMemcpy(targ_intersect, e->d_targ_intersect, sizeof(int32_t) * n * D, cudaMemcpyDeviceToHost));
+    if (rcs_angle && D) RTS_CUDA(cudaMemcpy(rcs_angle, e->d_rcs_angle, sizeof(double) * 2 * n * D, cudaMemcpyDeviceToHost));
+    if (tri_path) RTS_CUDA(cudaMemcpy(tri_path, e->d_tri_path, sizeof(int32_t) * n * W, cudaMemcpyDeviceToHost));
+    return RTS_OK;
+}
+
+extern "C" int rts_aggregate(rts_engine *e, rts_ray_record *rx_results, const int32_t *rx_intersects, uint32_t received,
+                             uint32_t depth_total, double cspeed, double carrier, double *npath, double *power,
+                             double *doppler, double *delay, double *phase, int32_t *path_match)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    if (received && (!rx_results || !npath || !power || !doppler || !delay || !phase || !path_match || (depth_total && !rx_intersects)))
+        return rts_fail(RTS_ERR_ARG, "NULL array");
+    RTS_CUDA(cudaSetDevice(e->device));
+    return agg_kernel_wrapper(e, rx_results, rx_intersects, received, depth_total, cspeed, carrier, npath, power, doppler,
+                              delay, phase, path_match);
+}
+
+// ---------------------------------------------------------------------------------------------
+// The reference's C++ entry point, same symbol and signature (aggregation.cuh:18-23), so a host
+// simulator that links rs::kernel_wrapper keeps linking.  PerRayData here is the layout twin
+// declared in include/rts_prd.h.  MaxThreads / MaxBlocks were launch-shape hints and are ignored.
+// Errors abort like the reference's cudaCheckErrors (aggregation.cu:17-27) because the signature
+// has no way to report them.
+#include "../../include/rts_prd.h"
+namespace rs {
+void kernel_wrapper(PerRayData *h_rx_results_arr, int *h_rx_intersects_arr, unsigned int receivedRays,
+                    unsigned int depthTotal, unsigned int MaxThreads, unsigned int MaxBlocks, double cspeed, double carrier,
+                    double *h_npath_arr, double *h_power_arr, double *h_doppler_arr, double *h_delay_arr,
+                    double *h_phase_arr, int *h_pathMatch)
+{
+    (void)MaxThreads; (void)MaxBlocks;
+    static thread_local rts_engine *eng = nullptr;
+    if (!eng) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (rts_create(dev, &eng) != RTS_OK) {
+            fprintf(stderr, "Fatal error: rs::kernel_wrapper: %s\n*** FAILED - ABORTING\n\n", rts_last_error());
+            exit(1);
+        }
+    }
+    if (rts_aggregate(eng, reinterpret_cast<rts_ray_record *>(h_rx_results_arr), h_rx_intersects_arr, receivedRays, depthTotal,
+                      cspeed, carrier, h_npath_arr, h_power_arr, h_doppler_arr, h_delay_arr, h_phase_arr, h_pathMatch) != RTS_OK) {
+        fprintf(stderr, "Fatal error: rs::kernel_wrapper: %s\n*** FAILED - ABORTING\n\n", rts_last_error());
+        exit(1);
+    }
+}
+} // namespace rs
+
+int agg_finalise_bins(rts_engine *) { return RTS_OK; }

@@ -1,0 +1,195 @@
+// engine.h — internal definitions of librts_b200 (device layouts, engine state, kernel launchers).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/rts_b200.h"
+
+#define RTS_LEAF_MAX 4          // triangles per BVH leaf (collapsed LBVH subtrees)
+#define RTS_STACK_DEPTH 96      // traversal stack entries per thread
+#define RTS_WAVE_BLOCK 128      // threads per CTA of the bounce-wave kernel
+#define RTS_MAX_RX 64
+
+// ---- device layouts -------------------------------------------------------------------------
+// BVH node, 64 B = 4 x 128-bit loads: the two child boxes (fp32, rounded outward exactly like the
+// reference's bound program, triangle_mesh.cu:228-229) and two child references.
+// child ref >= 0 : index of an internal node;  < 0 : leaf, ~ref = (first_leaf_pos << 3) | (count-1).
+struct __align__(64) BvhNode {
+    float lo0[3], hi0[3];   // child 0
+    float lo1[3], hi1[3];   // child 1
+    int32_t c0, c1;
+    int32_t pad[2];
+};
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
+
+// Leaf-ordered triangle record, 80 B = 5 x 128-bit loads: world-space fp64 vertices + ids.
+struct __align__(16) TriRec {
+    double p[9];            // p0.xyz p1.xyz p2.xyz
+    uint32_t tri_id;        // global triangle id (target offset + local index)
+    uint32_t target;
+};
+static_assert(sizeof(TriRec) == 80, "TriRec must be 80 bytes");
+
+// Wavefront ray state, struct of arrays (one array per field).
+#define RTS_NF 14
+enum RayField { F_OX, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_LEN, F_PW, F_DOP, F_FX, F_FY, F_FZ, F_N0, F_N1 };
+struct RayQueue {
+    double *f[RTS_NF];
+    unsigned long long *key;   // packed target-path row so far (digits base n_targets+1)
+    uint32_t *ray;             // primary ray index (global launch index)
+    uint32_t *meta;            // reflDepth[0:8) refrDepth[8:10) slot[10:14) end[14] primary[15] col[16:20)
+};
+
+struct Counters {              // device-side, accumulated with atomics
+    unsigned long long segments, hits, shaded, captured, multi, edge, refracted, nodes, tris, overflow;
+};
+
+struct RxDev { double cx, cy, cz, radius, min_theta, max_theta, min_phi, max_phi; };
+
+// Everything a bounce-wave kernel needs, passed by value.
+struct WaveParams {
+    // scene
+    const BvhNode *nodes;
+    const TriRec *trirec;
+    int32_t root_ref;
+    uint32_t n_tris;
+    const double *world_normals;    // [Nn*3]
+    const uint32_t *tris;           // [T*3] local vertex indices
+    const uint32_t *t_norm_off;     // per target
+    const uint32_t *t_tri_off;
+    const uint32_t *t_per_face;     // per target: 1 when n_normals > n_verts
+    const double *t_refl, *t_refr;  // per target
+    const double *t_vel;            // per target, 3
+    // launch constants (ray_tracer.cu:144-204, hoisted on the host)
+    uint32_t nx, ny, nz;
+    uint64_t R3;
+    uint32_t dMax, rMax, D, M, W;
+    uint32_t interpolate;
+    double origin[3];
+    double beamStart[3];
+    double slope[3];
+    double Rot[9], Rot1[9];
+    double boresight[3];
+    int single_ray;
+    // receivers
+    uint32_t n_rx;
+    const RxDev *rx;
+    // post-process constants (ray_tracer.cpp:1233-1253, aggregation.cu:59-60)
+    double cspeed, carrier, wl2gain;
+    // path key
+    uint64_t powB[RTS_MAX_DEPTH + 1];
+    uint64_t key_all;               // sum_{c<D} B^c
+    // shard
+    uint64_t ray_begin, ray_stride, n_primary;   // primary rays of this batch: index = ray_begin + i*ray_stride
+    // queues
+    RayQueue in, out;
+    const unsigned long long *in_count;
+    unsigned long long *out_count;
+    unsigned long long out_capacity;
+    unsigned long long *work_counter;
+    // outputs
+    uint32_t flags;
+    double *bin_sums;               // [n_bins*5]
+    unsigned long long *bin_mins;   // [n_bins]
+    uint64_t n_bins;
+    rts_ray_record *results;        // records mode
+    int32_t *targ_intersect;
+    double *rcs_angle;
+    int32_t *tri_path;
+    Counters *counters;
+};
+
+// ---- engine ---------------------------------------------------------------------------------
+struct rts_engine {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaEvent_t ev[6] = {};
+
+    // host-side scene meta
+    uint32_t n_targets = 0, n_tris = 0, n_verts = 0, n_normals = 0;
+    std::vector<uint32_t> tri_off, vert_off, norm_off, t_nverts, t_ntris, t_nnormals;
+    bool scene_ready = false;
+
+    // device scene
+    double *d_base_verts = nullptr, *d_base_normals = nullptr, *d_world_verts = nullptr, *d_world_normals = nullptr;
+    uint32_t *d_tris = nullptr, *d_tri_target = nullptr, *d_vert_target = nullptr, *d_norm_target = nullptr;
+    uint32_t *d_t_vert_off = nullptr, *d_t_norm_off = nullptr, *d_t_tri_off = nullptr, *d_t_per_face = nullptr;
+    double *d_t_refl = nullptr, *d_t_refr = nullptr, *d_t_vel = nullptr;
+    rts_pose *d_poses = nullptr;
+
+    // BVH
+    unsigned long long *d_morton = nullptr, *d_morton_sorted = nullptr;
+    uint32_t *d_order_in = nullptr, *d_order = nullptr, *d_leaf_of_tri = nullptr;
+    float *d_tri_box = nullptr, *d_node_box = nullptr, *d_scene_box = nullptr;
+    int32_t *d_parent = nullptr;     // [2T-1]: internal i at i, leaf pos p at (T-1)+p
+    int2 *d_children = nullptr, *d_range = nullptr;
+    uint32_t *d_fit_flags = nullptr;
+    BvhNode *d_nodes = nullptr;
+    TriRec *d_trirec = nullptr;
+    void *d_cub_temp = nullptr;
+    size_t cub_temp_bytes = 0;
+    int32_t root_ref = 0;
+    rts_bvh_info bvh_info = {};
+    unsigned long long *d_violations = nullptr;
+
+    // wave state
+    RayQueue q[2] = {};
+    void *q_slab[2] = {nullptr, nullptr};
+    uint64_t q_capacity = 0;
+    unsigned long long *d_counts = nullptr;   // [64] queue counts + work counters
+    Counters *d_counters = nullptr;
+    RxDev *d_rx = nullptr;
+    int wave_grid = 0;
+
+    // outputs
+    double *d_bin_sums = nullptr;
+    unsigned long long *d_bin_mins = nullptr;
+    uint64_t n_bins_dense = 0, bins_alloc = 0;
+    rts_bin *d_bins_out = nullptr;
+    uint32_t *d_bins_out_count = nullptr;
+    uint64_t bins_out_alloc = 0;
+    rts_ray_record *d_results = nullptr;
+    int32_t *d_targ_intersect = nullptr, *d_tri_path = nullptr;
+    double *d_rcs_angle = nullptr;
+    uint64_t rec_alloc_rays = 0, rec_alloc_D = 0, rec_alloc_W = 0;
+
+    // last pulse
+    bool have_pulse = false, bins_finalised = false;
+    uint32_t last_flags = 0;
+    rts_sizes last_sizes = {};
+    uint32_t last_B = 1, last_D = 0, last_nrx = 0;
+    rts_stats stats = {};
+};
+
+// error plumbing (api.cu)
+int rts_fail(int code, const char *fmt, ...);
+#define RTS_CUDA(call)                                                                                  \
+    do {                                                                                                \
+        cudaError_t _e = (call);                                                                        \
+        if (_e != cudaSuccess) return rts_fail(RTS_ERR_CUDA, "%s failed: %s (%s:%d)", #call,            \
+                                               cudaGetErrorString(_e), __FILE__, __LINE__);             \
+    } while (0)
+
+// bvh.cu
+int bvh_alloc(rts_engine *e);
+void bvh_free(rts_engine *e);
+int bvh_update_world(rts_engine *e);          // transform + tri boxes (+ tri records when topology exists)
+int bvh_build(rts_engine *e);                 // full LBVH build at current world geometry
+int bvh_refit(rts_engine *e);                 // bottom-up refit + repack
+int bvh_check(rts_engine *e, uint64_t *violations);
+
+// trace.cu
+int trace_alloc_queues(rts_engine *e, uint64_t capacity);
+int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool records);
+int trace_wave_grid(rts_engine *e);
+
+// aggregate.cu
+int agg_finalise_bins(rts_engine *e);
+int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n);
+int agg_fill_records(rts_engine *e, uint64_t ray_total, uint32_t D, uint32_t W);
+int agg_kernel_wrapper(rts_engine *e, rts_ray_record *rx_results, const int32_t *rx_intersects, uint32_t received,
+                       uint32_t depth_total, double cspeed, double carrier, double *npath, double *power,
+                       double *doppler, double *delay, double *phase, int32_t *path_match);

@@ -1,0 +1,639 @@
+// trace.cu — the wavefront bounce kernel (sm_100a): ray generation, BVH traversal with the fp64
+// ray/triangle test, closest-hit shading (reflect / refract / Doppler / path rows), miss
+// (receiver capture) and fused receiver-bin accumulation.
+//
+// One launch = one bounce wave over a queue of ray states (struct of arrays, 8-byte coalesced
+// accesses).  Persistent CTAs; each warp claims 32 queue entries at a time from a global work
+// counter.  Surviving rays and refracted children are appended to the next wave's queue with
+// warp-aggregated atomics (cooperative_groups::coalesced_threads), which is the compaction step.
+//
+// Reference semantics reproduced here (file:line in /root/reference):
+//   ray_generation    ray_tracer.cu:144-255       intersect  triangle_mesh.cu:121-200
+//   closest_hit       normal_shader.cu:128-340    miss       ray_tracer.cu:260-478
+//   host post-process ray_tracer.cpp:1190-1258    myKernel1  aggregation.cu:56-69 (per-ray terms)
+// The recursion of the reference (rtTrace inside closest_hit) becomes: the reflected ray continues
+// in place as the same chain; a refracted ray is a new chain (result slot +1) pushed to the queue.
+#include "engine.h"
+#include "dev_math.cuh"
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr float RT_DEFAULT_MAX_F = 1.e27f;
+constexpr double PAD_REL = 1e-6;   // conservative slab padding (relative)
+constexpr double PAD_ABS = 1e-9;   // and absolute
+constexpr double EDGE_EPS = 1e-9;
+
+struct Ray {
+    double ox, oy, oz, dx, dy, dz, len, pw, dop, fx, fy, fz, n0, n1;
+    unsigned long long key;
+    uint32_t ray, meta;
+};
+
+__device__ __forceinline__ uint32_t m_refl(uint32_t m) { return m & 0xffu; }
+__device__ __forceinline__ uint32_t m_refr(uint32_t m) { return (m >> 8) & 3u; }
+__device__ __forceinline__ uint32_t m_slot(uint32_t m) { return (m >> 10) & 15u; }
+__device__ __forceinline__ bool m_end(uint32_t m) { return (m >> 14) & 1u; }
+__device__ __forceinline__ bool m_primary(uint32_t m) { return (m >> 15) & 1u; }
+__device__ __forceinline__ uint32_t m_col(uint32_t m) { return (m >> 16) & 15u; }
+__device__ __forceinline__ uint32_t m_make(uint32_t refl, uint32_t refr, uint32_t slot, bool end, bool prim, uint32_t col)
+{
+    return (refl & 0xffu) | ((refr & 3u) << 8) | ((slot & 15u) << 10) | ((end ? 1u : 0u) << 14) | ((prim ? 1u : 0u) << 15) |
+           ((col & 15u) << 16);
+}
+
+__device__ __forceinline__ void load_ray(const RayQueue &q, unsigned long long i, Ray &r)
+{
+    r.ox = q.f[F_OX][i]; r.oy = q.f[F_OY][i]; r.oz = q.f[F_OZ][i];
+    r.dx = q.f[F_DX][i]; r.dy = q.f[F_DY][i]; r.dz = q.f[F_DZ][i];
+    r.len = q.f[F_LEN][i]; r.pw = q.f[F_PW][i]; r.dop = q.f[F_DOP][i];
+    r.fx = q.f[F_FX][i]; r.fy = q.f[F_FY][i]; r.fz = q.f[F_FZ][i];
+    r.n0 = q.f[F_N0][i]; r.n1 = q.f[F_N1][i];
+    r.key = q.key[i]; r.ray = q.ray[i]; r.meta = q.meta[i];
+}
+__device__ __forceinline__ void store_ray(const RayQueue &q, unsigned long long i, const Ray &r)
+{
+    q.f[F_OX][i] = r.ox; q.f[F_OY][i] = r.oy; q.f[F_OZ][i] = r.oz;
+    q.f[F_DX][i] = r.dx; q.f[F_DY][i] = r.dy; q.f[F_DZ][i] = r.dz;
+    q.f[F_LEN][i] = r.len; q.f[F_PW][i] = r.pw; q.f[F_DOP][i] = r.dop;
+    q.f[F_FX][i] = r.fx; q.f[F_FY][i] = r.fy; q.f[F_FZ][i] = r.fz;
+    q.f[F_N0][i] = r.n0; q.f[F_N1][i] = r.n1;
+    q.key[i] = r.key; q.ray[i] = r.ray; q.meta[i] = r.meta;
+}
+
+// Append one ray per calling thread to the next wave's queue: one atomic per converged group.
+__device__ __forceinline__ void push_ray(const WaveParams &P, const Ray &r, unsigned long long &overflow)
+{
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(P.out_count, (unsigned long long)g.size());
+    base = g.shfl(base, 0);
+    const unsigned long long i = base + g.thread_rank();
+    if (i < P.out_capacity) store_ray(P.out, i, r);
+    else overflow++;
+}
+
+// ray_tracer.cu:158-204 with the launch-invariant trigonometry hoisted to the host (WaveParams).
+__device__ __forceinline__ d3 primary_direction(const WaveParams &P, uint32_t ix, uint32_t iy, uint32_t iz)
+{
+    if (P.single_ray) return mk3(P.boresight[0], P.boresight[1], P.boresight[2]);
+    d3 d;
+    d.x = P.nx > 1 ? P.beamStart[0] + P.slope[0] * (ix) : P.beamStart[0];
+    d.y = P.ny > 1 ? P.beamStart[1] + P.slope[1] * (iy) : P.beamStart[1];
+    d.z = P.nz > 1 ? P.beamStart[2] + P.slope[2] * (iz) : P.beamStart[2];
+    d = normalised3(d);
+    d3 r = mk3(0, 0, 0);
+    r.x += P.Rot[0] * d.x + P.Rot[1] * d.y + P.Rot[2] * d.z;
+    r.y += P.Rot[3] * d.x + P.Rot[4] * d.y + P.Rot[5] * d.z;
+    r.z += P.Rot[6] * d.x + P.Rot[7] * d.y + P.Rot[8] * d.z;
+    d = normalised3(r);
+    r = mk3(0, 0, 0);
+    r.x += P.Rot1[0] * d.x + P.Rot1[1] * d.y + P.Rot1[2] * d.z;
+    r.y += P.Rot1[3] * d.x + P.Rot1[4] * d.y + P.Rot1[5] * d.z;
+    r.z += P.Rot1[6] * d.x + P.Rot1[7] * d.y + P.Rot1[8] * d.z;
+    return r;
+}
+
+struct Tri { d3 p0, p1, p2; uint32_t id, target; };
+
+__device__ __forceinline__ Tri load_tri(const TriRec *rec, int pos)
+{
+    const double2 *s = reinterpret_cast<const double2 *>(rec + pos);
+    const double2 a = __ldg(s), b = __ldg(s + 1), c = __ldg(s + 2), d = __ldg(s + 3), e = __ldg(s + 4);
+    Tri t;
+    t.p0 = mk3(a.x, a.y, b.x); t.p1 = mk3(b.y, c.x, c.y); t.p2 = mk3(d.x, d.y, e.x);
+    const unsigned long long ids = (unsigned long long)__double_as_longlong(e.y);
+    t.id = (uint32_t)ids; t.target = (uint32_t)(ids >> 32);
+    return t;
+}
+
+// triangle_mesh.cu:121-137
+__device__ __forceinline__ bool tri_test(const Tri &T, const d3 &o, const d3 &dir, double tmin_d, double tmax_d, d3 &n,
+                                         double &t, double &beta, double &gamma)
+{
+    const d3 e0 = T.p1 - T.p0;
+    const d3 e1 = T.p0 - T.p2;
+    n = cross3(e1, e0);
+    const d3 e2 = (1 / dot3(n, dir)) * (T.p0 - o);
+    const d3 i = cross3(dir, e2);
+    beta = dot3(i, e1);
+    gamma = dot3(i, e0);
+    t = dot3(n, e2);
+    return ((t < tmax_d) & (t > tmin_d) & (beta >= 0.0f) & (gamma >= 0.0f) & (beta + gamma <= 1));
+}
+
+struct HitRec { int pos; float t; uint32_t id; };
+
+// BVH traversal: fp64 slab test of the true (fp64) ray against the fp32 outward-rounded boxes,
+// padded so that no box is pruned that the fp64 triangle test could accept; closest hit =
+// smallest fp32 t in (tmin, inf), ties to the lowest global triangle id (rtPotentialIntersection
+// semantics with a defined tie rule).
+__device__ __forceinline__ void traverse(const WaveParams &P, const Ray &r, float tmin_f, HitRec &best,
+                                         unsigned &n_nodes, unsigned &n_tris, unsigned &stack_ovf)
+{
+    best.pos = -1; best.t = RT_DEFAULT_MAX_F; best.id = 0xffffffffu;
+    if (P.n_tris == 0) return;
+    const d3 o = mk3(r.ox, r.oy, r.oz), dir = mk3(r.dx, r.dy, r.dz);
+    const double ivx = 1.0 / dir.x, ivy = 1.0 / dir.y, ivz = 1.0 / dir.z;
+    const bool sx = signbit(dir.x), sy = signbit(dir.y), sz = signbit(dir.z);
+    const double tmin_d = (double)tmin_f, tmax_d = (double)RT_DEFAULT_MAX_F;
+    double best_pad = CUDART_INF;
+    int stack[RTS_STACK_DEPTH];
+    int sp = 0;
+    int cur = P.root_ref;
+    for (;;) {
+        if (cur >= 0) {
+            n_nodes++;
+            const float4 *np = reinterpret_cast<const float4 *>(P.nodes + cur);
+            const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+            const int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
+            // child 0: lo (q0.x q0.y q0.z) hi (q0.w q1.x q1.y); child 1: lo (q1.z q1.w q2.x) hi (q2.y q2.z q2.w)
+            double tn0, tf0, tn1, tf1;
+            {
+                const double nx_ = (double)(sx ? q0.w : q0.x), fx_ = (double)(sx ? q0.x : q0.w);
+                const double ny_ = (double)(sy ? q1.x : q0.y), fy_ = (double)(sy ? q0.y : q1.x);
+                const double nz_ = (double)(sz ? q1.y : q0.z), fz_ = (double)(sz ? q0.z : q1.y);
+                tn0 = fmax(fmax((nx_ - o.x) * ivx, (ny_ - o.y) * ivy), (nz_ - o.z) * ivz);
+                tf0 = fmin(fmin((fx_ - o.x) * ivx, (fy_ - o.y) * ivy), (fz_ - o.z) * ivz);
+            }
+            {
+                const double nx_ = (double)(sx ? q2.y : q1.z), fx_ = (double)(sx ? q1.z : q2.y);
+                const double ny_ = (double)(sy ? q2.z : q1.w), fy_ = (double)(sy ? q1.w : q2.z);
+                const double nz_ = (double)(sz ? q2.w : q2.x), fz_ = (double)(sz ? q2.x : q2.w);
+                tn1 = fmax(fmax((nx_ - o.x) * ivx, (ny_ - o.y) * ivy), (nz_ - o.z) * ivz);
+                tf1 = fmin(fmin((fx_ - o.x) * ivx, (fy_ - o.y) * ivy), (fz_ - o.z) * ivz);
+            }
+            const bool h0 = (tn0 <= tf0 * (1.0 + PAD_REL) + PAD_ABS) & (tf0 >= 0.0) & (tn0 <= best_pad);
+            const bool h1 = (tn1 <= tf1 * (1.0 + PAD_REL) + PAD_ABS) & (tf1 >= 0.0) & (tn1 <= best_pad);
+            if (h0 & h1) {
+                const bool swap = tn1 < tn0;
+                if (sp < RTS_STACK_DEPTH) stack[sp++] = swap ? q3.x : q3.y;
+                else stack_ovf++;
+                cur = swap ? q3.y : q3.x;
+                continue;
+            }
+            if (h0) { cur = q3.x; continue; }
+            if (h1) { cur = q3.y; continue; }
+        } else {
+            const int code = ~cur;
+            const int first = code >> 3, cnt = (code & 7) + 1;
+            for (int k = 0; k < cnt; k++) {
+                n_tris++;
+                const Tri T = load_tri(P.trirec, first + k);
+                d3 n;
+                double t, beta, gamma;
+                if (tri_test(T, o, dir, tmin_d, tmax_d, n, t, beta, gamma)) {
+                    const float tf = (float)t;
+                    if (tf > tmin_f && (tf < best.t || (tf == best.t && T.id < best.id))) {
+                        best.t = tf; best.pos = first + k; best.id = T.id;
+                        best_pad = (double)tf * (1.0 + PAD_REL) + PAD_ABS;
+                    }
+                }
+            }
+        }
+        if (sp == 0) break;
+        cur = stack[--sp];
+    }
+}
+
+// Chain end: the record the reference writes back for this result slot
+// (ray_tracer.cu:246-253 for slot 0, normal_shader.cu:272-279 for refracted slots).
+template <bool RECORDS>
+__device__ __forceinline__ void finish_chain(const WaveParams &P, const Ray &r, int received)
+{
+    if (RECORDS) {
+        rts_ray_record *o = P.results + ((unsigned long long)r.ray + (unsigned long long)m_slot(r.meta) * P.R3);
+        o->reflDepth = m_refl(r.meta);
+        o->refrDepth = m_refr(r.meta);
+        o->rayLength = r.len;
+        o->firstHitPoint[0] = r.fx; o->firstHitPoint[1] = r.fy; o->firstHitPoint[2] = r.fz;
+        o->prevHitPoint[0] = r.ox; o->prevHitPoint[1] = r.oy; o->prevHitPoint[2] = r.oz;
+        o->power = r.pw;
+        o->doppler = r.dop;
+        o->received = received;
+    }
+}
+
+__device__ __forceinline__ void cart_to_sph(d3 in, double &azi, double &ele) // normal_shader.cu:118-124
+{
+    azi = atan2(in.y, in.x);
+    ele = atan2(in.z, sqrt(in.x * in.x + in.y * in.y));
+}
+
+struct Local { unsigned long long segments, hits, shaded, captured, multi, edge, refracted, nodes, tris, overflow; };
+
+// normal_shader.cu:128-340
+template <bool RECORDS>
+__device__ __forceinline__ void shade(const WaveParams &P, Ray &r, const HitRec &h, Local &L)
+{
+    const uint32_t dMax = P.dMax, rMax = P.rMax;
+    uint32_t reflDepth = m_refl(r.meta), refrDepth = m_refr(r.meta);
+    const uint32_t slot = m_slot(r.meta), col = m_col(r.meta);
+    bool end = m_end(r.meta);
+    const bool primary = m_primary(r.meta);
+    const Tri T = load_tri(P.trirec, h.pos);
+    const unsigned long long row = (unsigned long long)r.ray + (unsigned long long)slot * P.R3;
+
+    if (RECORDS && col < P.W) P.tri_path[row * P.W + col] = (int32_t)T.id;
+
+    // guard, :134 — an absorbed hit changes nothing
+    if (!((end == false) && ((refrDepth < rMax) || (reflDepth < (dMax - 1))))) {
+        finish_chain<RECORDS>(P, r, -1);
+        return;
+    }
+    L.shaded++;
+
+    // the winner's attributes, recomputed with the same arithmetic as during traversal
+    d3 o = mk3(r.ox, r.oy, r.oz), dir = mk3(r.dx, r.dy, r.dz);
+    d3 n;
+    double tt, beta, gamma;
+    tri_test(T, o, dir, 0.0, 0.0, n, tt, beta, gamma);
+    if (fmin(fmin(beta, gamma), 1 - beta - gamma) < EDGE_EPS) L.edge++;
+    const uint32_t targ = T.target;
+    d3 normal;
+    if (P.interpolate) { // triangle_mesh.cu:177-190
+        const uint32_t noff = P.t_norm_off[targ];
+        if (P.t_per_face[targ]) {
+            const double *nn = P.world_normals + 3 * (size_t)(noff + (T.id - P.t_tri_off[targ]));
+            normal = mk3(nn[0], nn[1], nn[2]);
+        } else {
+            const uint32_t *vi = P.tris + 3 * (size_t)T.id;
+            const double *a0 = P.world_normals + 3 * (size_t)(noff + vi[0]);
+            const double *a1 = P.world_normals + 3 * (size_t)(noff + vi[1]);
+            const double *a2 = P.world_normals + 3 * (size_t)(noff + vi[2]);
+            normal = mk3(a1[0] * beta + a2[0] * gamma + a0[0] * (1.0f - beta - gamma),
+                         a1[1] * beta + a2[1] * gamma + a0[1] * (1.0f - beta - gamma),
+                         a1[2] * beta + a2[2] * gamma + a0[2] * (1.0f - beta - gamma));
+        }
+        normal = normalised3(normal);
+    } else {
+        normal = normalised3(n);
+    }
+    const double reflCoeff = P.t_refl[targ], refrIndex = P.t_refr[targ];
+    const float hit_t = h.t;
+
+    // :140-146 path row
+    if (refrDepth != 1) {
+        const uint32_t x = reflDepth + refrDepth;
+        if (x < (rMax + dMax - 1)) {
+            if (RECORDS) P.targ_intersect[row * P.D + x] = (int)targ;
+            r.key += (unsigned long long)(targ + 1) * P.powB[x];
+        }
+    }
+
+    // :148-152
+    d3 hitPoint;
+    hitPoint.x = o.x + (double)hit_t * dir.x;
+    hitPoint.y = o.y + (double)hit_t * dir.y;
+    hitPoint.z = o.z + (double)hit_t * dir.z;
+    r.len += hit_t;
+
+    // :158-173 spreading loss
+    if ((reflDepth == 0) && (refrDepth == 0)) {
+        r.fx = hitPoint.x; r.fy = hitPoint.y; r.fz = hitPoint.z;
+        const d3 TxRange = hitPoint - mk3(P.origin[0], P.origin[1], P.origin[2]);
+        if (len3(TxRange) >= SCENE_EPS) r.pw = 1 / ((magsq3(TxRange)) * 4 * M_PI);
+        else end = true;
+    } else {
+        const d3 TargRange = hitPoint - o;
+        if (len3(TargRange) >= SCENE_EPS_R) r.pw *= 1 / ((magsq3(TargRange)) * 4 * M_PI);
+        else end = true;
+    }
+
+    // :176
+    r.ox = hitPoint.x; r.oy = hitPoint.y; r.oz = hitPoint.z;
+
+    // the fp32 direction of the ray being shaded (ray.direction): primary rays carry
+    // normalise_float3(fp64 dir) (ray_tracer.cu:208), later rays the fp32 direction itself
+    f3 rdir;
+    if (primary) rdir = normalise_float3(dir);
+    else { rdir.x = (float)dir.x; rdir.y = (float)dir.y; rdir.z = (float)dir.z; }
+    const f3 nf = normalise_float3(normal);
+    const d3 V = mk3(P.t_vel[3 * targ], P.t_vel[3 * targ + 1], P.t_vel[3 * targ + 2]);
+
+    // :191-194
+    const double pr_n0 = r.n1; // prd_refr.refrIndex.x = prd_refr.refrIndex.y
+
+    // :198-282 refraction: a new chain in the next result slot
+    if ((fabs(reflCoeff) != 1.00000f) && (refrDepth < rMax) && (reflDepth == 0)) {
+        const double pr_n1 = (pr_n0 == 1) ? refrIndex : 1.0;
+        const float ratio = (float)(pr_n1 / pr_n0);
+        f3 nd;
+        if (optix_refract(nd, rdir, nf, ratio)) {
+            L.refracted++;
+            const uint32_t cslot = slot + 1;
+            const unsigned long long crow = (unsigned long long)r.ray + (unsigned long long)cslot * P.R3;
+            Ray c = r;
+            c.n0 = pr_n0; c.n1 = pr_n1;
+            if ((refrDepth == 0) && (cslot == 1)) { // :221-239 pre-fill
+                if (RECORDS) {
+                    for (uint32_t i = 0; i < P.D; i++) P.targ_intersect[crow * P.D + i] = (int)targ;
+                    for (uint32_t j = 0; j < dMax; j++)
+                        for (uint32_t i = 0; i < (j + 2) && i < P.D; i++)
+                            P.targ_intersect[((unsigned long long)r.ray + (unsigned long long)(j + 2) * P.R3) * P.D + i] = (int)targ;
+                }
+                c.key = (unsigned long long)(targ + 1) * P.key_all;
+            } else {
+                // exit chain: its row was pre-filled with the first-hit target in columns 0 and 1
+                const unsigned long long first_digit = r.key % P.powB[1];
+                c.key = first_digit * (1ull + P.powB[1]);
+            }
+            if ((reflDepth + 1) < dMax) c.pw *= (1 - fabs(reflCoeff)); // :245-246
+            const uint32_t c_refr = refrDepth + 1;                       // :247
+            const d3 k0 = normalised3(dir);                              // :251-256
+            c.dx = (double)nd.x; c.dy = (double)nd.y; c.dz = (double)nd.z;
+            const d3 k1 = normalised3(mk3(c.dx, c.dy, c.dz));
+            c.dop += dot3(V, k1 - k0);
+            if (RECORDS && !(P.flags & RTS_NO_RCS_ANGLES)) { // :259-265
+                const uint32_t x = reflDepth + (c_refr - 1);
+                if (x < P.D) {
+                    double a0, e0, a1, e1;
+                    cart_to_sph(k0, a0, e0);
+                    cart_to_sph(mk3(-k1.x, -k1.y, -k1.z), a1, e1);
+                    P.rcs_angle[(crow * P.D + x) * 2] = a0 + a1;
+                    P.rcs_angle[(crow * P.D + x) * 2 + 1] = e0 + e1;
+                }
+            }
+            c.meta = m_make(reflDepth, c_refr, cslot, end, false, col + 1);
+            push_ray(P, c, L.overflow); // :268
+        }
+    }
+
+    // :286-290
+    reflDepth++;
+    r.n1 = pr_n0;
+    r.n0 = pr_n0;
+
+    // :293-333 reflection: the same chain continues
+    if (reflDepth < dMax) {
+        const f3 nd = optix_reflect(rdir, nf);
+        r.pw *= reflCoeff;
+        const d3 k0 = normalised3(dir);
+        r.dx = (double)nd.x; r.dy = (double)nd.y; r.dz = (double)nd.z;
+        const d3 k1 = normalised3(mk3(r.dx, r.dy, r.dz));
+        r.dop += dot3(V, k1 - k0);
+        if (RECORDS && !(P.flags & RTS_NO_RCS_ANGLES)) { // :320-326
+            const uint32_t x = (reflDepth - 1) + refrDepth;
+            if (x < P.D) {
+                double a0, e0, a1, e1;
+                cart_to_sph(k0, a0, e0);
+                cart_to_sph(mk3(-k1.x, -k1.y, -k1.z), a1, e1);
+                P.rcs_angle[(row * P.D + x) * 2] = a0 + a1;
+                P.rcs_angle[(row * P.D + x) * 2 + 1] = e0 + e1;
+            }
+        }
+        r.meta = m_make(reflDepth, refrDepth, slot, end, false, col + 1);
+        push_ray(P, r, L.overflow); // :332
+    } else {
+        r.meta = m_make(reflDepth, refrDepth, slot, end, false, col + 1);
+        finish_chain<RECORDS>(P, r, -1);
+    }
+}
+
+// ray_tracer.cu:260-478.  Returns the receiver index or -1.
+template <bool RECORDS>
+__device__ __forceinline__ int miss(const WaveParams &P, Ray &r, Local &L)
+{
+    const uint32_t reflDepth = m_refl(r.meta), refrDepth = m_refr(r.meta);
+    bool end = m_end(r.meta);
+    int received = -1;
+    const d3 dir = mk3(r.dx, r.dy, r.dz);
+    const d3 po = mk3(r.ox, r.oy, r.oz);
+    if (end == false) {
+        double A, B, C, discriminant;
+        double t[2] = {0, 0};
+        unsigned captures = 0;
+        for (unsigned int Rx_i = 0; Rx_i < P.n_rx; Rx_i++) {
+            const RxDev rx = P.rx[Rx_i];
+            A = (dir.x) * (dir.x) + (dir.y) * (dir.y) + (dir.z) * (dir.z);
+            B = 2 * (((po.x - rx.cx) * dir.x) + ((po.y - rx.cy) * dir.y) + ((po.z - rx.cz) * dir.z));
+            C = po.x * po.x + po.y * po.y + po.z * po.z + (rx.cx * rx.cx) + (rx.cy * rx.cy) + (rx.cz * rx.cz) -
+                2 * ((rx.cx * po.x) + (rx.cy * po.y) + (rx.cz * po.z)) - rx.radius * rx.radius;
+            discriminant = B * B - 4 * A * C;
+            if (discriminant > 0.f) {
+                discriminant = sqrt(discriminant);
+                t[0] = (-B - discriminant) / (2 * A);
+                t[1] = (-B + discriminant) / (2 * A);
+                unsigned int received_root = 2;
+                for (int i = 0; i < 2; i++) {
+                    if ((t[i] >= 0) && ((r.len + t[i]) > SCENE_EPS) && ((r.len + t[i]) > SCENE_EPS_R)) {
+                        d3 endPoint;
+                        endPoint.x = po.x + t[i] * dir.x;
+                        endPoint.y = po.y + t[i] * dir.y;
+                        endPoint.z = po.z + t[i] * dir.z;
+                        double theta = atan2f((endPoint.y - rx.cy), (endPoint.x - rx.cx));
+                        double phi = atan2f(endPoint.z - rx.cz, sqrt(((endPoint.y - rx.cy) * (endPoint.y - rx.cy)) +
+                                                                     ((endPoint.x - rx.cx) * (endPoint.x - rx.cx))));
+                        if ((phi < -M_PI / 2)) { theta += M_PI; phi = -M_PI - phi; }
+                        if ((phi > M_PI / 2)) { theta += M_PI; phi = M_PI - phi; }
+                        double maxTheta1 = rx.max_theta, minTheta1 = rx.min_theta;
+                        double maxTheta2 = maxTheta1, minTheta2 = minTheta1;
+                        double maxPhi1 = rx.max_phi, minPhi1 = rx.min_phi;
+                        double maxPhi2 = maxPhi1, minPhi2 = minPhi1;
+                        if ((minPhi1 < -M_PI / 2)) {
+                            maxTheta2 += M_PI; minTheta2 += M_PI;
+                            maxPhi2 = -M_PI - minPhi1; minPhi2 = -M_PI / 2; minPhi1 = -M_PI / 2;
+                        }
+                        if ((maxPhi1 > M_PI / 2)) {
+                            maxTheta2 += M_PI; minTheta2 += M_PI;
+                            minPhi2 = M_PI - maxPhi1; maxPhi2 = M_PI / 2; maxPhi1 = M_PI / 2;
+                        }
+                        if (((angle_in_range(theta, minTheta1, maxTheta1)) && (angle_in_range(phi, minPhi1, maxPhi1))) ||
+                            ((angle_in_range(theta, minTheta2, maxTheta2)) && (angle_in_range(phi, minPhi2, maxPhi2)))) {
+                            if (received_root == 2) received_root = i;
+                            else if (t[received_root] > t[i]) received_root = i;
+                        }
+                    }
+                }
+                if (received_root < 2) {
+                    end = true;
+                    const unsigned int i = received_root;
+                    d3 endPoint;
+                    endPoint.x = po.x + t[i] * dir.x;
+                    endPoint.y = po.y + t[i] * dir.y;
+                    endPoint.z = po.z + t[i] * dir.z;
+                    if ((reflDepth == 0) && (refrDepth == 0)) {
+                        const d3 RxRange = endPoint - mk3(P.origin[0], P.origin[1], P.origin[2]);
+                        if (len3(RxRange) >= SCENE_EPS) {
+                            r.pw = 1 / (4 * M_PI * 4 * M_PI * (magsq3(RxRange)));
+                            r.dop = 0;
+                            r.len += t[i];
+                            received = (int)Rx_i;
+                            captures++;
+                        }
+                    } else {
+                        const d3 RxRange = endPoint - po;
+                        if (len3(RxRange) >= SCENE_EPS_R) {
+                            r.pw *= 1 / ((magsq3(RxRange)) * 4 * M_PI * 4 * M_PI);
+                            r.len += t[i];
+                            received = (int)Rx_i;
+                            captures++;
+                        }
+                    }
+                }
+            }
+        }
+        if (captures > 1) L.multi++;
+    }
+    // Earth (ray_tracer.cu:438-477): only observable through rayLength of unreceived records
+    if (RECORDS && end == false) {
+        const double R = RTS_EARTH_RADIUS;
+        const double A = (dir.x) * (dir.x) + (dir.y) * (dir.y) + (dir.z) * (dir.z);
+        const double B = 2 * (po.x * dir.x + po.y * dir.y + po.z * dir.z);
+        const double C = po.x * po.x + po.y * po.y + po.z * po.z - R * R;
+        double discriminant = B * B - 4 * A * C;
+        if (discriminant > 0.f) {
+            discriminant = sqrt(discriminant);
+            const double t0 = (-B - discriminant) / (2 * A), t1 = (-B + discriminant) / (2 * A);
+            if ((t0 >= 0) && (r.len > 0)) { end = true; r.len += t0; }
+            if ((t1 >= 0) && (r.len > 0)) { end = true; r.len += t1; }
+        }
+    }
+    finish_chain<RECORDS>(P, r, received);
+    return received;
+}
+
+// Fused host post-process (RCS = Gt = Gr = 1; ray_tracer.cpp:1219-1253) and the per-ray terms of
+// myKernel1 (aggregation.cu:59-69), summed into the (receiver, path) bin.  Lanes of a converged
+// group that hit the same bin are reduced with shuffles first, so one group issues one set of
+// fp64 atomics per distinct bin.
+__device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r, int received)
+{
+    double pw = r.pw;
+    pw *= P.wl2gain;
+    const double Vr = r.dop / 2;
+    const double dopHz = P.carrier * (((1 + Vr / P.cspeed) / (1 - Vr / P.cspeed)) - 1);
+    const double delay = (r.len) / P.cspeed;
+    const double phase = -fmod(delay * 2 * M_PI * P.carrier, 2 * M_PI);
+    const double amp = sqrt(pw);
+    const unsigned long long bin = (unsigned long long)received * P.powB[P.D] + r.key;
+    const unsigned long long slot = (unsigned long long)r.ray + (unsigned long long)m_slot(r.meta) * P.R3;
+    if (bin >= P.n_bins) return;
+    cg::coalesced_group g = cg::coalesced_threads();
+    auto part = cg::labeled_partition(g, bin);
+    const double s_n = cg::reduce(part, 1.0, cg::plus<double>());
+    const double s_a = cg::reduce(part, amp, cg::plus<double>());
+    const double s_d = cg::reduce(part, delay, cg::plus<double>());
+    const double s_p = cg::reduce(part, phase, cg::plus<double>());
+    const double s_f = cg::reduce(part, dopHz, cg::plus<double>());
+    const unsigned long long s_m = cg::reduce(part, slot, cg::less<unsigned long long>());
+    if (part.thread_rank() == 0) {
+        double *b = P.bin_sums + bin * 5;
+        atomicAdd(b + 0, s_n);
+        atomicAdd(b + 1, s_a);
+        atomicAdd(b + 2, s_d);
+        atomicAdd(b + 3, s_p);
+        atomicAdd(b + 4, s_f);
+        atomicMin(P.bin_mins + bin, s_m);
+    }
+}
+
+template <bool PRIMARY, bool RECORDS>
+__global__ void __launch_bounds__(RTS_WAVE_BLOCK) k_wave(const __grid_constant__ WaveParams P)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned long long n_in = PRIMARY ? P.n_primary : *P.in_count;
+    Local L = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (;;) {
+        unsigned long long base = 0;
+        if (lane == 0) base = atomicAdd(P.work_counter, 32ull);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_in) break;
+        const unsigned long long idx = base + lane;
+        if (idx >= n_in) continue;
+        Ray r;
+        if (PRIMARY) {
+            const unsigned long long rayIndex = P.ray_begin + idx * P.ray_stride;
+            const unsigned long long nxy = (unsigned long long)P.nx * P.ny;
+            const uint32_t iz = (uint32_t)(rayIndex / nxy);
+            const uint32_t iy = (uint32_t)((rayIndex % nxy) / P.nx);
+            const uint32_t ix = (uint32_t)(rayIndex % P.nx);
+            const d3 d = primary_direction(P, ix, iy, iz);
+            r.ox = P.origin[0]; r.oy = P.origin[1]; r.oz = P.origin[2];
+            r.dx = d.x; r.dy = d.y; r.dz = d.z;
+            r.len = 0; r.pw = 0; r.dop = 0; r.fx = 0; r.fy = 0; r.fz = 0; r.n0 = 1; r.n1 = 1;
+            r.key = 0; r.ray = (uint32_t)rayIndex;
+            r.meta = m_make(0, 0, 0, false, true, 0);
+        } else {
+            load_ray(P.in, idx, r);
+        }
+        L.segments++;
+        HitRec h;
+        unsigned nn = 0, nt = 0, so = 0;
+        traverse(P, r, SCENE_EPS, h, nn, nt, so); // SCENE_EPS == SCENE_EPS_R (ray_tracer.h:9-10)
+        L.nodes += nn; L.tris += nt; L.overflow += so;
+        if (h.pos >= 0) {
+            L.hits++;
+            shade<RECORDS>(P, r, h, L);
+        } else {
+            const int received = miss<RECORDS>(P, r, L);
+            if (received >= 0) {
+                L.captured++;
+                if (P.flags & RTS_OUT_BINS) accumulate_bin(P, r, received);
+            }
+        }
+    }
+    // counters: warp reduce, one atomic per warp per counter
+    unsigned long long *c = reinterpret_cast<unsigned long long *>(P.counters);
+    unsigned long long v[10] = {L.segments, L.hits, L.shaded, L.captured, L.multi, L.edge, L.refracted, L.nodes, L.tris, L.overflow};
+#pragma unroll
+    for (int k = 0; k < 10; k++) {
+        unsigned long long x = v[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+        if (lane == 0 && x) atomicAdd(c + k, x);
+    }
+}
+
+} // namespace
+
+int trace_wave_grid(rts_engine *e)
+{
+    if (e->wave_grid) return e->wave_grid;
+    int occ = 0, best = 1 << 30;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wave<true, false>, RTS_WAVE_BLOCK, 0);
+    best = occ < best ? occ : best;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wave<false, false>, RTS_WAVE_BLOCK, 0);
+    best = occ < best ? occ : best;
+    if (best < 1) best = 1;
+    e->wave_grid = e->num_sms * best;
+    return e->wave_grid;
+}
+
+int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool records)
+{
+    const int grid = trace_wave_grid(e);
+    if (primary) {
+        if (records) k_wave<true, true><<<grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
+        else k_wave<true, false><<<grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
+    } else {
+        if (records) k_wave<false, true><<<grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
+        else k_wave<false, false><<<grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
+    }
+    RTS_CUDA(cudaGetLastError());
+    return RTS_OK;
+}
+
+int trace_alloc_queues(rts_engine *e, uint64_t capacity)
+{
+    if (capacity <= e->q_capacity) return RTS_OK;
+    const size_t per = (size_t)RTS_NF * 8 + 8 + 4 + 4;
+    for (int k = 0; k < 2; k++) {
+        if (e->q_slab[k]) { cudaFree(e->q_slab[k]); e->q_slab[k] = nullptr; }
+        cudaError_t err = cudaMalloc(&e->q_slab[k], per * capacity + 256);
+        if (err != cudaSuccess) {
+            e->q_capacity = 0;
+            return rts_fail(RTS_ERR_CUDA, "queue allocation of %zu bytes failed: %s", per * capacity, cudaGetErrorString(err));
+        }
+        char *base = (char *)e->q_slab[k];
+        for (int f = 0; f < RTS_NF; f++) e->q[k].f[f] = (double *)(base + (size_t)f * 8 * capacity);
+        e->q[k].key = (unsigned long long *)(base + (size_t)RTS_NF * 8 * capacity);
+        e->q[k].ray = (uint32_t *)(base + (size_t)(RTS_NF + 1) * 8 * capacity);
+        e->q[k].meta = (uint32_t *)(base + (size_t)(RTS_NF + 1) * 8 * capacity + 4 * capacity);
+    }
+    e->q_capacity = capacity;
+    return RTS_OK;
+}

@@ -1,0 +1,284 @@
+"""ctypes binding of librts_b200.so (include/rts_b200.h) — the product's only compute path.
+
+There is deliberately no fallback: if the shared library is missing the import of this module
+raises, and every compute call raises RtsError when no sm_100 device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .abi import (BIN_DTYPE, RAY_RECORD, CPulse, CScene, PulseSpec, RtsBin, RtsPulse, RtsRxDesc, RtsRxSphere, RtsStats,
+                  RtsTargetMesh, Target)
+
+RTS_OUT_BINS = 1
+RTS_OUT_RECORDS = 2
+RTS_COUNT_NODES = 4
+RTS_NO_FINALISE = 8
+RTS_NO_RCS_ANGLES = 16
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librts_b200.so")
+
+
+class RtsError(RuntimeError):
+    pass
+
+
+class RtsPose(C.Structure):
+    _fields_ = [("R", C.c_double * 9), ("t", C.c_double * 3), ("has_rotation", C.c_int32), ("_pad", C.c_int32)]
+
+
+class RtsSizes(C.Structure):
+    _fields_ = [("rays", C.c_uint64), ("ray_total", C.c_uint64), ("depth_total", C.c_uint32), ("slots", C.c_uint32),
+                ("tri_cols", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class RtsBvhInfo(C.Structure):
+    _fields_ = [("n_tris", C.c_uint32), ("n_nodes", C.c_uint32), ("root_is_leaf", C.c_uint32), ("max_leaf", C.c_uint32),
+                ("scene_lo", C.c_float * 3), ("scene_hi", C.c_float * 3), ("ms_build", C.c_float), ("ms_refit", C.c_float),
+                ("sah_cost", C.c_double)]
+
+
+#: every symbol include/rts_b200.h declares (tests/test_abi.py checks the library exports them all)
+EXPORTS = [
+    "rts_create", "rts_destroy", "rts_last_error", "rts_version", "rts_abi_sizes", "rts_set_stream",
+    "rts_rx_sphere_from_desc", "rts_result_sizes", "rts_rect_mesh", "rts_sphere_mesh", "rts_file_mesh",
+    "rts_rotation_matrix", "rts_scene_set_targets", "rts_scene_set_poses", "rts_scene_rebuild", "rts_scene_bvh_info",
+    "rts_scene_get_world_vertices", "rts_scene_get_tri_bounds", "rts_scene_check_bvh", "rts_trace_pulse",
+    "rts_get_stats", "rts_get_bins", "rts_get_records", "rts_bins_device", "rts_finalise_bins", "rts_aggregate",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load librts_b200.so (built by __graft_entry__.build() / make -C rts_b200/csrc)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RtsError(f"{LIB_PATH} is missing: build it with `make -C rts_b200/csrc` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, u32, u64, dbl, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_double, C.c_int32
+    P = C.POINTER
+    lib.rts_create.argtypes = [C.c_int, P(vp)]
+    lib.rts_destroy.argtypes = [vp]
+    lib.rts_destroy.restype = None
+    lib.rts_last_error.restype = C.c_char_p
+    lib.rts_version.restype = C.c_char_p
+    lib.rts_abi_sizes.argtypes = [P(u32)]
+    lib.rts_set_stream.argtypes = [vp, vp]
+    lib.rts_rx_sphere_from_desc.argtypes = [P(RtsRxDesc), P(RtsRxSphere)]
+    lib.rts_rx_sphere_from_desc.restype = None
+    lib.rts_result_sizes.argtypes = [P(RtsPulse), P(RtsSizes)]
+    mesh_tail = [P(dbl), P(u32), P(u32), P(u32), P(dbl), P(u32)]
+    lib.rts_rect_mesh.argtypes = [C.c_float] * 6 + mesh_tail
+    lib.rts_sphere_mesh.argtypes = [u32] + [C.c_float] * 4 + mesh_tail
+    lib.rts_file_mesh.argtypes = [C.c_char_p, C.c_char_p] + [C.c_float] * 3 + mesh_tail
+    lib.rts_rotation_matrix.argtypes = [C.c_float] * 3 + [P(dbl)]
+    lib.rts_rotation_matrix.restype = None
+    lib.rts_scene_set_targets.argtypes = [vp, P(RtsTargetMesh), u32]
+    lib.rts_scene_set_poses.argtypes = [vp, P(RtsPose), u32]
+    lib.rts_scene_rebuild.argtypes = [vp]
+    lib.rts_scene_bvh_info.argtypes = [vp, P(RtsBvhInfo)]
+    lib.rts_scene_get_world_vertices.argtypes = [vp, u32, P(dbl)]
+    lib.rts_scene_get_tri_bounds.argtypes = [vp, P(C.c_float)]
+    lib.rts_scene_check_bvh.argtypes = [vp, P(u64)]
+    lib.rts_trace_pulse.argtypes = [vp, P(RtsPulse), u32]
+    lib.rts_get_stats.argtypes = [vp, P(RtsStats)]
+    lib.rts_get_bins.argtypes = [vp, P(RtsBin), u32, P(u32)]
+    lib.rts_get_records.argtypes = [vp, vp, P(i32), P(dbl), P(i32)]
+    lib.rts_bins_device.argtypes = [vp, P(vp), P(u64), P(vp), P(u64)]
+    lib.rts_finalise_bins.argtypes = [vp]
+    lib.rts_aggregate.argtypes = [vp, vp, P(i32), u32, u32, dbl, dbl, P(dbl), P(dbl), P(dbl), P(dbl), P(dbl), P(i32)]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise RtsError(f"rts error {rc}: {load().rts_last_error().decode()}")
+
+
+# ---- pure-host helpers (no GPU needed) --------------------------------------------------------
+
+def rx_sphere_from_desc(position, azimuth, elevation, radius, theta_span, phi_span) -> RtsRxSphere:
+    """Receiver sphere centre and angular window, /root/reference/ray_tracer.cpp:894-918."""
+    d = RtsRxDesc()
+    d.position = (C.c_double * 3)(*[float(v) for v in position])
+    d.azimuth, d.elevation, d.radius = float(azimuth), float(elevation), float(radius)
+    d.theta_span, d.phi_span = float(theta_span), float(phi_span)
+    out = RtsRxSphere()
+    load().rts_rx_sphere_from_desc(C.byref(d), C.byref(out))
+    return out
+
+
+def _mesh_call(fn, *head):
+    nv, nt, nn = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    null_d, null_u = C.POINTER(C.c_double)(), C.POINTER(C.c_uint32)()
+    _check(fn(*head, null_d, C.byref(nv), null_u, C.byref(nt), null_d, C.byref(nn)))
+    v = np.zeros((nv.value, 3)); t = np.zeros((nt.value, 3), dtype=np.uint32); n = np.zeros((nn.value, 3))
+    _check(fn(*head, v.ctypes.data_as(C.POINTER(C.c_double)), C.byref(nv), t.ctypes.data_as(C.POINTER(C.c_uint32)),
+              C.byref(nt), n.ctypes.data_as(C.POINTER(C.c_double)), C.byref(nn)))
+    return v, t, n
+
+
+def rect_mesh(w, h, d, yaw=0.0, pitch=0.0, roll=0.0):
+    """ray_tracer.cpp:226-297 — returns (verts[8,3], tris[12,3], face_normals[12,3])."""
+    return _mesh_call(load().rts_rect_mesh, C.c_float(w), C.c_float(h), C.c_float(d), C.c_float(yaw), C.c_float(pitch), C.c_float(roll))
+
+
+def sphere_mesh(subdivs, radius, yaw=0.0, pitch=0.0, roll=0.0):
+    """ray_tracer.cpp:300-426 — subdivided icosahedron, vertex normals = unit positions."""
+    return _mesh_call(load().rts_sphere_mesh, C.c_uint32(subdivs), C.c_float(radius), C.c_float(yaw), C.c_float(pitch), C.c_float(roll))
+
+
+def file_mesh(v_file, n_file, yaw=0.0, pitch=0.0, roll=0.0):
+    """ray_tracer.cpp:429-504 — text mesh, one triangle per line."""
+    return _mesh_call(load().rts_file_mesh, str(v_file).encode(), str(n_file).encode(), C.c_float(yaw), C.c_float(pitch), C.c_float(roll))
+
+
+def rotation_matrix(yaw, pitch, roll) -> np.ndarray:
+    """Rz*Ry*Rx with the reference's float angles, ray_tracer.cpp:156-162."""
+    R = np.zeros(9)
+    load().rts_rotation_matrix(C.c_float(yaw), C.c_float(pitch), C.c_float(roll), R.ctypes.data_as(C.POINTER(C.c_double)))
+    return R.reshape(3, 3)
+
+
+def result_sizes(spec: PulseSpec, n_targets: int = 0) -> RtsSizes:
+    cp = CPulse(spec, n_targets)
+    out = RtsSizes()
+    _check(load().rts_result_sizes(C.byref(cp.c), C.byref(out)))
+    return out
+
+
+# ---- the engine -------------------------------------------------------------------------------
+
+class Engine:
+    """One GPU's tracer: scene + BVH + wavefront launch (opaque rts_engine handle)."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load()
+        self._h = C.c_void_p()
+        _check(self._lib.rts_create(int(device), C.byref(self._h)))
+        self._scene: Optional[CScene] = None
+        self._pulse: Optional[CPulse] = None
+
+    def close(self):
+        if self._h:
+            self._lib.rts_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # scene -------------------------------------------------------------------------------
+    def set_targets(self, targets: Sequence[Target]):
+        self._scene = CScene(targets)
+        _check(self._lib.rts_scene_set_targets(self._h, self._scene.array, self._scene.n))
+
+    def set_poses(self, rotations: Sequence[Optional[np.ndarray]], translations: Sequence[Sequence[float]]):
+        n = len(translations)
+        arr = (RtsPose * max(1, n))()
+        for k in range(n):
+            R = rotations[k]
+            arr[k].has_rotation = 0 if R is None else 1
+            Rm = np.eye(3) if R is None else np.asarray(R, dtype=np.float64).reshape(3, 3)
+            arr[k].R = (C.c_double * 9)(*Rm.reshape(-1))
+            arr[k].t = (C.c_double * 3)(*[float(v) for v in translations[k]])
+        _check(self._lib.rts_scene_set_poses(self._h, arr, n))
+
+    def rebuild(self):
+        _check(self._lib.rts_scene_rebuild(self._h))
+
+    def bvh_info(self) -> RtsBvhInfo:
+        out = RtsBvhInfo()
+        _check(self._lib.rts_scene_bvh_info(self._h, C.byref(out)))
+        return out
+
+    def world_vertices(self, target: int) -> np.ndarray:
+        out = np.zeros((len(self._scene.targets[target].verts), 3))
+        _check(self._lib.rts_scene_get_world_vertices(self._h, target, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def tri_bounds(self) -> np.ndarray:
+        out = np.zeros((self._scene.total_tris, 6), dtype=np.float32)
+        _check(self._lib.rts_scene_get_tri_bounds(self._h, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def check_bvh(self) -> int:
+        v = C.c_uint64()
+        _check(self._lib.rts_scene_check_bvh(self._h, C.byref(v)))
+        return int(v.value)
+
+    # pulse -------------------------------------------------------------------------------
+    def trace(self, spec: PulseSpec, flags: int = RTS_OUT_BINS) -> dict:
+        self._pulse = CPulse(spec, self._scene.n if self._scene else 0)
+        _check(self._lib.rts_trace_pulse(self._h, C.byref(self._pulse.c), int(flags)))
+        return self.stats()
+
+    def stats(self) -> dict:
+        s = RtsStats()
+        _check(self._lib.rts_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def bins(self) -> np.ndarray:
+        n = C.c_uint32()
+        _check(self._lib.rts_get_bins(self._h, None, 0, C.byref(n)))
+        out = np.zeros(max(1, n.value), dtype=BIN_DTYPE)
+        _check(self._lib.rts_get_bins(self._h, out.ctypes.data_as(C.POINTER(RtsBin)), n.value, C.byref(n)))
+        return out[: n.value]
+
+    def records(self, rcs=True, tri_path=True):
+        spec = self._pulse.spec
+        n, D, W = spec.ray_total, spec.depth_total, spec.tri_cols
+        res = np.zeros(n, dtype=RAY_RECORD)
+        ti = np.zeros((n, max(D, 1)), dtype=np.int32)
+        rc = np.zeros((n, max(D, 1), 2)) if rcs else None
+        tp = np.zeros((n, W), dtype=np.int32) if tri_path else None
+        _check(self._lib.rts_get_records(
+            self._h, res.ctypes.data_as(C.c_void_p), ti.ctypes.data_as(C.POINTER(C.c_int32)),
+            rc.ctypes.data_as(C.POINTER(C.c_double)) if rcs else None,
+            tp.ctypes.data_as(C.POINTER(C.c_int32)) if tri_path else None))
+        return res, ti[:, :D], (rc[:, :D] if rcs else None), tp
+
+    def bins_device(self):
+        """(sums_ptr, n_doubles, mins_ptr, n_u64) of the raw bin accumulators, for an external all-reduce."""
+        sp, mp, ns, nm = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
+        _check(self._lib.rts_bins_device(self._h, C.byref(sp), C.byref(ns), C.byref(mp), C.byref(nm)))
+        return sp.value, int(ns.value), mp.value, int(nm.value)
+
+    def finalise_bins(self):
+        _check(self._lib.rts_finalise_bins(self._h))
+
+    def set_stream(self, cuda_stream: int):
+        _check(self._lib.rts_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def aggregate(self, rx_results: np.ndarray, rx_intersects: np.ndarray, cspeed: float, carrier: float, ray_total: int):
+        """rs::kernel_wrapper contract (aggregation.cu:103-184): returns dict of the written-back arrays."""
+        R = len(rx_results)
+        D = rx_intersects.shape[1] if rx_intersects.ndim == 2 else 0
+        res = np.ascontiguousarray(rx_results.copy())
+        rows = np.ascontiguousarray(rx_intersects, dtype=np.int32)
+        acc = {k: np.zeros(R) for k in ("npath", "power", "doppler", "delay", "phase")}
+        pm = np.full(R, ray_total + 1, dtype=np.int32)  # ray_tracer.cpp:1271
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+        _check(self._lib.rts_aggregate(self._h, res.ctypes.data_as(C.c_void_p), rows.ctypes.data_as(C.POINTER(C.c_int32)), R, D,
+                                       float(cspeed), float(carrier), dp(acc["npath"]), dp(acc["power"]), dp(acc["doppler"]),
+                                       dp(acc["delay"]), dp(acc["phase"]), pm.ctypes.data_as(C.POINTER(C.c_int32))))
+        acc["results"] = res
+        acc["path_match"] = pm
+        return acc
