@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of the ray-tracing radar path on the 1M-triangle scene (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # the CUDA library (librts_b200.so)
+    python bench.py --impl reference --gpus N --steps K ...   # the CPU oracle on the host cores
+
+Workload (config C4 of BASELINE.json / SURVEY.md Appendix C): 1,000,000-triangle synthetic terrain
++ 16 moving targets (8 boxes, 8 icospheres, 4 rotating), maxRefl = 3, 1 receiver.  One step = one
+pulse: per-pulse target poses (host -> device), device rigid transform + BVH refit, all bounce waves
+of a (1, 4096, 4096) ray grid per GPU with fused receiver-bin aggregation, and for N > 1 the NCCL
+all-reduce of the bins (rays are sharded in contiguous slabs of a (1, 4096, 4096*N) launch, scene and
+BVH replicated: weak scaling).  Pulses advance every step, so the movers really move.
+
+value  : steps timed without reading the bins back (inputs resident, CUDA events on the engine's stream)
+e2e    : the same steps through the C-ABI with host buffers, plus the device->host read of the bins
+roofline: the primary-ray wave kernel (k_wave<true,false>), algorithmic bytes per SURVEY.md §8(d)
+cpu_baseline: the oracle (BVH mode, OpenMP) on a strided sample of the same pulse
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GRID = 4096
+B_SEG_1M = 1632.0          # algorithmic bytes per traced segment, T = 1M (SURVEY.md §8d / BASELINE.md §3)
+B_CAPTURE = 40.0           # five fp64 bin updates per captured ray
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                pass
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        out = {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": None, "reasons": [], "samples": len(sm)}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 8:
+                try:
+                    out["sm_max_mhz"] = int(float(r[1]))
+                except ValueError:
+                    pass
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active") and n not in out["reasons"]:
+                        out["reasons"].append(n)
+        return out
+
+
+def build_scene(world):
+    from rts_b200 import scenes
+    t0 = time.time()
+    ms = scenes.terrain_scene(n=N_GRID, n_rx=1, nz=N_GRID * world)
+    log(f"[bench] scene generated in {time.time() - t0:.1f}s: {sum(len(t.tris) for t in ms.base)} triangles, {len(ms.base)} targets")
+    return ms
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    from rts_b200 import dist as rdist
+    from rts_b200 import lib as L
+
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world != args.gpus:
+        log(f"[bench] WORLD_SIZE={world} but --gpus {args.gpus}: using WORLD_SIZE")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    ms = build_scene(world)
+    eng = L.Engine(local)
+    eng.set_targets(ms.base)
+    info = eng.bvh_info()
+    log(f"[bench] rank {rank}: BVH built in {info.ms_build:.2f} ms ({info.n_nodes} nodes)")
+    # all of the engine's work and torch's events on one stream
+    stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(stream)
+    eng.set_stream(stream.cuda_stream)
+    begin, count = rdist.shard_range(ms.spec.rays, rank, world)
+
+    def step(pulse, read_back):
+        eng.set_poses(*ms.poses(pulse))                      # H2D poses + device transform + refit
+        spec = ms.spec_for(pulse)
+        spec.ray_begin, spec.ray_count = begin, count
+        st = eng.trace(spec, L.RTS_OUT_BINS | (L.RTS_NO_FINALISE if world > 1 else 0))
+        if world > 1:
+            rdist.allreduce_bins(eng, dev)
+        if read_back:
+            return st, eng.bins()                            # D2H
+        return st, None
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(k0, k, read_back):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = eng.kernel_launches()
+        t0 = time.perf_counter()
+        e0.record(stream)
+        waves, segs, caps, d2h = [], 0, 0, 0
+        for i in range(k):
+            st, bins = step(k0 + i, read_back)
+            waves.append(eng.wave_profile())
+            segs += st["segments"]
+            caps += st["captured"]
+            if bins is not None:
+                d2h += bins.nbytes
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms_dev = e0.elapsed_time(e1)
+        t = torch.tensor([ms_dev, wall * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return dict(ms=float(t[0]), wall_ms=float(t[1]), waves=waves, segments=segs, captured=caps, d2h=d2h,
+                    launches=eng.kernel_launches() - launches0)
+
+    for w in range(args.warmup):
+        step(w, True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    k0 = args.warmup
+    r_dev = timed(k0, args.steps, read_back=False)
+    r_e2e = timed(k0, args.steps, read_back=True)
+    clk = clocks.stop() if rank == 0 else None
+
+    rays_per_step_total = ms.spec.rays                       # all ranks together
+    value = rays_per_step_total * args.steps / (r_dev["ms"] * 1e-3) / 1e6
+    e2e = rays_per_step_total * args.steps / (r_e2e["ms"] * 1e-3) / 1e6
+
+    # roofline of the dominant kernel (primary wave), rank 0's launches, measured live with CUDA events
+    wave0_ms = [w[0][0] for w in r_dev["waves"]]
+    wave0_seg = [w[0][1] for w in r_dev["waves"]]
+    all_ms = [sum(x[0] for x in w) for w in r_dev["waves"]]
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    avg_ms = sum(wave0_ms) / max(1, len(wave0_ms))
+    avg_seg = sum(wave0_seg) / max(1, len(wave0_seg))
+    achieved = (avg_seg * B_SEG_1M) / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    roof = {"bound": "hbm", "kernel": "k_wave<PRIMARY=true,RECORDS=false>", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+            "bytes_per_segment": B_SEG_1M, "segments_per_launch": int(avg_seg), "ms_per_launch": round(avg_ms, 4),
+            "kernel_share_of_step": round(avg_ms / (r_dev["ms"] / args.steps), 4),
+            "all_waves_ms_per_step": round(sum(all_ms) / max(1, len(all_ms)), 4)}
+    prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(prof):
+        try:
+            roof["traffic"] = json.load(open(prof)).get("k_wave_primary_dram_bytes_per_launch")
+        except Exception:
+            pass
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(ms, args.cpu_stride)
+
+    if rank == 0:
+        seg_per_ray = r_dev["segments"] / (count * args.steps)
+        h2d = len(ms.base) * 112 + len(ms.base) * 24 + 64   # poses + target velocities + receiver
+        out = {
+            "metric": "Mrays/s (3-bounce, 1M-tri scene)", "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r_dev["ms"] / args.steps, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4: 1,000,000-triangle terrain + 16 moving targets, per-pulse pose update + BVH refit, "
+                                   f"(1,{N_GRID},{N_GRID}) rays per GPU per pulse, maxRefl=3, 1 Rx, fused bins"
+                                   + (", ray-sharded, NCCL all-reduce of bins" if world > 1 else ""),
+                       "triangles": int(sum(len(t.tris) for t in ms.base)), "rays_per_step": int(rays_per_step_total),
+                       "segments_per_ray": round(seg_per_ray, 4), "captured_per_step": int(r_dev["captured"] / args.steps),
+                       "l2_policy": "per-step working set (BVH 21 MB + triangles 81 MB + 2.4 GB ray queues written and re-read) exceeds the 126 MB L2",
+                       "parallelism": f"ray-shard x{world}"},
+            "e2e": {"value": round(e2e, 2), "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(r_e2e["d2h"] / args.steps),
+                    "ms_per_step": round(r_e2e["ms"] / args.steps, 4)},
+            "gpu_launches": int(r_dev["launches"]),
+            "roofline": roof,
+            "clocks": clk,
+            "msegments_per_s": round(r_dev["segments"] * world / (r_dev["ms"] * 1e-3) / 1e6, 2),
+        }
+        if cpu is not None:
+            out["cpu_baseline"] = cpu
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    eng.close()
+
+
+def cpu_baseline(ms, stride, pulse=3):
+    """The oracle (port of the reference math, BVH mode, OpenMP over all host cores) on every
+    `stride`-th primary ray of one pulse of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as O
+    spec = ms.spec_for(pulse)
+    spec.ray_begin, spec.ray_count, spec.ray_stride = 0, N_GRID * N_GRID, stride
+    world = ms.world_targets(pulse)
+    t0 = time.time()
+    bins, st = O.trace_bins(world, spec, use_bvh=True)
+    wall = time.time() - t0
+    trace_s = st["ms_trace"] * 1e-3
+    return {"value": round(st["primary_rays"] / trace_s / 1e6, 4), "unit": "Mrays/s", "cores": int(O.oracle().orc_num_threads()),
+            "kind": "port", "sample": f"every {stride}th primary ray of pulse {pulse} ({st['primary_rays']} rays, {st['segments']} segments); "
+                                      f"trace+aggregate {trace_s:.2f}s, oracle BVH build {st['ms_update'] * 1e-3:.2f}s excluded, wall {wall:.1f}s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU-runnable restatement (the oracle port; the reference itself needs
+    OptiX + SOARS and its sources-plus-shim build is exhaustive-search, single-threaded) on the host cores."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as O
+    ms = build_scene(1)
+    stride = args.cpu_stride
+    total_rays, total_s, per = 0, 0.0, []
+    for i in range(args.warmup + args.steps):
+        pulse = i
+        spec = ms.spec_for(pulse)
+        spec.ray_begin, spec.ray_count, spec.ray_stride = 0, N_GRID * N_GRID, stride
+        bins, st = O.trace_bins(ms.world_targets(pulse), spec, use_bvh=True)
+        if i >= args.warmup:
+            total_rays += st["primary_rays"]
+            total_s += st["ms_trace"] * 1e-3
+            per.append(st["ms_trace"])
+    v = total_rays / total_s / 1e6
+    cores = int(O.oracle().orc_num_threads())
+    sample = f"every {stride}th primary ray of a (1,{N_GRID},{N_GRID}) pulse per step ({total_rays // max(1, args.steps)} rays/step), oracle BVH build excluded"
+    out = {"impl": "reference", "metric": "Mrays/s (3-bounce, 1M-tri scene)", "value": round(v, 4), "unit": "Mrays/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sum(per) / len(per), 2), "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "C4: 1,000,000-triangle terrain + 16 moving targets, maxRefl=3, 1 Rx (CPU oracle, bounded sample)"},
+           "cpu_baseline": {"value": round(v, 4), "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": round(v, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-stride", type=int, default=16, help="oracle sample: every n-th primary ray")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

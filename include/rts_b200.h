@@ -112,6 +112,11 @@ int rts_scene_check_bvh(rts_engine *e, uint64_t *violations);
 /* ---- one pulse (replaces rtContextLaunch3D + the result hand-off, ray_tracer.cpp:1165-1258) ---- */
 int rts_trace_pulse(rts_engine *e, const rts_pulse *pulse, uint32_t flags);
 int rts_get_stats(rts_engine *e, rts_stats *out);
+/* Per-bounce-wave profile of the last pulse: device milliseconds (CUDA events on the engine's stream) and
+ * the number of ray segments each wave traced, summed over ray batches.  *n = number of waves. */
+int rts_get_wave_profile(rts_engine *e, uint32_t cap, float *ms, uint64_t *segments, uint32_t *n);
+/* Cumulative number of CUDA kernels this engine has launched (every <<<>>> of the library). */
+int rts_kernel_launches(rts_engine *e, uint64_t *out);
 /* RTS_OUT_BINS: non-empty bins sorted by (rx, path). *n is the total even when cap is smaller. */
 int rts_get_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n);
 /* RTS_OUT_RECORDS: copy out the reference-shaped arrays; any pointer may be NULL.

@@ -13,6 +13,7 @@
 // ("parity unpinned" for exactly those functions).
 #include "oracle_common.h"
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <map>
 #include <omp.h>
@@ -810,9 +811,11 @@ extern "C" int orc_trace_bins(const rts_target_mesh *targets, uint32_t n_targets
 {
     if (!pulse || (!targets && n_targets)) return -1;
     if (pulse->max_refl + (pulse->max_refr ? 2u : 0u) > RTS_MAX_DEPTH) return -2;
+    const auto t_start = std::chrono::steady_clock::now();
     Scene scene;
     build_scene(scene, targets, n_targets);
     if (use_bvh && scene.total_tris) build_bvh(scene);
+    const auto t_built = std::chrono::steady_clock::now();
     const bool bvh = use_bvh && scene.has_bvh;
     Launch L;
     setup_launch(L, scene, pulse);
@@ -913,6 +916,10 @@ extern "C" int orc_trace_bins(const rts_target_mesh *targets, uint32_t n_targets
         stats->primary_rays = nrays; stats->segments = segs; stats->hits = hits; stats->shaded_hits = shaded;
         stats->captured = captured; stats->multi_captured = multi; stats->edge_rays = edges; stats->refracted = refr;
         stats->n_bins = n;
+        const auto t_end = std::chrono::steady_clock::now();
+        stats->ms_update = std::chrono::duration<float, std::milli>(t_built - t_start).count();   // oracle BVH build
+        stats->ms_trace = std::chrono::duration<float, std::milli>(t_end - t_built).count();      // trace + aggregate
+        stats->ms_total = stats->ms_update + stats->ms_trace;
     }
     return 0;
 }

@@ -219,12 +219,12 @@ __global__ void k_scatter(rts_ray_record *res, uint32_t R, const uint32_t *__res
 int agg_fill_records(rts_engine *e, uint64_t ray_total, uint32_t D, uint32_t W)
 {
     const unsigned bs = 256;
-    k_fill_records<<<blocks_for(ray_total, bs), bs, 0, e->stream>>>(e->d_results, ray_total);
+    { k_fill_records<<<blocks_for(ray_total, bs), bs, 0, e->stream>>>(e->d_results, ray_total); e->launches++; }
     if (D) {
-        k_fill_i32<<<blocks_for(ray_total * D, bs), bs, 0, e->stream>>>(e->d_targ_intersect, ray_total * D, -1);
-        k_fill_f64<<<blocks_for(ray_total * D * 2, bs), bs, 0, e->stream>>>(e->d_rcs_angle, ray_total * D * 2, -1000000.0);
+        { k_fill_i32<<<blocks_for(ray_total * D, bs), bs, 0, e->stream>>>(e->d_targ_intersect, ray_total * D, -1); e->launches++; }
+        { k_fill_f64<<<blocks_for(ray_total * D * 2, bs), bs, 0, e->stream>>>(e->d_rcs_angle, ray_total * D * 2, -1000000.0); e->launches++; }
     }
-    k_fill_i32<<<blocks_for(ray_total * W, bs), bs, 0, e->stream>>>(e->d_tri_path, ray_total * W, -1);
+    { k_fill_i32<<<blocks_for(ray_total * W, bs), bs, 0, e->stream>>>(e->d_tri_path, ray_total * W, -1); e->launches++; }
     RTS_CUDA(cudaGetLastError());
     return RTS_OK;
 }
@@ -243,7 +243,7 @@ int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
     RTS_CUDA(cudaMemsetAsync(rx_sums, 0, sizeof(double) * 5 * n_rx, e->stream));
     RTS_CUDA(cudaMemsetAsync(rx_mins, 0xff, sizeof(unsigned long long) * n_rx, e->stream));
     dim3 grid((unsigned)std::min<uint64_t>(64, (per_rx + 255) / 256), n_rx);
-    k_rx_totals<<<grid, 256, 0, e->stream>>>(e->d_bin_sums, e->d_bin_mins, per_rx, n_rx, rx_sums, rx_mins);
+    { k_rx_totals<<<grid, 256, 0, e->stream>>>(e->d_bin_sums, e->d_bin_mins, per_rx, n_rx, rx_sums, rx_mins); e->launches++; }
     // compact non-empty bins
     const uint64_t want = std::max<uint64_t>(cap, 1);
     if (e->bins_out_alloc < want) {
@@ -254,8 +254,8 @@ int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
     }
     if (!e->d_bins_out_count) RTS_CUDA(cudaMalloc(&e->d_bins_out_count, sizeof(uint32_t)));
     RTS_CUDA(cudaMemsetAsync(e->d_bins_out_count, 0, sizeof(uint32_t), e->stream));
-    k_emit_bins<<<blocks_for(nb, 256), 256, 0, e->stream>>>(e->d_bin_sums, e->d_bin_mins, nb, per_rx, B, D, rx_sums, rx_mins,
-                                                           e->d_bins_out, e->d_bins_out_count, cap);
+    { k_emit_bins<<<blocks_for(nb, 256), 256, 0, e->stream>>>(e->d_bin_sums, e->d_bin_mins, nb, per_rx, B, D, rx_sums, rx_mins,
+                                                           e->d_bins_out, e->d_bins_out_count, cap); e->launches++; }
     RTS_CUDA(cudaGetLastError());
     uint32_t count = 0;
     RTS_CUDA(cudaMemcpyAsync(&count, e->d_bins_out_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
@@ -328,11 +328,11 @@ int agg_kernel_wrapper(rts_engine *e, rts_ray_record *rx_results, const int32_t 
     AGG_CUDA(cudaMemsetAsync(d_rs, 0, sizeof(double) * 5 * (size_t)n_rx_slots, st));
     {
         const unsigned bs = 256, gb = blocks_for(R, bs);
-        k_group<<<gb, bs, 0, st>>>(d_res, d_rows, R, D, d_table, table_size - 1, d_slot);
-        k_accumulate<<<gb, bs, 0, st>>>(d_res, R, d_slot, cspeed, carrier, d_gs, d_gmin, d_rs, d_rmin, n_rx_slots);
-        k_scatter<<<gb, bs, 0, st>>>(d_res, R, d_slot, d_gs, d_gmin, d_rs, d_rmin, n_rx_slots, d_acc + 0 * (size_t)R,
+        { k_group<<<gb, bs, 0, st>>>(d_res, d_rows, R, D, d_table, table_size - 1, d_slot); e->launches++; }
+        { k_accumulate<<<gb, bs, 0, st>>>(d_res, R, d_slot, cspeed, carrier, d_gs, d_gmin, d_rs, d_rmin, n_rx_slots); e->launches++; }
+        { k_scatter<<<gb, bs, 0, st>>>(d_res, R, d_slot, d_gs, d_gmin, d_rs, d_rmin, n_rx_slots, d_acc + 0 * (size_t)R,
                                      d_acc + 1 * (size_t)R, d_acc + 2 * (size_t)R, d_acc + 3 * (size_t)R,
-                                     d_acc + 4 * (size_t)R, d_pm);
+                                     d_acc + 4 * (size_t)R, d_pm); e->launches++; }
         AGG_CUDA(cudaGetLastError());
     }
     AGG_CUDA(cudaMemcpyAsync(rx_results, d_res, sizeof(rts_ray_record) * (size_t)R, cudaMemcpyDeviceToHost, st));

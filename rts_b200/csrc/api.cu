@@ -79,6 +79,8 @@ extern "C" int rts_create(int device, rts_engine **out)
     }
     e->stream = e->own_stream;
     for (auto &ev : e->ev) cudaEventCreate(&ev);
+    for (auto &ev : e->wave_ev) cudaEventCreate(&ev);
+    cudaMalloc(&e->d_wave_segs, sizeof(unsigned long long) * 32);
     cudaMalloc(&e->d_counts, sizeof(unsigned long long) * 64);
     cudaMalloc(&e->d_counters, sizeof(Counters));
     cudaMalloc(&e->d_rx, sizeof(RxDev) * RTS_MAX_RX);
@@ -112,6 +114,8 @@ extern "C" void rts_destroy(rts_engine *e)
                     e->d_results, e->d_targ_intersect, e->d_tri_path, e->d_rcs_angle};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->wave_ev) if (ev) cudaEventDestroy(ev);
+    if (e->d_wave_segs) cudaFree(e->d_wave_segs);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
 }
@@ -426,6 +430,11 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     }
     const uint32_t max_waves = p->max_refl + 1 + (rMax ? 2 : 0); // longest chain: see DESIGN.md (wave count)
     uint64_t waves = 0;
+    P.wave_segs = e->d_wave_segs;
+    RTS_CUDA(cudaMemsetAsync(e->d_wave_segs, 0, sizeof(unsigned long long) * 32, st));
+    for (int w = 0; w < 32; w++) e->wave_ms[w] = 0.f;
+    e->n_waves = std::min<uint32_t>(max_waves, 31);
+    const bool single_batch = n_primary_total <= batch;
     for (uint64_t done = 0; done < n_primary_total; done += batch) {
         const uint64_t nb = std::min<uint64_t>(batch, n_primary_total - done);
         // d_counts: [0..31] queue counts per wave, [32..63] work counters per wave
@@ -437,10 +446,13 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
             Q.in_count = e->d_counts + w;
             Q.out_count = e->d_counts + w + 1;
             Q.work_counter = e->d_counts + 32 + w;
+            Q.wave_index = w;
+            if (single_batch) cudaEventRecord(e->wave_ev[w], st);
             int rc = trace_launch_wave(e, Q, w == 0, records);
             if (rc) return rc;
             waves++;
         }
+        if (single_batch) cudaEventRecord(e->wave_ev[e->n_waves], st);
     }
     cudaEventRecord(e->ev[1], st);
     Counters c;
@@ -448,6 +460,9 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     RTS_CUDA(cudaStreamSynchronize(st));
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+    RTS_CUDA(cudaMemcpy(e->wave_segs, e->d_wave_segs, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost));
+    if (single_batch && n_primary_total)
+        for (uint32_t w = 0; w < e->n_waves; w++) cudaEventElapsedTime(&e->wave_ms[w], e->wave_ev[w], e->wave_ev[w + 1]);
 
     rts_stats &s = e->stats;
     memset(&s, 0, sizeof(s));
@@ -466,6 +481,25 @@ extern "C" int rts_get_stats(rts_engine *e, rts_stats *out)
 {
     if (!e || !out) return rts_fail(RTS_ERR_ARG, "NULL argument");
     *out = e->stats;
+    return RTS_OK;
+}
+
+extern "C" int rts_get_wave_profile(rts_engine *e, uint32_t cap, float *ms, uint64_t *segments, uint32_t *n)
+{
+    if (!e || !n) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    if (!e->have_pulse) return rts_fail(RTS_ERR_STATE, "no pulse traced yet");
+    *n = e->n_waves;
+    for (uint32_t w = 0; w < e->n_waves && w < cap; w++) {
+        if (ms) ms[w] = e->wave_ms[w];
+        if (segments) segments[w] = e->wave_segs[w];
+    }
+    return RTS_OK;
+}
+
+extern "C" int rts_kernel_launches(rts_engine *e, uint64_t *out)
+{
+    if (!e || !out) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    *out = e->launches;
     return RTS_OK;
 }
 

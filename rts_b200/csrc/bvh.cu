@@ -335,18 +335,18 @@ int bvh_update_world(rts_engine *e)
 {
     const unsigned bs = 256;
     if (e->n_verts)
-        k_transform<<<blocks_for(e->n_verts, bs), bs, 0, e->stream>>>(e->d_base_verts, e->d_world_verts, e->d_vert_target,
-                                                                     e->d_poses, e->n_verts, 1);
+        { k_transform<<<blocks_for(e->n_verts, bs), bs, 0, e->stream>>>(e->d_base_verts, e->d_world_verts, e->d_vert_target,
+                                                                     e->d_poses, e->n_verts, 1); e->launches++; }
     if (e->n_normals)
-        k_transform<<<blocks_for(e->n_normals, bs), bs, 0, e->stream>>>(e->d_base_normals, e->d_world_normals,
-                                                                       e->d_norm_target, e->d_poses, e->n_normals, 0);
+        { k_transform<<<blocks_for(e->n_normals, bs), bs, 0, e->stream>>>(e->d_base_normals, e->d_world_normals,
+                                                                       e->d_norm_target, e->d_poses, e->n_normals, 0); e->launches++; }
     // scene box reset: lo = +inf, hi = -inf in ordered encoding
     static const unsigned init_box[6] = {0xff800000u, 0xff800000u, 0xff800000u, 0x007fffffu, 0x007fffffu, 0x007fffffu};
     RTS_CUDA(cudaMemcpyAsync(e->d_scene_box, init_box, sizeof(init_box), cudaMemcpyHostToDevice, e->stream));
     if (e->n_tris)
-        k_tri_boxes<<<blocks_for(e->n_tris, bs), bs, 0, e->stream>>>(e->d_world_verts, e->d_tris, e->d_tri_target,
+        { k_tri_boxes<<<blocks_for(e->n_tris, bs), bs, 0, e->stream>>>(e->d_world_verts, e->d_tris, e->d_tri_target,
                                                                     e->d_t_vert_off, e->d_tri_box,
-                                                                    (unsigned *)e->d_scene_box, e->n_tris);
+                                                                    (unsigned *)e->d_scene_box, e->n_tris); e->launches++; }
     RTS_CUDA(cudaGetLastError());
     return RTS_OK;
 }
@@ -356,14 +356,14 @@ static int fit_and_pack(rts_engine *e)
     const unsigned bs = 256;
     const int n = (int)e->n_tris;
     if (n == 0) { e->root_ref = 0; return RTS_OK; }
-    k_tri_records<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_world_verts, e->d_tris, e->d_tri_target, e->d_t_vert_off,
-                                                          e->d_order, e->d_trirec, n);
+    { k_tri_records<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_world_verts, e->d_tris, e->d_tri_target, e->d_t_vert_off,
+                                                          e->d_order, e->d_trirec, n); e->launches++; }
     if (n >= 2) {
         RTS_CUDA(cudaMemsetAsync(e->d_fit_flags, 0, sizeof(uint32_t) * (size_t)n, e->stream));
-        k_fit<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_children, e->d_parent, e->d_order, e->d_tri_box, e->d_node_box,
-                                                      e->d_fit_flags, n);
-        k_pack<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_children, e->d_range, e->d_order, e->d_tri_box,
-                                                           e->d_node_box, e->d_nodes, n);
+        { k_fit<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_children, e->d_parent, e->d_order, e->d_tri_box, e->d_node_box,
+                                                      e->d_fit_flags, n); e->launches++; }
+        { k_pack<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_children, e->d_range, e->d_order, e->d_tri_box,
+                                                           e->d_node_box, e->d_nodes, n); e->launches++; }
     }
     RTS_CUDA(cudaGetLastError());
     e->root_ref = n <= RTS_LEAF_MAX ? ~((0 << 3) | (n - 1)) : 0;
@@ -378,15 +378,15 @@ int bvh_build(rts_engine *e)
     int rc = bvh_update_world(e);
     if (rc) return rc;
     if (n > 0) {
-        k_morton<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_tri_box, (const unsigned *)e->d_scene_box, e->d_morton,
-                                                         e->d_order_in, n);
+        { k_morton<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_tri_box, (const unsigned *)e->d_scene_box, e->d_morton,
+                                                         e->d_order_in, n); e->launches++; }
         size_t bytes = e->cub_temp_bytes;
         RTS_CUDA(cub::DeviceRadixSort::SortPairs(e->d_cub_temp, bytes, e->d_morton, e->d_morton_sorted, e->d_order_in,
                                                  e->d_order, n, 0, 63, e->stream));
-        k_leaf_of_tri<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_order, e->d_leaf_of_tri, n);
+        { k_leaf_of_tri<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_order, e->d_leaf_of_tri, n); e->launches++; }
         if (n >= 2)
-            k_hierarchy<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_morton_sorted, n, e->d_children, e->d_range,
-                                                                    e->d_parent);
+            { k_hierarchy<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_morton_sorted, n, e->d_children, e->d_range,
+                                                                    e->d_parent); e->launches++; }
         RTS_CUDA(cudaGetLastError());
     }
     rc = fit_and_pack(e);
@@ -426,8 +426,8 @@ int bvh_check(rts_engine *e, uint64_t *violations)
     unsigned long long v = 0;
     if (n >= 2) {
         RTS_CUDA(cudaMemsetAsync(e->d_violations, 0, sizeof(unsigned long long), e->stream));
-        k_check<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->d_parent, e->d_order, e->d_tri_box, e->d_node_box, n,
-                                                          e->d_violations);
+        { k_check<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->d_parent, e->d_order, e->d_tri_box, e->d_node_box, n,
+                                                          e->d_violations); e->launches++; }
         RTS_CUDA(cudaGetLastError());
         RTS_CUDA(cudaMemcpyAsync(&v, e->d_violations, sizeof(v), cudaMemcpyDeviceToHost, e->stream));
         RTS_CUDA(cudaStreamSynchronize(e->stream));

@@ -99,6 +99,8 @@ struct WaveParams {
     double *rcs_angle;
     int32_t *tri_path;
     Counters *counters;
+    unsigned long long *wave_segs;  // [32] segments traced per wave index
+    uint32_t wave_index;
 };
 
 // ---- engine ---------------------------------------------------------------------------------
@@ -107,6 +109,12 @@ struct rts_engine {
     int num_sms = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev[6] = {};
+    cudaEvent_t wave_ev[34] = {};
+    unsigned long long *d_wave_segs = nullptr;
+    float wave_ms[32] = {};
+    unsigned long long wave_segs[32] = {};
+    uint32_t n_waves = 0;
+    uint64_t launches = 0;
 
     // host-side scene meta
     uint32_t n_targets = 0, n_tris = 0, n_verts = 0, n_normals = 0;

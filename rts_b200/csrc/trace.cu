@@ -537,6 +537,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK) k_wave(const __grid_constant__
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n_in = PRIMARY ? P.n_primary : *P.in_count;
     Local L = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.wave_segs + P.wave_index, n_in);
     for (;;) {
         unsigned long long base = 0;
         if (lane == 0) base = atomicAdd(P.work_counter, 32ull);
@@ -614,6 +615,7 @@ int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool rec
         else k_wave<false, false><<<grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
     }
     RTS_CUDA(cudaGetLastError());
+    e->launches++;
     return RTS_OK;
 }
 

@@ -1,0 +1,71 @@
+"""Multi-GPU plumbing: one process per GPU (torchrun), scene and BVH replicated, primary rays
+sharded in contiguous slabs, receiver bins reduced with one all-reduce pair per pulse.
+
+The reference has no multi-GPU path; primary rays are independent
+(/root/reference/ray_tracer.cu:151, 227-253) and the only cross-ray step is the commutative
+aggregation (/root/reference/aggregation.cu:56-69), so the exchange is:
+    all_reduce(SUM, float64) over bins[n][5] = {npath, sum sqrt(P), sum delay, sum phase, sum Doppler}
+    all_reduce(MIN, int64)   over the smallest result-slot index per bin (orders like d_pathMatch)
+torch.distributed (NCCL on GPUs, gloo in the CPU tests) is the transport; the bins live in the
+library's own device memory and are wrapped zero-copy.
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import numpy as np
+
+
+def shard_range(n_rays: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous slab [begin, begin+count) of the primary-ray index space for `rank`."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    base, rem = divmod(int(n_rays), world)
+    begin = rank * base + min(rank, rem)
+    count = base + (1 if rank < rem else 0)
+    return begin, count
+
+
+class _DevArray:
+    """Minimal __cuda_array_interface__ holder so torch can alias library-owned device memory."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def bins_as_tensors(engine, device):
+    """Zero-copy torch views of the engine's raw bin accumulators: (sums float64[n*5], mins int64[n])."""
+    import torch
+
+    sp, ns, mp, nm = engine.bins_device()
+    sums = torch.as_tensor(_DevArray(sp, ns, "<f8"), device=device)
+    mins = torch.as_tensor(_DevArray(mp, nm, "<i8"), device=device)
+    return sums, mins
+
+
+def allreduce_bin_tensors(sums, mins, group=None):
+    """The exchange step. `mins` holds uint64 slot indices (< 2^63) viewed as int64, so MIN is order-preserving;
+    empty bins hold 0xFFFF…F = -1 as int64, which must not win: map to int64 max before reducing."""
+    import torch
+    import torch.distributed as dist
+
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    big = torch.iinfo(torch.int64).max
+    mins.masked_fill_(mins < 0, big)
+    dist.all_reduce(mins, op=dist.ReduceOp.MIN, group=group)
+    mins.masked_fill_(mins == big, -1)
+    return sums, mins
+
+
+def allreduce_bins(engine, device, group=None):
+    """All-reduce the engine's bins in place over NCCL, then mark them final (myKernel2 runs at collection)."""
+    sums, mins = bins_as_tensors(engine, device)
+    allreduce_bin_tensors(sums, mins, group)
+    engine.finalise_bins()
+
+
+def merge_bins_numpy(parts):
+    """CPU statement of the same reduction for tests: list of (sums[n,5], mins[n] uint64) -> merged."""
+    sums = np.sum([p[0] for p in parts], axis=0)
+    mins = np.min([p[1] for p in parts], axis=0)
+    return sums, mins

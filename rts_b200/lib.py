@@ -49,7 +49,7 @@ EXPORTS = [
     "rts_rx_sphere_from_desc", "rts_result_sizes", "rts_rect_mesh", "rts_sphere_mesh", "rts_file_mesh",
     "rts_rotation_matrix", "rts_scene_set_targets", "rts_scene_set_poses", "rts_scene_rebuild", "rts_scene_bvh_info",
     "rts_scene_get_world_vertices", "rts_scene_get_tri_bounds", "rts_scene_check_bvh", "rts_trace_pulse",
-    "rts_get_stats", "rts_get_bins", "rts_get_records", "rts_bins_device", "rts_finalise_bins", "rts_aggregate",
+    "rts_get_stats", "rts_get_wave_profile", "rts_kernel_launches", "rts_get_bins", "rts_get_records", "rts_bins_device", "rts_finalise_bins", "rts_aggregate",
 ]
 
 _lib = None
@@ -90,6 +90,8 @@ def load() -> C.CDLL:
     lib.rts_scene_check_bvh.argtypes = [vp, P(u64)]
     lib.rts_trace_pulse.argtypes = [vp, P(RtsPulse), u32]
     lib.rts_get_stats.argtypes = [vp, P(RtsStats)]
+    lib.rts_get_wave_profile.argtypes = [vp, u32, P(C.c_float), P(u64), P(u32)]
+    lib.rts_kernel_launches.argtypes = [vp, P(u64)]
     lib.rts_get_bins.argtypes = [vp, P(RtsBin), u32, P(u32)]
     lib.rts_get_records.argtypes = [vp, vp, P(i32), P(dbl), P(i32)]
     lib.rts_bins_device.argtypes = [vp, P(vp), P(u64), P(vp), P(u64)]
@@ -234,6 +236,17 @@ class Engine:
         s = RtsStats()
         _check(self._lib.rts_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def wave_profile(self):
+        """[(ms, segments)] per bounce wave of the last pulse (CUDA events on the engine's stream)."""
+        ms = (C.c_float * 32)(); seg = (C.c_uint64 * 32)(); n = C.c_uint32()
+        _check(self._lib.rts_get_wave_profile(self._h, 32, ms, seg, C.byref(n)))
+        return [(float(ms[i]), int(seg[i])) for i in range(n.value)]
+
+    def kernel_launches(self) -> int:
+        v = C.c_uint64()
+        _check(self._lib.rts_kernel_launches(self._h, C.byref(v)))
+        return int(v.value)
 
     def bins(self) -> np.ndarray:
         n = C.c_uint32()

@@ -130,8 +130,8 @@ def ship(n: int = 4096, hull_res: int = 200, cubic: bool = False) -> Tuple[List[
         ang = math.radians(-15.0 + 10.0 * k)
         pos = np.array([-2000.0 * math.cos(ang), 2000.0 * math.sin(ang) + 40.0 * (k - 1.5), 200.0 + 60.0 * k])
         back = np.array([0.0, 0.0, 5.0]) - pos
-        rx.append(_rx(pos, math.atan2(back[1], back[0]) + math.pi, -math.atan2(back[2], math.hypot(back[0], back[1])), 25.0,
-                      1.2, 1.2))
+        rx.append(_rx(pos, math.atan2(back[1], back[0]) + math.pi, -math.atan2(back[2], math.hypot(back[0], back[1])), 150.0,
+                      2.4, 2.4))
     grid = (n, n, n) if cubic else (1, n, n)
     spec = PulseSpec(grid=grid, max_refl=3, max_refr=2, interpolate_smooth=True, tx_origin=tuple(tx), tx_dir=(az, el),
                      tx_span=(0.07, 0.012, 0.0), rx=rx, targ_vel=np.array([[8.0, 1.0, 0.0], [8.0, 1.0, 0.0], [0.0, 0, 0]]))
@@ -246,9 +246,10 @@ class MovingScene:
 
 
 def terrain_scene(n: int = 4096, cells_x: int = 1000, cells_y: int = 500, n_rx: int = 1, movers: int = 16,
-                  nz: Optional[int] = None, seed: int = 0x52545301) -> MovingScene:
-    """C4/C5: 1M-triangle terrain (static target 0) + boxes and spheres moving over it."""
-    cell = 4.0
+                  nz: Optional[int] = None, seed: int = 0x52545301, extent_x: float = 4000.0) -> MovingScene:
+    """C4/C5: terrain patch of extent_x by extent_x*cells_y/cells_x metres (static target 0; 1000 x 500 cells of
+    4 m = 1,000,000 triangles by default) + boxes and spheres moving over it."""
+    cell = extent_x / cells_x
     terr = terrain_mesh(cells_x, cells_y, cell, 30.0, seed)
     base = [terr]
     K = movers + 1

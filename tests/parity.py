@@ -1,0 +1,89 @@
+"""Shared comparison helpers for the parity tests (CUDA library vs CPU oracle)."""
+from __future__ import annotations
+
+import numpy as np
+
+import oracle_api as O
+from rts_b200 import lib as L
+
+#: relative tolerance of the per-bin fp64 sums (BASELINE.json acceptance: 1e-5)
+SUM_RTOL = 1e-5
+#: rcs angles come from fp64 atan2 (CUDA libdevice vs glibc: a few ulp)
+RCS_ATOL = 1e-12
+
+
+def compare_records(gpu, orc, spec, label=""):
+    """gpu = (results, targ_intersect, rcs_angle, tri_path) from Engine.records(); orc = oracle_api.trace() dict.
+    Returns a dict of mismatch counts; rays flagged as receiver-window edge cases by the oracle are
+    excluded from the `received`-dependent fields and counted separately."""
+    res, ti, rcs, tp = gpu
+    R3, M = spec.rays, spec.slots
+    edge = orc["edge"]
+    window_edge = (edge & O.EDGE_WINDOW) != 0
+    slot_edge = np.tile(window_edge, M)
+    out = {"label": label, "rays": int(R3), "window_edge_rays": int(window_edge.sum()),
+           "tri_edge_rays": int(((edge & O.EDGE_TRI) != 0).sum()), "tie_rays": int(((edge & O.EDGE_TIE) != 0).sum())}
+    o = orc["results"]
+    out["tri_path_mismatch"] = int((tp != orc["tri_path"]).any(axis=1).sum())
+    out["targ_intersect_mismatch"] = int((ti != orc["targ_intersect"]).any(axis=1).sum()) if spec.depth_total else 0
+    for f in ("reflDepth", "refrDepth"):
+        out[f + "_mismatch"] = int((res[f] != o[f]).sum())
+    # fields independent of capture: bit-exact everywhere
+    for f in ("firstHitPoint", "prevHitPoint"):
+        out[f + "_mismatch"] = int((res[f].view(np.uint64) != o[f].view(np.uint64)).any(axis=1).sum())
+    ok = ~slot_edge
+    out["received_mismatch"] = int((res["received"][ok] != o["received"][ok]).sum())
+    same_rx = ok & (res["received"] == o["received"])
+    for f in ("rayLength", "power", "doppler"):
+        out[f + "_mismatch"] = int((res[f][same_rx].view(np.uint64) != o[f][same_rx].view(np.uint64)).sum())
+    for f in ("maxRayIndex", "end"):
+        out[f + "_mismatch"] = int((res[f] != o[f]).sum())
+    out["untouched_mismatch"] = int((res["rayDirection"] != o["rayDirection"]).any(axis=1).sum() + (res["refrIndex"] != o["refrIndex"]).any(axis=1).sum())
+    if rcs is not None and spec.depth_total:
+        d = np.abs(rcs - orc["rcs_angle"])
+        out["rcs_angle_max_abs_diff"] = float(d.max()) if d.size else 0.0
+    return out
+
+
+def assert_records_equal(cmp):
+    bad = {k: v for k, v in cmp.items() if k.endswith("_mismatch") and v}
+    assert not bad, f"{cmp['label']}: {bad} (edge rays: window={cmp['window_edge_rays']} tri={cmp['tri_edge_rays']})"
+    if "rcs_angle_max_abs_diff" in cmp:
+        assert cmp["rcs_angle_max_abs_diff"] <= RCS_ATOL, cmp
+
+
+def compare_bins(gbins, obins, rtol=SUM_RTOL):
+    """Both arrays sorted by (rx, path). Returns dict with key/count equality and max relative errors."""
+    out = {"n_gpu": len(gbins), "n_oracle": len(obins)}
+    if len(gbins) != len(obins):
+        out["keys_equal"] = False
+        return out
+    keys_equal = bool(np.array_equal(gbins["rx"], obins["rx"]) and np.array_equal(gbins["path"], obins["path"]))
+    out["keys_equal"] = keys_equal
+    out["npath_equal"] = bool(np.array_equal(gbins["npath"], obins["npath"]))
+    out["min_slot_equal"] = bool(np.array_equal(gbins["min_slot"], obins["min_slot"]))
+    out["direct_equal"] = bool(np.array_equal(gbins["direct"], obins["direct"]))
+    for f in ("sum_sqrt_power", "sum_delay", "sum_phase", "sum_doppler", "power", "delay", "phase", "doppler"):
+        a, b = gbins[f], obins[f]
+        denom = np.maximum(np.abs(b), 1e-300)
+        rel = np.abs(a - b) / denom
+        rel = np.where((a == 0) & (b == 0), 0.0, rel)
+        out[f + "_max_rel"] = float(rel.max()) if len(rel) else 0.0
+    return out
+
+
+def assert_bins_close(cmp, rtol=SUM_RTOL, exact_counts=True):
+    assert cmp.get("keys_equal"), cmp
+    if exact_counts:
+        assert cmp["npath_equal"] and cmp["min_slot_equal"] and cmp["direct_equal"], cmp
+    for k, v in cmp.items():
+        if k.endswith("_max_rel"):
+            # Doppler sums of static scenes are exactly 0 on both sides; otherwise relative
+            assert v <= rtol, (k, v, cmp)
+
+
+def run_gpu_records(engine, targets, spec, flags=None):
+    engine.set_targets(targets)
+    f = (L.RTS_OUT_RECORDS | L.RTS_OUT_BINS) if flags is None else flags
+    stats = engine.trace(spec, f)
+    return engine.records(), engine.bins(), stats
