@@ -59,7 +59,10 @@ typedef struct rts_bvh_info {
     uint32_t n_tris, n_nodes, root_is_leaf, max_leaf;
     float    scene_lo[3], scene_hi[3];
     float    ms_build, ms_refit;
-    double   sah_cost;     /* surface-area-heuristic cost of the current tree (diagnostic) */
+    double   sah_cost;     /* sum of internal-node box areas of the current tree (m^2)                 */
+    double   sah_at_build; /* the same when the topology was last built; refit rebuilds beyond 1.2 x   */
+    uint32_t builds;       /* number of full builds so far                                             */
+    uint32_t _pad;
 } rts_bvh_info;
 
 /* ---- life cycle (replaces rtContextCreate / rtContextDestroy, ray_tracer.cpp:532-534,1358) ---- */
@@ -97,7 +100,8 @@ void rts_rotation_matrix(float yaw, float pitch, float roll, double R[9]);
  *      ray_tracer.cpp:1017-1133, and OptiX's "Bvh" builder) ---- */
 /* Upload all targets in their base pose and build the BVH (Morton LBVH) on the device. */
 int rts_scene_set_targets(rts_engine *e, const rts_target_mesh *targets, uint32_t n_targets);
-/* Per-pulse target motion (ray_tracer.cpp:936-1014): transform on the device, refit the BVH. */
+/* Per-pulse target motion (ray_tracer.cpp:936-1014): transform on the device, refit the BVH; falls back to
+ * a full rebuild when the refitted tree's SAH cost has drifted more than 20 % above its as-built cost. */
 int rts_scene_set_poses(rts_engine *e, const rts_pose *poses, uint32_t n_targets);
 /* Full rebuild at the current poses (what the reference does every pulse, ray_tracer.cpp:1126-1130). */
 int rts_scene_rebuild(rts_engine *e);

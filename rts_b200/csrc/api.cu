@@ -231,6 +231,9 @@ extern "C" int rts_scene_bvh_info(rts_engine *e, rts_bvh_info *out)
 {
     if (!e || !out) return rts_fail(RTS_ERR_ARG, "NULL argument");
     *out = e->bvh_info;
+    out->sah_at_build = e->sah_at_build;
+    out->builds = e->builds;
+    out->_pad = 0;
     return RTS_OK;
 }
 

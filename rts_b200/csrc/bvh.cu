@@ -113,11 +113,15 @@ __global__ void k_morton(const float *__restrict__ tri_box, const unsigned *__re
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     unsigned long long code = 0;
+    // one scale for all three axes (cubic Morton cells): a flat scene such as a height field must not
+    // spend every third split on its thin axis
+    float ext = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; a++) ext = fmaxf(ext, ord2f(scene_box[3 + a]) - ord2f(scene_box[a]));
 #pragma unroll
     for (int a = 0; a < 3; a++) {
-        float lo = ord2f(scene_box[a]), hi = ord2f(scene_box[3 + a]);
+        float lo = ord2f(scene_box[a]);
         float c = 0.5f * (tri_box[6 * (size_t)i + a] + tri_box[6 * (size_t)i + 3 + a]);
-        float ext = hi - lo;
         float u = ext > 0.f ? (c - lo) / ext : 0.f;
         u = fminf(fmaxf(u, 0.f), 1.f);
         unsigned long long q = (unsigned long long)(u * 2097151.0f);
@@ -229,9 +233,20 @@ __global__ void k_fit(const int2 *__restrict__ children, const int32_t *__restri
 
 __global__ void k_pack(const int2 *__restrict__ children, const int2 *__restrict__ range,
                        const uint32_t *__restrict__ order, const float *__restrict__ tri_box,
-                       const float *__restrict__ node_box, BvhNode *__restrict__ nodes, int n)
+                       const float *__restrict__ node_box, BvhNode *__restrict__ nodes, int n, double *sah)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    // surface-area-heuristic cost of the tree = sum of internal-node box areas (relative to the root's):
+    // warp-reduced, one fp64 atomic per warp
+    double area = 0.0;
+    if (i < n - 1) {
+        const float *b = node_box + 6 * (size_t)i;
+        const double dx = (double)b[3] - b[0], dy = (double)b[4] - b[1], dz = (double)b[5] - b[2];
+        area = dx * dy + dy * dz + dz * dx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(0xffffffffu, area, o);
+    if ((threadIdx.x & 31) == 0 && area > 0.0) atomicAdd(sah, area);
     if (i >= n - 1) return;
     const int2 ch = children[i];
     BvhNode nd;
@@ -296,7 +311,7 @@ void bvh_free(rts_engine *e)
     void **ptrs[] = {(void **)&e->d_morton, (void **)&e->d_morton_sorted, (void **)&e->d_order_in, (void **)&e->d_order,
                      (void **)&e->d_leaf_of_tri, (void **)&e->d_tri_box, (void **)&e->d_node_box, (void **)&e->d_scene_box,
                      (void **)&e->d_parent, (void **)&e->d_children, (void **)&e->d_range, (void **)&e->d_fit_flags,
-                     (void **)&e->d_nodes, (void **)&e->d_trirec, (void **)&e->d_cub_temp, (void **)&e->d_violations};
+                     (void **)&e->d_nodes, (void **)&e->d_trirec, (void **)&e->d_cub_temp, (void **)&e->d_violations, (void **)&e->d_sah};
     for (void **p : ptrs) {
         if (*p) cudaFree(*p);
         *p = nullptr;
@@ -322,6 +337,7 @@ int bvh_alloc(rts_engine *e)
     if ((rc = dalloc(&e->d_nodes, T))) return rc;
     if ((rc = dalloc(&e->d_trirec, T))) return rc;
     if ((rc = dalloc(&e->d_violations, (size_t)1))) return rc;
+    if ((rc = dalloc(&e->d_sah, (size_t)1))) return rc;
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, e->d_morton, e->d_morton_sorted, e->d_order_in, e->d_order, (int)T, 0,
                                     63, e->stream);
@@ -362,8 +378,9 @@ static int fit_and_pack(rts_engine *e)
         RTS_CUDA(cudaMemsetAsync(e->d_fit_flags, 0, sizeof(uint32_t) * (size_t)n, e->stream));
         { k_fit<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_children, e->d_parent, e->d_order, e->d_tri_box, e->d_node_box,
                                                       e->d_fit_flags, n); e->launches++; }
+        RTS_CUDA(cudaMemsetAsync(e->d_sah, 0, sizeof(double), e->stream));
         { k_pack<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_children, e->d_range, e->d_order, e->d_tri_box,
-                                                           e->d_node_box, e->d_nodes, n); e->launches++; }
+                                                           e->d_node_box, e->d_nodes, n, e->d_sah); e->launches++; }
     }
     RTS_CUDA(cudaGetLastError());
     e->root_ref = n <= RTS_LEAF_MAX ? ~((0 << 3) | (n - 1)) : 0;
@@ -409,15 +426,29 @@ int bvh_build(rts_engine *e)
         memcpy(&bi.scene_hi[a], &h, 4);
     }
     bi.ms_build = ms;
-    bi.sah_cost = 0;
+    double sah = 0;
+    if (n >= 2) RTS_CUDA(cudaMemcpy(&sah, e->d_sah, sizeof(double), cudaMemcpyDeviceToHost));
+    bi.sah_cost = sah;
+    e->sah_at_build = sah;
+    e->builds++;
     return RTS_OK;
 }
 
+// Refit; when the tree's SAH cost has drifted more than RTS_REBUILD_RATIO above the cost it had when
+// its topology was built (targets moved far from where they were clustered), rebuild instead.
 int bvh_refit(rts_engine *e)
 {
     int rc = bvh_update_world(e);
     if (rc) return rc;
-    return fit_and_pack(e);
+    if ((rc = fit_and_pack(e))) return rc;
+    if (e->n_tris >= 2) {
+        double sah = 0;
+        RTS_CUDA(cudaMemcpyAsync(&sah, e->d_sah, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        RTS_CUDA(cudaStreamSynchronize(e->stream));
+        e->bvh_info.sah_cost = sah;
+        if (sah > RTS_REBUILD_RATIO * e->sah_at_build) return bvh_build(e);
+    }
+    return RTS_OK;
 }
 
 int bvh_check(rts_engine *e, uint64_t *violations)

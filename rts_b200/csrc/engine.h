@@ -11,6 +11,7 @@
 #define RTS_STACK_DEPTH 96      // traversal stack entries per thread
 #define RTS_WAVE_BLOCK 128      // threads per CTA of the bounce-wave kernel
 #define RTS_MAX_RX 64
+#define RTS_REBUILD_RATIO 1.2   // refit falls back to a rebuild when SAH cost exceeds this x the as-built cost
 
 // ---- device layouts -------------------------------------------------------------------------
 // BVH node, 64 B = 4 x 128-bit loads: the two child boxes (fp32, rounded outward exactly like the
@@ -142,6 +143,9 @@ struct rts_engine {
     int32_t root_ref = 0;
     rts_bvh_info bvh_info = {};
     unsigned long long *d_violations = nullptr;
+    double *d_sah = nullptr;
+    double sah_at_build = 0;
+    uint32_t builds = 0;
 
     // wave state
     RayQueue q[2] = {};
