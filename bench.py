@@ -8,7 +8,7 @@ Workload (config C4 of BASELINE.json / SURVEY.md Appendix C): 1,000,000-triangle
 + 16 moving targets (8 boxes, 8 icospheres, 4 rotating), maxRefl = 3, 1 receiver.  One step = one
 pulse: per-pulse target poses (host -> device), device rigid transform + BVH refit, all bounce waves
 of a (1, 4096, 4096) ray grid per GPU with fused receiver-bin aggregation, and for N > 1 the NCCL
-all-reduce of the bins (rays are sharded in contiguous slabs of a (1, 4096, 4096*N) launch, scene and
+all-reduce of the bins (rays of a (1, 4096*N, 4096) launch are dealt round-robin to the ranks, scene and
 BVH replicated: weak scaling).  Pulses advance every step, so the movers really move.
 
 value  : steps timed without reading the bins back (inputs resident, CUDA events on the engine's stream)
@@ -83,7 +83,7 @@ class ClockSampler:
 def build_scene(world):
     from rts_b200 import scenes
     t0 = time.time()
-    ms = scenes.terrain_scene(n=N_GRID, n_rx=1, nz=N_GRID * world)
+    ms = scenes.terrain_scene(n=N_GRID * world, n_rx=1, nz=N_GRID)
     log(f"[bench] scene generated in {time.time() - t0:.1f}s: {sum(len(t.tris) for t in ms.base)} triangles, {len(ms.base)} targets")
     return ms
 
@@ -114,12 +114,15 @@ def run_ours(args):
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
-    begin, count = rdist.shard_range(ms.spec.rays, rank, world)
+    # weak scaling: the launch grid is (1, 4096*N, 4096) — N x denser in azimuth — and rank r traces rays
+    # r, r+N, r+2N, ... of it, so every rank sees the N = 1 ray density, coherence and workload
+    begin, count, stride = rank, 0, world
+    n_mine = (ms.spec.rays - begin + stride - 1) // stride
 
     def step(pulse, read_back):
         eng.set_poses(*ms.poses(pulse))                      # H2D poses + device transform + refit
         spec = ms.spec_for(pulse)
-        spec.ray_begin, spec.ray_count = begin, count
+        spec.ray_begin, spec.ray_count, spec.ray_stride = begin, count, stride
         st = eng.trace(spec, L.RTS_OUT_BINS | (L.RTS_NO_FINALISE if world > 1 else 0))
         if world > 1:
             rdist.allreduce_bins(eng, dev)
@@ -156,11 +159,11 @@ def run_ours(args):
         return dict(ms=float(t[0]), wall_ms=float(t[1]), waves=waves, segments=segs, captured=caps, d2h=d2h,
                     launches=eng.kernel_launches() - launches0)
 
-    for w in range(args.warmup):
-        step(w, True)
     clocks = ClockSampler(local)
     if rank == 0:
-        clocks.start()
+        clocks.start()          # nvidia-smi needs ~0.5 s to start sampling: begin before the warm-up
+    for w in range(args.warmup):
+        step(w, True)
     k0 = args.warmup
     r_dev = timed(k0, args.steps, read_back=False)
     r_e2e = timed(k0, args.steps, read_back=True)
@@ -198,10 +201,10 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(ms, args.cpu_stride)
+        cpu = cpu_baseline(ms, args.cpu_stride or 1)
 
     if rank == 0:
-        seg_per_ray = r_dev["segments"] / (count * args.steps)
+        seg_per_ray = r_dev["segments"] / (n_mine * args.steps)
         h2d = len(ms.base) * 112 + len(ms.base) * 24 + 64   # poses + target velocities + receiver
         out = {
             "metric": "Mrays/s (3-bounce, 1M-tri scene)", "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world,
@@ -209,7 +212,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C4: 1,000,000-triangle terrain + 16 moving targets, per-pulse pose update + BVH refit, "
                                    f"(1,{N_GRID},{N_GRID}) rays per GPU per pulse, maxRefl=3, 1 Rx, fused bins"
-                                   + (", ray-sharded, NCCL all-reduce of bins" if world > 1 else ""),
+                                   + (f", launch grid (1,{N_GRID * world},{N_GRID}) ray-sharded round-robin, NCCL all-reduce of bins" if world > 1 else ""),
                        "triangles": int(sum(len(t.tris) for t in ms.base)), "rays_per_step": int(rays_per_step_total),
                        "segments_per_ray": round(seg_per_ray, 4), "captured_per_step": int(r_dev["captured"] / args.steps),
                        "l2_policy": "per-step working set (BVH 21 MB + triangles 81 MB + 2.4 GB ray queues written and re-read) exceeds the 126 MB L2",
@@ -255,7 +258,7 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_api as O
     ms = build_scene(1)
-    stride = args.cpu_stride
+    stride = args.cpu_stride or 4
     total_rays, total_s, per = 0, 0.0, []
     for i in range(args.warmup + args.steps):
         pulse = i
@@ -281,10 +284,10 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-stride", type=int, default=16, help="oracle sample: every n-th primary ray")
+    ap.add_argument("--cpu-stride", type=int, default=0, help="oracle sample: every n-th primary ray (0 = 1 for cpu_baseline, 4 for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

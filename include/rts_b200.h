@@ -130,7 +130,8 @@ int rts_get_records(rts_engine *e, rts_ray_record *results, int32_t *targ_inters
 
 /* ---- multi-GPU plumbing: raw bin accumulators for an external reduction (NCCL all-reduce) ----
  * sums_device: double[n_bins_dense*5] {npath, Σ√P, Σdelay, Σphase, ΣDoppler}  (reduce with SUM)
- * mins_device: uint64[n_bins_dense]   smallest result-slot index               (reduce with MIN) */
+ * mins_device: uint64[n_bins_dense]   smallest result-slot index; empty bins hold 0x7f7f7f7f7f7f7f7f, so a MIN
+ *              reduction over either uint64 or int64 views is correct */
 int rts_bins_device(rts_engine *e, void **sums_device, uint64_t *n_sum_doubles, void **mins_device,
                     uint64_t *n_mins);
 int rts_finalise_bins(rts_engine *e);

@@ -401,7 +401,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
         }
         e->n_bins_dense = p->n_rx ? nb : 0;
         RTS_CUDA(cudaMemsetAsync(e->d_bin_sums, 0, sizeof(double) * 5 * nb, st));
-        RTS_CUDA(cudaMemsetAsync(e->d_bin_mins, 0xff, sizeof(unsigned long long) * nb, st));
+        RTS_CUDA(cudaMemsetAsync(e->d_bin_mins, 0x7f, sizeof(unsigned long long) * nb, st)); // empty = 0x7f7f…7f: positive as int64, so a signed MIN all-reduce keeps it last
         P.bin_sums = e->d_bin_sums; P.bin_mins = e->d_bin_mins; P.n_bins = e->n_bins_dense;
     } else {
         e->n_bins_dense = 0;

@@ -43,23 +43,30 @@ def bins_as_tensors(engine, device):
     return sums, mins
 
 
+EMPTY_MIN = 0x7F7F7F7F7F7F7F7F   # what librts_b200 stores in the slot-index array of a bin nobody hit
+
+
 def allreduce_bin_tensors(sums, mins, group=None):
-    """The exchange step. `mins` holds uint64 slot indices (< 2^63) viewed as int64, so MIN is order-preserving;
-    empty bins hold 0xFFFF…F = -1 as int64, which must not win: map to int64 max before reducing."""
-    import torch
+    """The exchange step: SUM over the five fp64 accumulators, MIN over the representative slot index.
+    Slot indices are < 2^63 and empty bins hold EMPTY_MIN, so MIN on the int64 view is order-preserving."""
     import torch.distributed as dist
 
     dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    big = torch.iinfo(torch.int64).max
-    mins.masked_fill_(mins < 0, big)
     dist.all_reduce(mins, op=dist.ReduceOp.MIN, group=group)
-    mins.masked_fill_(mins == big, -1)
     return sums, mins
 
 
+_views = {}
+
+
 def allreduce_bins(engine, device, group=None):
-    """All-reduce the engine's bins in place over NCCL, then mark them final (myKernel2 runs at collection)."""
-    sums, mins = bins_as_tensors(engine, device)
+    """All-reduce the engine's bins in place over NCCL, then mark them final (myKernel2 runs at collection).
+    The zero-copy views are cached per (engine, device pointers)."""
+    key = (id(engine),) + tuple(engine.bins_device())
+    if key not in _views:
+        _views.clear()
+        _views[key] = bins_as_tensors(engine, device)
+    sums, mins = _views[key]
     allreduce_bin_tensors(sums, mins, group)
     engine.finalise_bins()
 

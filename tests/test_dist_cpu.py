@@ -41,7 +41,7 @@ def _worker(rank, world, port, n_bins, out_dir):
     mins = rng.integers(0, 1 << 40, size=n_bins).astype(np.uint64)
     empty = rng.uniform(size=n_bins) < 0.5          # bins this rank never touched
     sums[empty] = 0
-    mins[empty] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    mins[empty] = np.uint64(rdist.EMPTY_MIN)
     np.save(os.path.join(out_dir, f"sums{rank}.npy"), sums)
     np.save(os.path.join(out_dir, f"mins{rank}.npy"), mins)
     ts = torch.from_numpy(sums.reshape(-1).copy())
@@ -60,4 +60,4 @@ def test_bin_allreduce_gloo_world2(tmp_path):
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"rsums{r}.npy"), esums)      # two addends: order-independent
         assert np.array_equal(np.load(tmp_path / f"rmins{r}.npy"), emins)
-    assert (emins == np.uint64(0xFFFFFFFFFFFFFFFF)).any()                      # bins empty on every rank stay empty
+    assert (emins == np.uint64(rdist.EMPTY_MIN)).any()                      # bins empty on every rank stay empty
