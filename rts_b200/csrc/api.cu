@@ -9,6 +9,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <algorithm>
 
 static thread_local char g_err[512] = "";
@@ -78,6 +79,7 @@ extern "C" int rts_create(int device, rts_engine **out)
         return rts_fail(RTS_ERR_CUDA, "cudaStreamCreate failed");
     }
     e->stream = e->own_stream;
+    if (const char *lm = getenv("RTS_LEAF_MAX")) { int v = atoi(lm); if (v >= 1 && v <= 8) e->leaf_max = v; }
     for (auto &ev : e->ev) cudaEventCreate(&ev);
     for (auto &ev : e->wave_ev) cudaEventCreate(&ev);
     cudaMalloc(&e->d_wave_segs, sizeof(unsigned long long) * 32);
@@ -340,6 +342,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     WaveParams P;
     memset(&P, 0, sizeof(P));
     P.nodes = e->d_nodes; P.trirec = e->d_trirec; P.root_ref = e->root_ref; P.n_tris = e->n_tris;
+    for (int a = 0; a < 3; a++) P.scene_abs[a] = e->scene_abs[a];
     P.world_normals = e->d_world_normals; P.tris = e->d_tris;
     P.t_norm_off = e->d_t_norm_off; P.t_tri_off = e->d_t_tri_off; P.t_per_face = e->d_t_per_face;
     P.t_refl = e->d_t_refl; P.t_refr = e->d_t_refr; P.t_vel = e->d_t_vel;

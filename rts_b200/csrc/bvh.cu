@@ -17,6 +17,8 @@
 #include "engine.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <math_constants.h>
+#include <cstring>
+#include <cmath>
 
 namespace {
 
@@ -233,7 +235,7 @@ __global__ void k_fit(const int2 *__restrict__ children, const int32_t *__restri
 
 __global__ void k_pack(const int2 *__restrict__ children, const int2 *__restrict__ range,
                        const uint32_t *__restrict__ order, const float *__restrict__ tri_box,
-                       const float *__restrict__ node_box, BvhNode *__restrict__ nodes, int n, double *sah)
+                       const float *__restrict__ node_box, BvhNode *__restrict__ nodes, int n, double *sah, int leaf_max)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     // surface-area-heuristic cost of the tree = sum of internal-node box areas (relative to the root's):
@@ -261,7 +263,7 @@ __global__ void k_pack(const int2 *__restrict__ children, const int2 *__restrict
         } else {
             const int2 rg = range[r];
             const int cnt = rg.y - rg.x + 1;
-            refs[c] = cnt <= RTS_LEAF_MAX ? ~((rg.x << 3) | (cnt - 1)) : r;
+            refs[c] = cnt <= leaf_max ? ~((rg.x << 3) | (cnt - 1)) : r;
             src = node_box + 6 * (size_t)r;
         }
         float *lo = c == 0 ? nd.lo0 : nd.lo1, *hi = c == 0 ? nd.hi0 : nd.hi1;
@@ -380,10 +382,27 @@ static int fit_and_pack(rts_engine *e)
                                                       e->d_fit_flags, n); e->launches++; }
         RTS_CUDA(cudaMemsetAsync(e->d_sah, 0, sizeof(double), e->stream));
         { k_pack<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_children, e->d_range, e->d_order, e->d_tri_box,
-                                                           e->d_node_box, e->d_nodes, n, e->d_sah); e->launches++; }
+                                                           e->d_node_box, e->d_nodes, n, e->d_sah, e->leaf_max); e->launches++; }
     }
     RTS_CUDA(cudaGetLastError());
-    e->root_ref = n <= RTS_LEAF_MAX ? ~((0 << 3) | (n - 1)) : 0;
+    e->root_ref = n <= e->leaf_max ? ~((0 << 3) | (n - 1)) : 0;
+    return RTS_OK;
+}
+
+static int read_scene_box(rts_engine *e)
+{
+    unsigned sb[6];
+    RTS_CUDA(cudaMemcpyAsync(sb, e->d_scene_box, sizeof(sb), cudaMemcpyDeviceToHost, e->stream));
+    RTS_CUDA(cudaStreamSynchronize(e->stream));
+    rts_bvh_info &bi = e->bvh_info;
+    for (int a = 0; a < 3; a++) {
+        const unsigned lo = sb[a], hi = sb[3 + a];
+        const uint32_t l = (lo & 0x80000000u) ? (lo & 0x7fffffffu) : ~lo, h = (hi & 0x80000000u) ? (hi & 0x7fffffffu) : ~hi;
+        memcpy(&bi.scene_lo[a], &l, 4);
+        memcpy(&bi.scene_hi[a], &h, 4);
+        const float m = fmaxf(fabsf(bi.scene_lo[a]), fabsf(bi.scene_hi[a]));
+        e->scene_abs[a] = (e->n_tris && m < 3.0e38f) ? m : 0.f;
+    }
     return RTS_OK;
 }
 
@@ -412,19 +431,12 @@ int bvh_build(rts_engine *e)
     RTS_CUDA(cudaStreamSynchronize(e->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]);
-    unsigned sb[6];
-    RTS_CUDA(cudaMemcpy(sb, e->d_scene_box, sizeof(sb), cudaMemcpyDeviceToHost));
+    if ((rc = read_scene_box(e))) return rc;
     rts_bvh_info &bi = e->bvh_info;
     bi.n_tris = e->n_tris;
     bi.n_nodes = n >= 2 ? n - 1 : 0;
     bi.root_is_leaf = e->root_ref < 0;
-    bi.max_leaf = RTS_LEAF_MAX;
-    for (int a = 0; a < 3; a++) {
-        unsigned lo = sb[a], hi = sb[3 + a];
-        uint32_t l = (lo & 0x80000000u) ? (lo & 0x7fffffffu) : ~lo, h = (hi & 0x80000000u) ? (hi & 0x7fffffffu) : ~hi;
-        memcpy(&bi.scene_lo[a], &l, 4);
-        memcpy(&bi.scene_hi[a], &h, 4);
-    }
+    bi.max_leaf = e->leaf_max;
     bi.ms_build = ms;
     double sah = 0;
     if (n >= 2) RTS_CUDA(cudaMemcpy(&sah, e->d_sah, sizeof(double), cudaMemcpyDeviceToHost));
@@ -441,6 +453,7 @@ int bvh_refit(rts_engine *e)
     int rc = bvh_update_world(e);
     if (rc) return rc;
     if ((rc = fit_and_pack(e))) return rc;
+    if ((rc = read_scene_box(e))) return rc;
     if (e->n_tris >= 2) {
         double sah = 0;
         RTS_CUDA(cudaMemcpyAsync(&sah, e->d_sah, sizeof(double), cudaMemcpyDeviceToHost, e->stream));

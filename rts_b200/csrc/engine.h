@@ -7,7 +7,7 @@
 
 #include "../../include/rts_b200.h"
 
-#define RTS_LEAF_MAX 4          // triangles per BVH leaf (collapsed LBVH subtrees)
+#define RTS_LEAF_MAX 2          // triangles per BVH leaf (collapsed LBVH subtrees); measured best of 1/2/4 on B200
 #define RTS_STACK_DEPTH 96      // traversal stack entries per thread
 #define RTS_WAVE_BLOCK 128      // threads per CTA of the bounce-wave kernel
 #define RTS_MAX_RX 64
@@ -56,6 +56,7 @@ struct WaveParams {
     const TriRec *trirec;
     int32_t root_ref;
     uint32_t n_tris;
+    float scene_abs[3];             // max |coordinate| of the scene box per axis (slab error bound)
     const double *world_normals;    // [Nn*3]
     const uint32_t *tris;           // [T*3] local vertex indices
     const uint32_t *t_norm_off;     // per target
@@ -141,7 +142,9 @@ struct rts_engine {
     void *d_cub_temp = nullptr;
     size_t cub_temp_bytes = 0;
     int32_t root_ref = 0;
+    int leaf_max = RTS_LEAF_MAX;       // 1..8; RTS_LEAF_MAX env var overrides (tuning)
     rts_bvh_info bvh_info = {};
+    float scene_abs[3] = {0, 0, 0};
     unsigned long long *d_violations = nullptr;
     double *d_sah = nullptr;
     double sah_at_build = 0;

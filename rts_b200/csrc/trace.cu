@@ -23,8 +23,6 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr float RT_DEFAULT_MAX_F = 1.e27f;
-constexpr double PAD_REL = 1e-6;   // conservative slab padding (relative)
-constexpr double PAD_ABS = 1e-9;   // and absolute
 constexpr double EDGE_EPS = 1e-9;
 
 struct Ray {
@@ -125,22 +123,62 @@ __device__ __forceinline__ bool tri_test(const Tri &T, const d3 &o, const d3 &di
     return ((t < tmax_d) & (t > tmin_d) & (beta >= 0.0f) & (gamma >= 0.0f) & (beta + gamma <= 1));
 }
 
+// The same test, same operations and rounding, evaluated t-first so that candidates outside
+// (tmin, tmax) skip the barycentric part; accept/reject and t are bit-identical to tri_test.
+__device__ __forceinline__ bool tri_accept(const Tri &T, const d3 &o, const d3 &dir, double tmin_d, double tmax_d, double &t)
+{
+    const d3 e0 = T.p1 - T.p0;
+    const d3 e1 = T.p0 - T.p2;
+    const d3 n = cross3(e1, e0);
+    const d3 e2 = (1 / dot3(n, dir)) * (T.p0 - o);
+    t = dot3(n, e2);
+    if (!((t < tmax_d) & (t > tmin_d))) return false;
+    const d3 i = cross3(dir, e2);
+    const double beta = dot3(i, e1);
+    const double gamma = dot3(i, e0);
+    return ((beta >= 0.0f) & (gamma >= 0.0f) & (beta + gamma <= 1));
+}
+
 struct HitRec { int pos; float t; uint32_t id; };
 
-// BVH traversal: fp64 slab test of the true (fp64) ray against the fp32 outward-rounded boxes,
-// padded so that no box is pruned that the fp64 triangle test could accept; closest hit =
-// smallest fp32 t in (tmin, inf), ties to the lowest global triangle id (rtPotentialIntersection
-// semantics with a defined tie rule).
+// BVH traversal.  Boxes are tested in fp32 with a rigorous error bound so that the test is
+// conservative with respect to the exact slab distances of the true fp64 ray:
+//   t*_a = (b - o_a) / d_a             exact distance to plane b (b is an fp32 value, exact)
+//   t_a  = fma(b, inv_a, -oi_a)        inv_a = fl32(1/d_a), oi_a = fl32(o_a/d_a)
+//   |t_a - t*_a| <= 2^-24 (2+eps) (|b| + |o_a|) / |d_a|  <=  E_a := 2^-21 (S_a + |o_a|) |inv_a|
+// with S_a = max |coordinate| of the scene box on that axis.  The near distances are lowered and
+// the far distances raised by E_a (folded into the fma addend), so a box is never pruned when the
+// fp64 triangle test (triangle_mesh.cu:121-137) could accept a hit inside it; FMA contraction is
+// harmless here because only the bound matters, not the rounding.  Axes with |d_a| < 1e-20 are
+// ignored (always overlapping).  Closest hit = smallest fp32 t in (tmin, inf), ties to the lowest
+// global triangle id (rtPotentialIntersection semantics with a defined tie rule).
 __device__ __forceinline__ void traverse(const WaveParams &P, const Ray &r, float tmin_f, HitRec &best,
                                          unsigned &n_nodes, unsigned &n_tris, unsigned &stack_ovf)
 {
     best.pos = -1; best.t = RT_DEFAULT_MAX_F; best.id = 0xffffffffu;
     if (P.n_tris == 0) return;
     const d3 o = mk3(r.ox, r.oy, r.oz), dir = mk3(r.dx, r.dy, r.dz);
-    const double ivx = 1.0 / dir.x, ivy = 1.0 / dir.y, ivz = 1.0 / dir.z;
-    const bool sx = signbit(dir.x), sy = signbit(dir.y), sz = signbit(dir.z);
+    float inv[3], cn[3], cf[3];
+    bool neg[3];
+    {
+        const double oo[3] = {o.x, o.y, o.z}, dd[3] = {dir.x, dir.y, dir.z};
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            neg[a] = signbit(dd[a]);
+            if (fabs(dd[a]) < 1e-20) {
+                inv[a] = 0.f; cn[a] = -CUDART_INF_F; cf[a] = CUDART_INF_F;
+            } else {
+                const double id = 1.0 / dd[a];
+                inv[a] = (float)id;
+                const float oi = (float)(oo[a] * id);
+                const float E = 4.76837158203125e-07f * ((P.scene_abs[a] + fabsf((float)oo[a])) * fabsf(inv[a])) * 1.0001f + 1e-30f;
+                cn[a] = -oi - E;
+                cf[a] = -oi + E;
+            }
+        }
+    }
     const double tmin_d = (double)tmin_f, tmax_d = (double)RT_DEFAULT_MAX_F;
-    double best_pad = CUDART_INF;
+    float best_pad = CUDART_INF_F;
     int stack[RTS_STACK_DEPTH];
     int sp = 0;
     int cur = P.root_ref;
@@ -151,23 +189,16 @@ __device__ __forceinline__ void traverse(const WaveParams &P, const Ray &r, floa
             const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
             const int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
             // child 0: lo (q0.x q0.y q0.z) hi (q0.w q1.x q1.y); child 1: lo (q1.z q1.w q2.x) hi (q2.y q2.z q2.w)
-            double tn0, tf0, tn1, tf1;
-            {
-                const double nx_ = (double)(sx ? q0.w : q0.x), fx_ = (double)(sx ? q0.x : q0.w);
-                const double ny_ = (double)(sy ? q1.x : q0.y), fy_ = (double)(sy ? q0.y : q1.x);
-                const double nz_ = (double)(sz ? q1.y : q0.z), fz_ = (double)(sz ? q0.z : q1.y);
-                tn0 = fmax(fmax((nx_ - o.x) * ivx, (ny_ - o.y) * ivy), (nz_ - o.z) * ivz);
-                tf0 = fmin(fmin((fx_ - o.x) * ivx, (fy_ - o.y) * ivy), (fz_ - o.z) * ivz);
-            }
-            {
-                const double nx_ = (double)(sx ? q2.y : q1.z), fx_ = (double)(sx ? q1.z : q2.y);
-                const double ny_ = (double)(sy ? q2.z : q1.w), fy_ = (double)(sy ? q1.w : q2.z);
-                const double nz_ = (double)(sz ? q2.w : q2.x), fz_ = (double)(sz ? q2.x : q2.w);
-                tn1 = fmax(fmax((nx_ - o.x) * ivx, (ny_ - o.y) * ivy), (nz_ - o.z) * ivz);
-                tf1 = fmin(fmin((fx_ - o.x) * ivx, (fy_ - o.y) * ivy), (fz_ - o.z) * ivz);
-            }
-            const bool h0 = (tn0 <= tf0 * (1.0 + PAD_REL) + PAD_ABS) & (tf0 >= 0.0) & (tn0 <= best_pad);
-            const bool h1 = (tn1 <= tf1 * (1.0 + PAD_REL) + PAD_ABS) & (tf1 >= 0.0) & (tn1 <= best_pad);
+            const float tn0 = fmaxf(fmaxf(__fmaf_rn(neg[0] ? q0.w : q0.x, inv[0], cn[0]), __fmaf_rn(neg[1] ? q1.x : q0.y, inv[1], cn[1])),
+                                    __fmaf_rn(neg[2] ? q1.y : q0.z, inv[2], cn[2]));
+            const float tf0 = fminf(fminf(__fmaf_rn(neg[0] ? q0.x : q0.w, inv[0], cf[0]), __fmaf_rn(neg[1] ? q0.y : q1.x, inv[1], cf[1])),
+                                    __fmaf_rn(neg[2] ? q0.z : q1.y, inv[2], cf[2]));
+            const float tn1 = fmaxf(fmaxf(__fmaf_rn(neg[0] ? q2.y : q1.z, inv[0], cn[0]), __fmaf_rn(neg[1] ? q2.z : q1.w, inv[1], cn[1])),
+                                    __fmaf_rn(neg[2] ? q2.w : q2.x, inv[2], cn[2]));
+            const float tf1 = fminf(fminf(__fmaf_rn(neg[0] ? q1.z : q2.y, inv[0], cf[0]), __fmaf_rn(neg[1] ? q1.w : q2.z, inv[1], cf[1])),
+                                    __fmaf_rn(neg[2] ? q2.x : q2.w, inv[2], cf[2]));
+            const bool h0 = (tn0 <= tf0) & (tf0 >= 0.f) & (tn0 <= best_pad);
+            const bool h1 = (tn1 <= tf1) & (tf1 >= 0.f) & (tn1 <= best_pad);
             if (h0 & h1) {
                 const bool swap = tn1 < tn0;
                 if (sp < RTS_STACK_DEPTH) stack[sp++] = swap ? q3.x : q3.y;
@@ -183,13 +214,12 @@ __device__ __forceinline__ void traverse(const WaveParams &P, const Ray &r, floa
             for (int k = 0; k < cnt; k++) {
                 n_tris++;
                 const Tri T = load_tri(P.trirec, first + k);
-                d3 n;
-                double t, beta, gamma;
-                if (tri_test(T, o, dir, tmin_d, tmax_d, n, t, beta, gamma)) {
+                double t;
+                if (tri_accept(T, o, dir, tmin_d, tmax_d, t)) {
                     const float tf = (float)t;
                     if (tf > tmin_f && (tf < best.t || (tf == best.t && T.id < best.id))) {
                         best.t = tf; best.pos = first + k; best.id = T.id;
-                        best_pad = (double)tf * (1.0 + PAD_REL) + PAD_ABS;
+                        best_pad = tf * 1.000001f;
                     }
                 }
             }
@@ -313,6 +343,11 @@ __device__ __forceinline__ void shade(const WaveParams &P, Ray &r, const HitRec 
     else { rdir.x = (float)dir.x; rdir.y = (float)dir.y; rdir.z = (float)dir.z; }
     const f3 nf = normalise_float3(normal);
     const d3 V = mk3(P.t_vel[3 * targ], P.t_vel[3 * targ + 1], P.t_vel[3 * targ + 2]);
+    // The unit vectors k0, k1 (normal_shader.cu:251-253, 302-304) feed only the Doppler term V.(k1-k0)
+    // and the RCS angles.  For a target at rest V.(k1-k0) is exactly +0 and doppler += 0 leaves the value
+    // unchanged, so the two fp64 normalisations are skipped unless the angles are wanted.
+    const bool want_rcs = RECORDS && !(P.flags & RTS_NO_RCS_ANGLES);
+    const bool need_k = want_rcs || (V.x != 0.0) || (V.y != 0.0) || (V.z != 0.0);
 
     // :191-194
     const double pr_n0 = r.n1; // prd_refr.refrIndex.x = prd_refr.refrIndex.y
@@ -343,11 +378,12 @@ __device__ __forceinline__ void shade(const WaveParams &P, Ray &r, const HitRec 
             }
             if ((reflDepth + 1) < dMax) c.pw *= (1 - fabs(reflCoeff)); // :245-246
             const uint32_t c_refr = refrDepth + 1;                       // :247
-            const d3 k0 = normalised3(dir);                              // :251-256
             c.dx = (double)nd.x; c.dy = (double)nd.y; c.dz = (double)nd.z;
-            const d3 k1 = normalised3(mk3(c.dx, c.dy, c.dz));
-            c.dop += dot3(V, k1 - k0);
-            if (RECORDS && !(P.flags & RTS_NO_RCS_ANGLES)) { // :259-265
+            if (need_k) {
+                const d3 k0 = normalised3(dir);                          // :251-256
+                const d3 k1 = normalised3(mk3(c.dx, c.dy, c.dz));
+                c.dop += dot3(V, k1 - k0);
+            if (want_rcs) { // :259-265
                 const uint32_t x = reflDepth + (c_refr - 1);
                 if (x < P.D) {
                     double a0, e0, a1, e1;
@@ -356,6 +392,7 @@ __device__ __forceinline__ void shade(const WaveParams &P, Ray &r, const HitRec 
                     P.rcs_angle[(crow * P.D + x) * 2] = a0 + a1;
                     P.rcs_angle[(crow * P.D + x) * 2 + 1] = e0 + e1;
                 }
+            }
             }
             c.meta = m_make(reflDepth, c_refr, cslot, end, false, col + 1);
             push_ray(P, c, L.overflow); // :268
@@ -371,11 +408,12 @@ __device__ __forceinline__ void shade(const WaveParams &P, Ray &r, const HitRec 
     if (reflDepth < dMax) {
         const f3 nd = optix_reflect(rdir, nf);
         r.pw *= reflCoeff;
-        const d3 k0 = normalised3(dir);
         r.dx = (double)nd.x; r.dy = (double)nd.y; r.dz = (double)nd.z;
+        if (need_k) {
+        const d3 k0 = normalised3(dir);
         const d3 k1 = normalised3(mk3(r.dx, r.dy, r.dz));
         r.dop += dot3(V, k1 - k0);
-        if (RECORDS && !(P.flags & RTS_NO_RCS_ANGLES)) { // :320-326
+        if (want_rcs) { // :320-326
             const uint32_t x = (reflDepth - 1) + refrDepth;
             if (x < P.D) {
                 double a0, e0, a1, e1;
@@ -384,6 +422,7 @@ __device__ __forceinline__ void shade(const WaveParams &P, Ray &r, const HitRec 
                 P.rcs_angle[(row * P.D + x) * 2] = a0 + a1;
                 P.rcs_angle[(row * P.D + x) * 2 + 1] = e0 + e1;
             }
+        }
         }
         r.meta = m_make(reflDepth, refrDepth, slot, end, false, col + 1);
         push_ray(P, r, L.overflow); // :332
