@@ -10,6 +10,12 @@
 #define RTS_LEAF_MAX 2          // triangles per BVH leaf (collapsed LBVH subtrees); measured best of 1/2/4 on B200
 #define RTS_STACK_DEPTH 96      // traversal stack entries per thread
 #define RTS_WAVE_BLOCK 128      // threads per CTA of the bounce-wave kernel
+#ifndef RTS_WAVE_MIN_BLOCKS
+#define RTS_WAVE_MIN_BLOCKS 6           // resident CTAs per SM the register allocation must allow (later waves)
+#endif
+#ifndef RTS_WAVE_MIN_BLOCKS_PRIMARY
+#define RTS_WAVE_MIN_BLOCKS_PRIMARY 8   // same, primary wave (its state is smaller)
+#endif
 #define RTS_MAX_RX 64
 #define RTS_REBUILD_RATIO 1.2   // refit falls back to a rebuild when SAH cost exceeds this x the as-built cost
 
@@ -157,7 +163,7 @@ struct rts_engine {
     unsigned long long *d_counts = nullptr;   // [64] queue counts + work counters
     Counters *d_counters = nullptr;
     RxDev *d_rx = nullptr;
-    int wave_grid = 0;
+    int wave_grid = 0, wave_grid_primary = 0;
 
     // outputs
     double *d_bin_sums = nullptr;

@@ -43,14 +43,21 @@ __device__ __forceinline__ uint32_t m_make(uint32_t refl, uint32_t refr, uint32_
            ((col & 15u) << 16);
 }
 
-__device__ __forceinline__ void load_ray(const RayQueue &q, unsigned long long i, Ray &r)
+// The state is loaded in two parts: what traversal needs (origin, direction, flags) before it, the
+// rest (length, power, Doppler, first hit, indices, path key) only after it — that keeps ~20 registers
+// free during the traversal loop (occupancy is the lever: see profiles/).
+__device__ __forceinline__ void load_ray_geom(const RayQueue &q, unsigned long long i, Ray &r)
 {
     r.ox = q.f[F_OX][i]; r.oy = q.f[F_OY][i]; r.oz = q.f[F_OZ][i];
     r.dx = q.f[F_DX][i]; r.dy = q.f[F_DY][i]; r.dz = q.f[F_DZ][i];
+    r.meta = q.meta[i];
+}
+__device__ __forceinline__ void load_ray_rest(const RayQueue &q, unsigned long long i, Ray &r)
+{
     r.len = q.f[F_LEN][i]; r.pw = q.f[F_PW][i]; r.dop = q.f[F_DOP][i];
     r.fx = q.f[F_FX][i]; r.fy = q.f[F_FY][i]; r.fz = q.f[F_FZ][i];
     r.n0 = q.f[F_N0][i]; r.n1 = q.f[F_N1][i];
-    r.key = q.key[i]; r.ray = q.ray[i]; r.meta = q.meta[i];
+    r.key = q.key[i]; r.ray = q.ray[i];
 }
 __device__ __forceinline__ void store_ray(const RayQueue &q, unsigned long long i, const Ray &r)
 {
@@ -571,7 +578,7 @@ __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r
 }
 
 template <bool PRIMARY, bool RECORDS>
-__global__ void __launch_bounds__(RTS_WAVE_BLOCK) k_wave(const __grid_constant__ WaveParams P)
+__global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_PRIMARY : RTS_WAVE_MIN_BLOCKS) k_wave(const __grid_constant__ WaveParams P)
 {
     const unsigned lane = threadIdx.x & 31u;
     const unsigned long long n_in = PRIMARY ? P.n_primary : *P.in_count;
@@ -594,17 +601,21 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK) k_wave(const __grid_constant__
             const d3 d = primary_direction(P, ix, iy, iz);
             r.ox = P.origin[0]; r.oy = P.origin[1]; r.oz = P.origin[2];
             r.dx = d.x; r.dy = d.y; r.dz = d.z;
-            r.len = 0; r.pw = 0; r.dop = 0; r.fx = 0; r.fy = 0; r.fz = 0; r.n0 = 1; r.n1 = 1;
-            r.key = 0; r.ray = (uint32_t)rayIndex;
             r.meta = m_make(0, 0, 0, false, true, 0);
         } else {
-            load_ray(P.in, idx, r);
+            load_ray_geom(P.in, idx, r);
         }
         L.segments++;
         HitRec h;
         unsigned nn = 0, nt = 0, so = 0;
         traverse(P, r, SCENE_EPS, h, nn, nt, so); // SCENE_EPS == SCENE_EPS_R (ray_tracer.h:9-10)
         L.nodes += nn; L.tris += nt; L.overflow += so;
+        if (PRIMARY) {
+            r.len = 0; r.pw = 0; r.dop = 0; r.fx = 0; r.fy = 0; r.fz = 0; r.n0 = 1; r.n1 = 1;
+            r.key = 0; r.ray = (uint32_t)(P.ray_begin + idx * P.ray_stride);
+        } else {
+            load_ray_rest(P.in, idx, r);
+        }
         if (h.pos >= 0) {
             L.hits++;
             shade<RECORDS>(P, r, h, L);
@@ -635,17 +646,18 @@ int trace_wave_grid(rts_engine *e)
     if (e->wave_grid) return e->wave_grid;
     int occ = 0, best = 1 << 30;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wave<true, false>, RTS_WAVE_BLOCK, 0);
-    best = occ < best ? occ : best;
+    best = occ > 0 ? occ : 1;
+    e->wave_grid_primary = e->num_sms * best;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wave<false, false>, RTS_WAVE_BLOCK, 0);
-    best = occ < best ? occ : best;
-    if (best < 1) best = 1;
+    best = occ > 0 ? occ : 1;
     e->wave_grid = e->num_sms * best;
     return e->wave_grid;
 }
 
 int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool records)
 {
-    const int grid = trace_wave_grid(e);
+    trace_wave_grid(e);
+    const int grid = primary ? e->wave_grid_primary : e->wave_grid;   // persistent: resident CTAs per SM x SMs
     if (primary) {
         if (records) k_wave<true, true><<<grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
         else k_wave<true, false><<<grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);

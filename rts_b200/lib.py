@@ -21,7 +21,7 @@ RTS_NO_FINALISE = 8
 RTS_NO_RCS_ANGLES = 16
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librts_b200.so")
+LIB_PATH = os.environ.get("RTS_B200_LIB", os.path.join(_HERE, "librts_b200.so"))   # override: tuning builds only
 
 
 class RtsError(RuntimeError):
