@@ -72,8 +72,8 @@ const char *rts_last_error(void);
 const char *rts_version(void);
 /* sizeof() of the POD structs as compiled, for binding self-checks:
  * [0] rts_ray_record [1] rts_target_mesh [2] rts_rx_sphere [3] rts_rx_desc [4] rts_pulse
- * [5] rts_bin [6] rts_stats [7] rts_pose */
-int         rts_abi_sizes(uint32_t sizes[8]);
+ * [5] rts_bin [6] rts_stats [7] rts_pose [8] rts_response [9] rts_sizes */
+int         rts_abi_sizes(uint32_t sizes[10]);
 /* Run subsequent work of this engine on a caller-provided cudaStream_t (NULL = engine's own). */
 int         rts_set_stream(rts_engine *e, void *cuda_stream);
 
@@ -123,6 +123,12 @@ int rts_get_wave_profile(rts_engine *e, uint32_t cap, float *ms, uint64_t *segme
 int rts_kernel_launches(rts_engine *e, uint64_t *out);
 /* RTS_OUT_BINS: non-empty bins sorted by (rx, path). *n is the total even when cap is smaller. */
 int rts_get_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n);
+/* RTS_OUT_BINS: the responses the reference would emit for this pulse (ray_tracer.cpp:1289-1320): one per
+ * unique d_pathMatch value, i.e. one per non-direct bin plus one for a receiver's direct bin when a direct
+ * ray is that receiver's first received ray; sorted by representative slot like sort+unique(:1291-1292).
+ * The host forms InterpPoint(power, t + delay, delay, doppler, phase, noise_temperature(rx)) from each.
+ * *n is the total even when cap is smaller. */
+int rts_get_responses(rts_engine *e, rts_response *out, uint32_t cap, uint32_t *n);
 /* RTS_OUT_RECORDS: copy out the reference-shaped arrays; any pointer may be NULL.
  *   results [ray_total] · targ_intersect [ray_total*D] · rcs_angle [ray_total*D*2] · tri_path [ray_total*W] */
 int rts_get_records(rts_engine *e, rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle,

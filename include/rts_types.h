@@ -100,6 +100,11 @@ typedef struct rts_pulse {
     uint64_t ray_begin;           /* first primary-ray index of this shard            */
     uint64_t ray_count;           /* number of primary rays in this shard (0 = to end) */
     uint64_t ray_stride;          /* sample every ray_stride-th primary ray (0/1 = all) */
+    /* Fused post-process (RTS_OUT_BINS) stand-ins for the SOARS callbacks of ray_tracer.cpp:1219-1247.
+     * Hosts that need Target::GetRCS(angles) / antenna patterns use the two-phase path instead
+     * (rts_collect_received -> host callbacks -> rts_aggregate). */
+    const double *targ_rcs;       /* [n_targets] scalar RCS per target, NULL = 1 (Target::GetRCS, :1226) */
+    double   gain_tx, gain_rx;    /* Gt, Gr (:1233-1235); 0 is read as 1                              */
 } rts_pulse;
 
 /* One (receiver, target-path) group — the unit the reference's aggregation produces
@@ -114,9 +119,19 @@ typedef struct rts_bin {
     double   sum_phase;            /* d_phase_arr   (:64) */
     double   sum_doppler;          /* d_doppler_arr (:65) */
     uint64_t min_slot;             /* smallest result-slot index among the rays summed (orders like d_pathMatch, :68-69) */
+    uint64_t own_min_slot;         /* smallest result-slot index among this bin's own member rays (differs for direct bins) */
     /* myKernel2 outputs (aggregation.cu:86-92) */
     double   power, delay, phase, doppler;
 } rts_bin;
+
+/* One emitted response: what ray_tracer.cpp:1301-1320 puts into InterpPoint(power, t+delay, delay,
+ * doppler, phase, noise_temperature) for one unique path of one receiver. */
+typedef struct rts_response {
+    int32_t  rx;
+    int32_t  _pad;
+    uint64_t slot;                 /* representative ray (result-slot index), the unique d_pathMatch value */
+    double   power, delay, doppler, phase;
+} rts_response;
 
 /* Counters returned with every pulse. */
 typedef struct rts_stats {

@@ -134,3 +134,29 @@ extern "C" uint32_t orc_unique_paths(const int32_t *path_match, uint32_t receive
     if (out) std::copy(u.begin(), u.end(), out);
     return (uint32_t)u.size();
 }
+
+// ray_tracer.cpp:1289-1320
+extern "C" uint32_t orc_responses(const rts_ray_record *rx_results, const double *delay, const double *phase,
+                                  const int32_t *path_match, const uint64_t *rx_slots, uint32_t received,
+                                  rts_response *out, uint32_t cap)
+{
+    std::vector<int32_t> unique_path_rays(path_match, path_match + received);   // :1290
+    std::sort(unique_path_rays.begin(), unique_path_rays.end());               // :1291
+    unique_path_rays.erase(std::unique(unique_path_rays.begin(), unique_path_rays.end()), unique_path_rays.end()); // :1292
+    uint32_t n = 0;
+    for (size_t k = 0; k < unique_path_rays.size(); k++) {                      // :1301
+        const uint32_t i = (uint32_t)unique_path_rays[k];                       // :1304
+        if (i >= received) continue; // untouched pre-fill value (never happens for rays that went through aggregation)
+        if (out && n < cap) {
+            rts_response &r = out[n];
+            r.rx = rx_results[i].received; r._pad = 0;                          // :1305
+            r.slot = rx_slots ? rx_slots[i] : i;
+            r.power = rx_results[i].power;                                      // :1312
+            r.delay = delay[i];                                                 // :1308
+            r.doppler = rx_results[i].doppler;                                  // :1314
+            r.phase = phase[i];                                                 // :1309
+        }
+        n++;
+    }
+    return n;
+}

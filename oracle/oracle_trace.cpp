@@ -845,16 +845,20 @@ extern "C" int orc_trace_bins(const rts_target_mesh *targets, uint32_t n_targets
                 rts_ray_record r = res[k];
                 if (r.received < 0) continue;
                 captured++;
-                // host post-process, ray_tracer.cpp:1190-1258 with RCS = Gt = Gr = 1
+                // host post-process, ray_tracer.cpp:1190-1258; Target::GetRCS -> pulse->targ_rcs[k] (NULL = 1),
+                // Transmitter/Receiver::GetGain -> pulse->gain_tx / gain_rx (0 = 1)
                 BinKey key;
                 key.rx = r.received;
                 for (uint32_t c = 0; c < RTS_MAX_DEPTH; c++) key.path[c] = -1;
                 for (uint32_t c = 0; c < L.D; c++) {
                     int targ_k = ti[(size_t)k * L.D + c];
                     key.path[c] = targ_k;
-                    if (targ_k >= 0) r.power *= 1.0;
+                    if (targ_k >= 0) {
+                        const double targRCS = pulse->targ_rcs ? pulse->targ_rcs[targ_k] : 1.0; // :1226
+                        r.power *= targRCS;                                                     // :1228
+                    }
                 }
-                const double Gt = 1.0, Gr = 1.0;
+                const double Gt = pulse->gain_tx != 0 ? pulse->gain_tx : 1.0, Gr = pulse->gain_rx != 0 ? pulse->gain_rx : 1.0;
                 r.power *= (Wl * Wl * Gt * Gr);
                 double Vr = r.doppler / 2;
                 r.doppler = carrier * (((1 + Vr / cspeed) / (1 - Vr / cspeed)) - 1);
@@ -900,6 +904,7 @@ extern "C" int orc_trace_bins(const rts_target_mesh *targets, uint32_t n_targets
             o.direct = kv.second.direct ? 1 : 0;
             o.npath = a.n; o.sum_sqrt_power = a.sp; o.sum_delay = a.sd; o.sum_phase = a.sph; o.sum_doppler = a.sdop;
             o.min_slot = a.min_slot;
+            o.own_min_slot = kv.second.min_slot;
             // aggregation.cu:86-92
             if (a.n > 0) {
                 o.power = pow(a.sp / a.n, 2);

@@ -61,7 +61,7 @@ int orc_trace(const rts_target_mesh *targets, uint32_t n_targets, const rts_puls
               rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle, int32_t *tri_path,
               uint8_t *edge_flags, rts_stats *stats);
 
-/* Launch + host post-process (RCS = Gt = Gr = 1) + binned aggregation without materialising
+/* Launch + host post-process (RCS = pulse->targ_rcs[k] or 1, Gt/Gr = pulse->gain_tx/gain_rx or 1) + binned aggregation without materialising
  * per-ray arrays.  bins sorted by (rx, path).  Returns number of bins in *n_bins (may exceed cap). */
 int orc_trace_bins(const rts_target_mesh *targets, uint32_t n_targets, const rts_pulse *pulse, int use_bvh,
                    rts_bin *bins, uint32_t cap, uint32_t *n_bins, rts_stats *stats);
@@ -87,6 +87,13 @@ int orc_aggregate_binned(rts_ray_record *rx_results, const int32_t *rx_intersect
 
 /* ray_tracer.cpp:1289-1294: sort + unique of path_match. Returns count; out may be NULL. */
 uint32_t orc_unique_paths(const int32_t *path_match, uint32_t received, int32_t *out);
+
+/* ray_tracer.cpp:1289-1320 on the arrays rs::kernel_wrapper returned: one response per unique path_match
+ * value u, carrying ray u's aggregated power / delay / Doppler / phase (the InterpPoint arguments) and,
+ * as `slot`, rx_slots[u] (the result-slot index of that received ray).  Returns the count. */
+uint32_t orc_responses(const rts_ray_record *rx_results, const double *delay, const double *phase,
+                       const int32_t *path_match, const uint64_t *rx_slots, uint32_t received,
+                       rts_response *out, uint32_t cap);
 
 /* Mesh generators, ray_tracer.cpp:156-170, 226-297, 300-426, 429-504.  Two-call protocol:
  * call with NULL outputs to obtain counts, then with buffers. */

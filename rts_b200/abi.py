@@ -55,6 +55,7 @@ class RtsPulse(C.Structure):
         ("n_rx", C.c_uint32), ("n_targets", C.c_uint32),
         ("rx", C.POINTER(RtsRxSphere)), ("targ_vel", C.POINTER(C.c_double)),
         ("ray_begin", C.c_uint64), ("ray_count", C.c_uint64), ("ray_stride", C.c_uint64),
+        ("targ_rcs", C.POINTER(C.c_double)), ("gain_tx", C.c_double), ("gain_rx", C.c_double),
     ]
 
 
@@ -62,7 +63,7 @@ class RtsBin(C.Structure):
     _fields_ = [
         ("rx", C.c_int32), ("path", C.c_int32 * RTS_MAX_DEPTH), ("direct", C.c_int32),
         ("npath", C.c_double), ("sum_sqrt_power", C.c_double), ("sum_delay", C.c_double),
-        ("sum_phase", C.c_double), ("sum_doppler", C.c_double), ("min_slot", C.c_uint64),
+        ("sum_phase", C.c_double), ("sum_doppler", C.c_double), ("min_slot", C.c_uint64), ("own_min_slot", C.c_uint64),
         ("power", C.c_double), ("delay", C.c_double), ("phase", C.c_double), ("doppler", C.c_double),
     ]
 
@@ -70,10 +71,18 @@ class RtsBin(C.Structure):
 BIN_DTYPE = np.dtype(
     [("rx", "<i4"), ("path", "<i4", (RTS_MAX_DEPTH,)), ("direct", "<i4"), ("npath", "<f8"),
      ("sum_sqrt_power", "<f8"), ("sum_delay", "<f8"), ("sum_phase", "<f8"), ("sum_doppler", "<f8"),
-     ("min_slot", "<u8"), ("power", "<f8"), ("delay", "<f8"), ("phase", "<f8"), ("doppler", "<f8")],
+     ("min_slot", "<u8"), ("own_min_slot", "<u8"), ("power", "<f8"), ("delay", "<f8"), ("phase", "<f8"), ("doppler", "<f8")],
     align=True,
 )
 assert BIN_DTYPE.itemsize == C.sizeof(RtsBin), (BIN_DTYPE.itemsize, C.sizeof(RtsBin))
+
+
+class RtsResponse(C.Structure):
+    _fields_ = [("rx", C.c_int32), ("_pad", C.c_int32), ("slot", C.c_uint64), ("power", C.c_double), ("delay", C.c_double),
+                ("doppler", C.c_double), ("phase", C.c_double)]
+
+
+RESPONSE_DTYPE = np.dtype([("rx", "<i4"), ("_pad", "<i4"), ("slot", "<u8"), ("power", "<f8"), ("delay", "<f8"), ("doppler", "<f8"), ("phase", "<f8")])
 
 
 class RtsStats(C.Structure):
@@ -125,6 +134,9 @@ class PulseSpec:
     ray_begin: int = 0
     ray_count: int = 0
     ray_stride: int = 0
+    targ_rcs: Optional[np.ndarray] = None  # [K] scalar RCS per target (fused bins), None = 1
+    gain_tx: float = 1.0
+    gain_rx: float = 1.0
 
     @property
     def rays(self) -> int:
@@ -193,4 +205,10 @@ class CPulse:
         p.n_targets = n_targets
         p.targ_vel = self.vel.ctypes.data_as(C.POINTER(C.c_double))
         p.ray_begin, p.ray_count, p.ray_stride = int(spec.ray_begin), int(spec.ray_count), int(spec.ray_stride)
+        self.rcs = None
+        if spec.targ_rcs is not None:
+            self.rcs = np.ascontiguousarray(spec.targ_rcs, dtype=np.float64).reshape(-1)
+            assert self.rcs.shape[0] == n_targets, "targ_rcs must have one entry per target"
+            p.targ_rcs = self.rcs.ctypes.data_as(C.POINTER(C.c_double))
+        p.gain_tx, p.gain_rx = float(spec.gain_tx), float(spec.gain_rx)
         self.c = p

@@ -98,6 +98,7 @@ __global__ void k_emit_bins(const double *__restrict__ sums, const unsigned long
     const double *s = direct ? rx_sums + rx * 5 : sums + g * 5;
     b.npath = s[0]; b.sum_sqrt_power = s[1]; b.sum_delay = s[2]; b.sum_phase = s[3]; b.sum_doppler = s[4];
     b.min_slot = direct ? rx_mins[rx] : mins[g];
+    b.own_min_slot = mins[g];
     // myKernel2 (aggregation.cu:86-92)
     b.power = pow(b.sum_sqrt_power / b.npath, 2);
     b.delay = b.sum_delay / b.npath;

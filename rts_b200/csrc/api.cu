@@ -11,6 +11,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <algorithm>
+#include <vector>
 
 static thread_local char g_err[512] = "";
 
@@ -26,11 +27,12 @@ int rts_fail(int code, const char *fmt, ...)
 extern "C" const char *rts_last_error(void) { return g_err; }
 extern "C" const char *rts_version(void) { return "rts_b200 0.1 (sm_100a; wavefront LBVH tracer; no CPU fallback)"; }
 
-extern "C" int rts_abi_sizes(uint32_t s[8])
+extern "C" int rts_abi_sizes(uint32_t s[10])
 {
     if (!s) return rts_fail(RTS_ERR_ARG, "sizes is NULL");
     s[0] = sizeof(rts_ray_record); s[1] = sizeof(rts_target_mesh); s[2] = sizeof(rts_rx_sphere); s[3] = sizeof(rts_rx_desc);
     s[4] = sizeof(rts_pulse); s[5] = sizeof(rts_bin); s[6] = sizeof(rts_stats); s[7] = sizeof(rts_pose);
+    s[8] = sizeof(rts_response); s[9] = sizeof(rts_sizes);
     return RTS_OK;
 }
 
@@ -95,7 +97,7 @@ static void free_scene(rts_engine *e)
     void **ptrs[] = {(void **)&e->d_base_verts, (void **)&e->d_base_normals, (void **)&e->d_world_verts,
                      (void **)&e->d_world_normals, (void **)&e->d_tris, (void **)&e->d_tri_target, (void **)&e->d_vert_target,
                      (void **)&e->d_norm_target, (void **)&e->d_t_vert_off, (void **)&e->d_t_norm_off, (void **)&e->d_t_tri_off,
-                     (void **)&e->d_t_per_face, (void **)&e->d_t_refl, (void **)&e->d_t_refr, (void **)&e->d_t_vel,
+                     (void **)&e->d_t_per_face, (void **)&e->d_t_refl, (void **)&e->d_t_refr, (void **)&e->d_t_vel, (void **)&e->d_t_rcs,
                      (void **)&e->d_poses};
     for (void **p : ptrs) {
         if (*p) cudaFree(*p);
@@ -197,6 +199,7 @@ extern "C" int rts_scene_set_targets(rts_engine *e, const rts_target_mesh *targe
     if ((rc = upload(&e->d_t_refl, refl))) return rc;
     if ((rc = upload(&e->d_t_refr, refr))) return rc;
     if ((rc = upload(&e->d_t_vel, vel))) return rc;
+    if ((rc = upload(&e->d_t_rcs, refl))) return rc;   // sized [n_targets]; filled per pulse when targ_rcs is given
     if ((rc = upload(&e->d_poses, poses))) return rc;
     if ((rc = bvh_alloc(e))) return rc;
     if ((rc = bvh_build(e))) return rc;
@@ -356,9 +359,12 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     P.cspeed = p->cspeed; P.carrier = p->carrier;
     {
         const double Wl = p->cspeed / p->carrier;                 // ray_tracer.cpp:815
-        const double Gt = 1.0, Gr = 1.0;
+        const double Gt = p->gain_tx != 0 ? p->gain_tx : 1.0;     // Transmitter::GetGain stand-in (:1233)
+        const double Gr = p->gain_rx != 0 ? p->gain_rx : 1.0;     // Receiver::GetGain stand-in (:1234-1235)
         P.wl2gain = (Wl * Wl * Gt * Gr);                          // ray_tracer.cpp:1247
     }
+    P.t_rcs = p->targ_rcs ? e->d_t_rcs : nullptr;
+    P.B = (uint64_t)e->n_targets + 1;
     // path key: digits base B = n_targets + 1 (digit 0 <=> -1)
     const uint64_t B = (uint64_t)e->n_targets + 1;
     P.powB[0] = 1;
@@ -384,6 +390,8 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
         if (p->n_rx) RTS_CUDA(cudaMemcpyAsync(e->d_rx, rx, sizeof(RxDev) * p->n_rx, cudaMemcpyHostToDevice, st));
         if (p->n_targets)
             RTS_CUDA(cudaMemcpyAsync(e->d_t_vel, p->targ_vel, sizeof(double) * 3 * p->n_targets, cudaMemcpyHostToDevice, st));
+        if (p->n_targets && p->targ_rcs)
+            RTS_CUDA(cudaMemcpyAsync(e->d_t_rcs, p->targ_rcs, sizeof(double) * p->n_targets, cudaMemcpyHostToDevice, st));
         RTS_CUDA(cudaStreamSynchronize(st)); // rx[] is a stack array, targ_vel is caller-owned
     }
 
@@ -515,6 +523,39 @@ extern "C" int rts_get_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t 
     if (!e->have_pulse || !(e->last_flags & RTS_OUT_BINS)) return rts_fail(RTS_ERR_STATE, "last pulse did not produce bins");
     RTS_CUDA(cudaSetDevice(e->device));
     return agg_collect_bins(e, out, cap, n);
+}
+
+// ray_tracer.cpp:1289-1320 on the fused bins.  d_pathMatch of a ray = smallest received-list index among the
+// rays it summed (aggregation.cu:68-69); the received list is in result-slot order (ray_tracer.cpp:1190), so
+// slot order == list order.  Non-direct bin: its members share min_slot, which is one of them -> one response
+// with the bin's values.  Direct bin: its members' d_pathMatch is the receiver-wide minimum; that ray is a
+// member of the direct bin only when own_min_slot == min_slot, otherwise the value coincides with another
+// bin's representative and unique() drops it.
+extern "C" int rts_get_responses(rts_engine *e, rts_response *out, uint32_t cap, uint32_t *n)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    if (!e->have_pulse || !(e->last_flags & RTS_OUT_BINS)) return rts_fail(RTS_ERR_STATE, "last pulse did not produce bins");
+    if (!e->bins_finalised) return rts_fail(RTS_ERR_STATE, "bins are not finalised (RTS_NO_FINALISE without rts_finalise_bins)");
+    RTS_CUDA(cudaSetDevice(e->device));
+    uint32_t nb = 0;
+    int rc = agg_collect_bins(e, nullptr, 0, &nb);
+    if (rc) return rc;
+    std::vector<rts_bin> bins(nb ? nb : 1);
+    if (nb && (rc = agg_collect_bins(e, bins.data(), nb, &nb))) return rc;
+    std::vector<rts_response> r;
+    r.reserve(nb);
+    for (uint32_t i = 0; i < nb; i++) {
+        const rts_bin &b = bins[i];
+        if (b.direct && b.own_min_slot != b.min_slot) continue;
+        rts_response x;
+        x.rx = b.rx; x._pad = 0; x.slot = b.min_slot;
+        x.power = b.power; x.delay = b.delay; x.doppler = b.doppler; x.phase = b.phase;
+        r.push_back(x);
+    }
+    std::sort(r.begin(), r.end(), [](const rts_response &a, const rts_response &b) { return a.slot < b.slot; });
+    if (n) *n = (uint32_t)r.size();
+    if (out) for (size_t i = 0; i < r.size() && i < cap; i++) out[i] = r[i];
+    return RTS_OK;
 }
 
 extern "C" int rts_bins_device(rts_engine *e, void **sums, uint64_t *n_sum, void **mins, uint64_t *n_mins)

@@ -86,6 +86,8 @@ struct WaveParams {
     const RxDev *rx;
     // post-process constants (ray_tracer.cpp:1233-1253, aggregation.cu:59-60)
     double cspeed, carrier, wl2gain;
+    const double *t_rcs;            // per-target scalar RCS (Target::GetRCS stand-in, ray_tracer.cpp:1226) or NULL = 1
+    uint64_t B;                     // path-key base = n_targets + 1
     // path key
     uint64_t powB[RTS_MAX_DEPTH + 1];
     uint64_t key_all;               // sum_{c<D} B^c
@@ -133,7 +135,7 @@ struct rts_engine {
     double *d_base_verts = nullptr, *d_base_normals = nullptr, *d_world_verts = nullptr, *d_world_normals = nullptr;
     uint32_t *d_tris = nullptr, *d_tri_target = nullptr, *d_vert_target = nullptr, *d_norm_target = nullptr;
     uint32_t *d_t_vert_off = nullptr, *d_t_norm_off = nullptr, *d_t_tri_off = nullptr, *d_t_per_face = nullptr;
-    double *d_t_refl = nullptr, *d_t_refr = nullptr, *d_t_vel = nullptr;
+    double *d_t_refl = nullptr, *d_t_refr = nullptr, *d_t_vel = nullptr, *d_t_rcs = nullptr;
     rts_pose *d_poses = nullptr;
 
     // BVH

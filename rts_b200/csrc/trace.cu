@@ -542,13 +542,21 @@ __device__ __forceinline__ int miss(const WaveParams &P, Ray &r, Local &L)
     return received;
 }
 
-// Fused host post-process (RCS = Gt = Gr = 1; ray_tracer.cpp:1219-1253) and the per-ray terms of
+// Fused host post-process (per-target scalar RCS, constant Gt/Gr; ray_tracer.cpp:1219-1253) and the per-ray terms of
 // myKernel1 (aggregation.cu:59-69), summed into the (receiver, path) bin.  Lanes of a converged
 // group that hit the same bin are reduced with shuffles first, so one group issues one set of
 // fp64 atomics per distinct bin.
 __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r, int received)
 {
     double pw = r.pw;
+    if (P.t_rcs) { // ray_tracer.cpp:1219-1230: one factor per path-row entry >= 0, in column order
+        unsigned long long k = r.key;
+        for (uint32_t c = 0; c < P.D; c++) {
+            const uint32_t digit = (uint32_t)(k % P.B);
+            k /= P.B;
+            if (digit) pw *= P.t_rcs[digit - 1];
+        }
+    }
     pw *= P.wl2gain;
     const double Vr = r.dop / 2;
     const double dopHz = P.carrier * (((1 + Vr / P.cspeed) / (1 - Vr / P.cspeed)) - 1);

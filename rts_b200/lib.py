@@ -11,8 +11,8 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from .abi import (BIN_DTYPE, RAY_RECORD, CPulse, CScene, PulseSpec, RtsBin, RtsPulse, RtsRxDesc, RtsRxSphere, RtsStats,
-                  RtsTargetMesh, Target)
+from .abi import (BIN_DTYPE, RAY_RECORD, RESPONSE_DTYPE, CPulse, CScene, PulseSpec, RtsBin, RtsPulse, RtsResponse, RtsRxDesc,
+                  RtsRxSphere, RtsStats, RtsTargetMesh, Target)
 
 RTS_OUT_BINS = 1
 RTS_OUT_RECORDS = 2
@@ -49,7 +49,7 @@ EXPORTS = [
     "rts_rx_sphere_from_desc", "rts_result_sizes", "rts_rect_mesh", "rts_sphere_mesh", "rts_file_mesh",
     "rts_rotation_matrix", "rts_scene_set_targets", "rts_scene_set_poses", "rts_scene_rebuild", "rts_scene_bvh_info",
     "rts_scene_get_world_vertices", "rts_scene_get_tri_bounds", "rts_scene_check_bvh", "rts_trace_pulse",
-    "rts_get_stats", "rts_get_wave_profile", "rts_kernel_launches", "rts_get_bins", "rts_get_records", "rts_bins_device", "rts_finalise_bins", "rts_aggregate",
+    "rts_get_stats", "rts_get_wave_profile", "rts_kernel_launches", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_bins_device", "rts_finalise_bins", "rts_aggregate",
 ]
 
 _lib = None
@@ -93,6 +93,7 @@ def load() -> C.CDLL:
     lib.rts_get_wave_profile.argtypes = [vp, u32, P(C.c_float), P(u64), P(u32)]
     lib.rts_kernel_launches.argtypes = [vp, P(u64)]
     lib.rts_get_bins.argtypes = [vp, P(RtsBin), u32, P(u32)]
+    lib.rts_get_responses.argtypes = [vp, P(RtsResponse), u32, P(u32)]
     lib.rts_get_records.argtypes = [vp, vp, P(i32), P(dbl), P(i32)]
     lib.rts_bins_device.argtypes = [vp, P(vp), P(u64), P(vp), P(u64)]
     lib.rts_finalise_bins.argtypes = [vp]
@@ -253,6 +254,14 @@ class Engine:
         _check(self._lib.rts_get_bins(self._h, None, 0, C.byref(n)))
         out = np.zeros(max(1, n.value), dtype=BIN_DTYPE)
         _check(self._lib.rts_get_bins(self._h, out.ctypes.data_as(C.POINTER(RtsBin)), n.value, C.byref(n)))
+        return out[: n.value]
+
+    def responses(self) -> np.ndarray:
+        """One entry per response the reference would emit (ray_tracer.cpp:1289-1320), sorted by representative slot."""
+        n = C.c_uint32()
+        _check(self._lib.rts_get_responses(self._h, None, 0, C.byref(n)))
+        out = np.zeros(max(1, n.value), dtype=RESPONSE_DTYPE)
+        _check(self._lib.rts_get_responses(self._h, out.ctypes.data_as(C.POINTER(RtsResponse)), n.value, C.byref(n)))
         return out[: n.value]
 
     def records(self, rcs=True, tri_path=True):

@@ -73,6 +73,21 @@ def slab(n: int = 64, cubic: bool = False, refr_index: float = 2.0, refl_coeff: 
     return targets, spec
 
 
+def direct_and_plate(n: int = 64, side: int = 1) -> Tuple[List[Target], PulseSpec]:
+    """Direct-ray rule KAT (aggregation.cu:56, ray_tracer.cpp:1289-1294): one receiver that captures both direct rays
+    and rays mirrored by a plate in the plane y = 30*side.  side=+1: the receiver's first received ray (lowest slot) is
+    a direct one, so the direct bin emits its own response; side=-1: a reflected ray comes first and the direct rays'
+    d_pathMatch collapses onto that path's representative."""
+    y = 30.0 * side
+    verts = np.array([[85.0, y, -6.0], [115.0, y, -6.0], [115.0, y, 6.0], [85.0, y, 6.0]])
+    tris = np.array([[0, 1, 2], [0, 2, 3]], dtype=np.uint32)
+    normals = np.tile(np.array([[0.0, -float(side), 0.0]]), (4, 1))
+    targets = [Target(verts, tris, normals, refl_coeff=0.8, refr_index=1.0)]
+    spec = PulseSpec(grid=(1, n, n), max_refl=2, max_refr=0, tx_origin=(0, 0, 0), tx_dir=(0.0, 0.0), tx_span=(0.8, 0.2, 0.0),
+                     rx=[_rx((200.0, 0.0, 0.0), math.pi, 0.0, 10.0, 2.0, 2.0)], targ_vel=np.array([[4.0, 1.0, 0.0]]))
+    return targets, spec
+
+
 # ---- C3: dielectric "ship" -------------------------------------------------------------------
 
 def _superellipsoid(nu: int, nv: int, a: float, b: float, c: float, e1: float = 0.6, e2: float = 0.8):

@@ -12,7 +12,7 @@ import subprocess
 
 import numpy as np
 
-from rts_b200.abi import BIN_DTYPE, RAY_RECORD, CPulse, CScene, PulseSpec, RtsBin, RtsPulse, RtsRxDesc, RtsRxSphere, RtsStats, RtsTargetMesh
+from rts_b200.abi import BIN_DTYPE, RAY_RECORD, RESPONSE_DTYPE, RtsResponse, CPulse, CScene, PulseSpec, RtsBin, RtsPulse, RtsRxDesc, RtsRxSphere, RtsStats, RtsTargetMesh
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
@@ -49,6 +49,8 @@ def oracle() -> C.CDLL:
         lib.orc_aggregate_binned.argtypes = agg
         lib.orc_unique_paths.argtypes = [P(i32), u32, P(i32)]
         lib.orc_unique_paths.restype = u32
+        lib.orc_responses.argtypes = [vp, P(dbl), P(dbl), P(i32), P(u64), u32, P(RtsResponse), u32]
+        lib.orc_responses.restype = u32
         tail = [P(dbl), P(u32), P(u32), P(u32), P(dbl), P(u32)]
         lib.orc_rect_mesh.argtypes = [C.c_float] * 6 + tail
         lib.orc_sphere_mesh.argtypes = [u32] + [C.c_float] * 4 + tail
@@ -173,6 +175,30 @@ def unique_paths(path_match):
     out = np.zeros(max(1, len(pm)), dtype=np.int32)
     n = oracle().orc_unique_paths(pm.ctypes.data_as(C.POINTER(C.c_int32)), len(pm), out.ctypes.data_as(C.POINTER(C.c_int32)))
     return out[:n]
+
+
+def responses(agg, rx_slots):
+    """ray_tracer.cpp:1289-1320 on the output of aggregate(): one response per unique path_match value."""
+    res = np.ascontiguousarray(agg["results"])
+    R = len(res)
+    out = np.zeros(max(1, R), dtype=RESPONSE_DTYPE)
+    slots = np.ascontiguousarray(rx_slots, dtype=np.uint64)
+    dp = lambda a: np.ascontiguousarray(a).ctypes.data_as(C.POINTER(C.c_double))
+    n = oracle().orc_responses(res.ctypes.data_as(C.c_void_p), dp(agg["delay"]), dp(agg["phase"]),
+                               np.ascontiguousarray(agg["path_match"], dtype=np.int32).ctypes.data_as(C.POINTER(C.c_int32)),
+                               slots.ctypes.data_as(C.POINTER(C.c_uint64)), R, out.ctypes.data_as(C.POINTER(RtsResponse)), R)
+    return out[:n]
+
+
+def responses_from_bins(bins):
+    """The same responses derived from (receiver, path) bins (rule documented at rts_get_responses)."""
+    keep = [b for b in bins if not (b["direct"] and b["own_min_slot"] != b["min_slot"])]
+    out = np.zeros(len(keep), dtype=RESPONSE_DTYPE)
+    for i, b in enumerate(sorted(keep, key=lambda b: int(b["min_slot"]))):
+        out[i]["rx"], out[i]["slot"] = b["rx"], b["min_slot"]
+        for f in ("power", "delay", "doppler", "phase"):
+            out[i][f] = b[f]
+    return out
 
 
 def _mesh(fn, *head):

@@ -34,10 +34,10 @@ def test_kernel_wrapper_cpp_symbol_exported():
 
 
 def test_pod_sizes_match_ctypes():
-    sizes = (C.c_uint32 * 8)()
+    sizes = (C.c_uint32 * 10)()
     assert lib.load().rts_abi_sizes(sizes) == 0
     expect = [144, C.sizeof(abi.RtsTargetMesh), C.sizeof(abi.RtsRxSphere), C.sizeof(abi.RtsRxDesc), C.sizeof(abi.RtsPulse),
-              C.sizeof(abi.RtsBin), C.sizeof(abi.RtsStats), C.sizeof(lib.RtsPose)]
+              C.sizeof(abi.RtsBin), C.sizeof(abi.RtsStats), C.sizeof(lib.RtsPose), C.sizeof(abi.RtsResponse), C.sizeof(lib.RtsSizes)]
     assert list(sizes) == expect
 
 

@@ -109,3 +109,32 @@ def test_aggregate_matches_reference_aggregation_cu(engine, seed):
     # and the oracle's literal transcription agrees with the reference kernel too
     b = O.aggregate(res, rows, spec, literal=True, ray_total=R)
     assert np.array_equal(b["path_match"], pm) and np.allclose(b["delay"], acc["delay"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("scene", ["slab", "direct+", "direct-"])
+def test_fused_rcs_gains_and_responses(engine, scene):
+    """RTS_OUT_BINS with per-target RCS and Gt/Gr (the SOARS callbacks of ray_tracer.cpp:1219-1247 as scalars) and
+    rts_get_responses == oracle trace -> host post-process -> literal aggregation -> sort+unique -> InterpPoint
+    arguments (ray_tracer.cpp:1289-1320)."""
+    from rts_b200 import lib as L
+    if scene == "slab":
+        targets, spec = scenes.slab(n=64)
+    else:
+        targets, spec = scenes.direct_and_plate(n=96, side=1 if scene == "direct+" else -1)
+    spec.targ_rcs = np.array([2.5 + 0.75 * k for k in range(len(targets))])
+    spec.gain_tx, spec.gain_rx = 31.0, 7.5
+    engine.set_targets(targets)
+    engine.trace(spec, L.RTS_OUT_BINS)
+    gbins, got = engine.bins(), engine.responses()
+    obins, _ = O.trace_bins(targets, spec, use_bvh=False)
+    parity.assert_bins_close(parity.compare_bins(gbins, obins))
+    assert np.array_equal(gbins["own_min_slot"], obins["own_min_slot"])
+    r = O.trace(targets, spec)
+    rx_res, rx_rows, rx_slots = O.postprocess(r["results"], r["targ_intersect"], spec, rcs_per_target=spec.targ_rcs,
+                                              gain=spec.gain_tx * spec.gain_rx)
+    a = O.aggregate(rx_res, rx_rows, spec, literal=True)
+    want = O.responses(a, rx_slots)
+    assert len(got) == len(want) > 0
+    assert np.array_equal(got["rx"], want["rx"]) and np.array_equal(got["slot"], want["slot"])
+    for f in ("power", "delay", "doppler", "phase"):
+        assert np.allclose(got[f], want[f], rtol=1e-5, atol=1e-300), f

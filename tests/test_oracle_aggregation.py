@@ -86,3 +86,32 @@ def test_trace_bins_equals_postprocess_plus_literal():
         assert b["npath"] == a["npath"][u] and b["min_slot"] == rx_slots[u]
         assert np.isclose(b["power"], a["results"]["power"][u], rtol=1e-12) and np.isclose(b["delay"], a["delay"][u], rtol=1e-13)
         assert np.isclose(b["phase"], a["phase"][u], rtol=1e-11) and np.isclose(b["doppler"], a["results"]["doppler"][u], rtol=1e-11)
+
+
+@pytest.mark.parametrize("scene", ["slab", "direct+", "direct-"])
+def test_responses_with_rcs_and_gains(scene):
+    """Fused bins with per-target RCS and Gt/Gr -> responses == trace -> post-process (ray_tracer.cpp:1190-1258)
+    -> literal aggregation -> sort+unique(pathMatch) -> InterpPoint arguments (ray_tracer.cpp:1289-1320)."""
+    from rts_b200 import scenes
+    if scene == "slab":
+        targets, spec = scenes.slab(n=24)
+    else:
+        targets, spec = scenes.direct_and_plate(n=96, side=1 if scene == "direct+" else -1)
+    spec.targ_rcs = np.array([2.5 + 0.75 * k for k in range(len(targets))])
+    spec.gain_tx, spec.gain_rx = 31.0, 7.5
+    r = O.trace(targets, spec)
+    rx_res, rx_rows, rx_slots = O.postprocess(r["results"], r["targ_intersect"], spec, rcs_per_target=spec.targ_rcs,
+                                              gain=spec.gain_tx * spec.gain_rx)
+    assert len(rx_res) > 0
+    a = O.aggregate(rx_res, rx_rows, spec, literal=True)
+    want = O.responses(a, rx_slots)
+    bins, _ = O.trace_bins(targets, spec, use_bvh=False)
+    got = O.responses_from_bins(bins)
+    assert len(got) == len(want) > 0
+    if scene.startswith("direct"):
+        direct = [b for b in bins if b["direct"]]
+        assert len(direct) == 1 and len(bins) == 2
+        assert (len(got) == 2) == (scene == "direct+")   # the direct bin emits its own response only when a direct ray comes first
+    assert np.array_equal(got["rx"], want["rx"]) and np.array_equal(got["slot"], want["slot"])
+    for f in ("power", "delay", "doppler", "phase"):
+        assert np.allclose(got[f], want[f], rtol=1e-11, atol=1e-300), f
