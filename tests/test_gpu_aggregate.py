@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 import oracle_api as O
+import parity
 from rts_b200 import scenes
 from rts_b200.abi import RAY_RECORD, PulseSpec
 
