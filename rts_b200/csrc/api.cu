@@ -449,13 +449,20 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     for (int w = 0; w < 32; w++) e->wave_ms[w] = 0.f;
     e->n_waves = std::min<uint32_t>(max_waves, 31);
     const bool single_batch = n_primary_total <= batch;
+    // primary-ray tiling (trace.cu: k_wave): with nx == 1 the shard-local index space is a (y,z) plane whose rows
+    // hold ny/stride of this shard's rays; whole bands of four rows are walked in 8x4 tiles
+    P.swz_w = 0; P.swz_limit = 0;
+    if (p->nx == 1 && !getenv("RTS_NO_TILES") && p->ny % stride == 0 && (p->ny / stride) % 8 == 0 && (p->ny / stride) >= 8) {
+        P.swz_w = (uint32_t)(p->ny / stride);
+        P.swz_limit = n_primary_total / (4ull * P.swz_w) * (4ull * P.swz_w);
+    }
     for (uint64_t done = 0; done < n_primary_total; done += batch) {
         const uint64_t nb = std::min<uint64_t>(batch, n_primary_total - done);
         // d_counts: [0..31] queue counts per wave, [32..63] work counters per wave
         RTS_CUDA(cudaMemsetAsync(e->d_counts, 0, sizeof(unsigned long long) * 64, st));
         for (uint32_t w = 0; w < max_waves && w < 31; w++) {
             WaveParams Q = P;
-            Q.ray_begin = begin + done * stride; Q.ray_stride = stride; Q.n_primary = nb;
+            Q.ray_begin = begin; Q.ray_stride = stride; Q.n_primary = nb; Q.batch_base = done;
             Q.in = e->q[w & 1]; Q.out = e->q[(w + 1) & 1];
             Q.in_count = e->d_counts + w;
             Q.out_count = e->d_counts + w + 1;

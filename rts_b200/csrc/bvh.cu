@@ -253,6 +253,7 @@ __global__ void k_pack(const int2 *__restrict__ children, const int2 *__restrict
     const int2 ch = children[i];
     BvhNode nd;
     int refs[2];
+    float cc[2][3], hh[2][3];
 #pragma unroll
     for (int c = 0; c < 2; c++) {
         const int r = c == 0 ? ch.x : ch.y;
@@ -266,11 +267,21 @@ __global__ void k_pack(const int2 *__restrict__ children, const int2 *__restrict
             refs[c] = cnt <= leaf_max ? ~((rg.x << 3) | (cnt - 1)) : r;
             src = node_box + 6 * (size_t)r;
         }
-        float *lo = c == 0 ? nd.lo0 : nd.lo1, *hi = c == 0 ? nd.hi0 : nd.hi1;
 #pragma unroll
-        for (int a = 0; a < 3; a++) { lo[a] = src[a]; hi[a] = src[3 + a]; }
+        for (int a = 0; a < 3; a++) {
+            // centre / half-extent with [c-h, c+h] >= [lo, hi]: the differences are evaluated in fp64 (relative
+            // error 2^-53), rounded up to fp32 and bumped one more ulp, so containment holds exactly
+            const float lo = src[a], hi = src[3 + a];
+            const float c0 = 0.5f * lo + 0.5f * hi;
+            const double d = fmax((double)hi - (double)c0, (double)c0 - (double)lo);
+            cc[c][a] = c0;
+            hh[c][a] = nextafterf(__double2float_ru(d), CUDART_INF_F);
+        }
     }
-    nd.c0 = refs[0]; nd.c1 = refs[1]; nd.pad[0] = nd.pad[1] = 0;
+    nd.c0x = cc[0][0]; nd.c0y = cc[0][1]; nd.h0x = hh[0][0]; nd.h0y = hh[0][1];
+    nd.c1x = cc[1][0]; nd.c1y = cc[1][1]; nd.h1x = hh[1][0]; nd.h1y = hh[1][1];
+    nd.c0z = cc[0][2]; nd.c1z = cc[1][2]; nd.h0z = hh[0][2]; nd.h1z = hh[1][2];
+    nd.ref0 = refs[0]; nd.ref1 = refs[1]; nd.pad[0] = nd.pad[1] = 0;
     float4 *dst = reinterpret_cast<float4 *>(nodes + i);
     const float4 *s4 = reinterpret_cast<const float4 *>(&nd);
     dst[0] = s4[0]; dst[1] = s4[1]; dst[2] = s4[2]; dst[3] = s4[3];

@@ -20,13 +20,17 @@
 #define RTS_REBUILD_RATIO 1.2   // refit falls back to a rebuild when SAH cost exceeds this x the as-built cost
 
 // ---- device layouts -------------------------------------------------------------------------
-// BVH node, 64 B = 4 x 128-bit loads: the two child boxes (fp32, rounded outward exactly like the
-// reference's bound program, triangle_mesh.cu:228-229) and two child references.
+// BVH node, 64 B = 3 x 128-bit + 1 x 64-bit loads: the two child boxes and two child references.
+// A box is stored as centre c and half-extent h (fp32) with [c-h, c+h] containing the fp32 box that the
+// reference's bound program produces (triangle_mesh.cu:228-229, rounded outward) — h is rounded up.
+// The words are ordered so that each 64-bit half of a 128-bit load is one operand of a packed fp32
+// instruction (FFMA2 / FADD2 on sm_100a): (x,y) pairs per child, (child0, child1) pairs for z.
 // child ref >= 0 : index of an internal node;  < 0 : leaf, ~ref = (first_leaf_pos << 3) | (count-1).
 struct __align__(64) BvhNode {
-    float lo0[3], hi0[3];   // child 0
-    float lo1[3], hi1[3];   // child 1
-    int32_t c0, c1;
+    float c0x, c0y, h0x, h0y;   // child 0: centre xy, half-extent xy
+    float c1x, c1y, h1x, h1y;   // child 1
+    float c0z, c1z, h0z, h1z;   // z of both children
+    int32_t ref0, ref1;
     int32_t pad[2];
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
@@ -92,7 +96,12 @@ struct WaveParams {
     uint64_t powB[RTS_MAX_DEPTH + 1];
     uint64_t key_all;               // sum_{c<D} B^c
     // shard
-    uint64_t ray_begin, ray_stride, n_primary;   // primary rays of this batch: index = ray_begin + i*ray_stride
+    uint64_t ray_begin, ray_stride, n_primary;   // primary rays of this batch: index = ray_begin + (batch_base + i)*ray_stride
+    uint64_t batch_base;            // first shard-local primary index of this batch
+    // primary-ray tiling: shard-local indices below swz_limit are visited in 8x4 tiles of the (y,z) launch
+    // plane (one tile per warp) instead of 32x1 strips; swz_w = row length in local indices, 0 = off
+    uint32_t swz_w;
+    uint64_t swz_limit;
     // queues
     RayQueue in, out;
     const unsigned long long *in_count;

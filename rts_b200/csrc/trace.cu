@@ -70,7 +70,7 @@ __device__ __forceinline__ void store_ray(const RayQueue &q, unsigned long long 
 }
 
 // Append one ray per calling thread to the next wave's queue: one atomic per converged group.
-__device__ __forceinline__ void push_ray(const WaveParams &P, const Ray &r, unsigned long long &overflow)
+__device__ __forceinline__ void push_ray(const WaveParams &P, const Ray &r, unsigned &overflow)
 {
     cg::coalesced_group g = cg::coalesced_threads();
     unsigned long long base = 0;
@@ -148,78 +148,96 @@ __device__ __forceinline__ bool tri_accept(const Tri &T, const d3 &o, const d3 &
 
 struct HitRec { int pos; float t; uint32_t id; };
 
-// BVH traversal.  Boxes are tested in fp32 with a rigorous error bound so that the test is
-// conservative with respect to the exact slab distances of the true fp64 ray:
-//   t*_a = (b - o_a) / d_a             exact distance to plane b (b is an fp32 value, exact)
-//   t_a  = fma(b, inv_a, -oi_a)        inv_a = fl32(1/d_a), oi_a = fl32(o_a/d_a)
-//   |t_a - t*_a| <= 2^-24 (2+eps) (|b| + |o_a|) / |d_a|  <=  E_a := 2^-21 (S_a + |o_a|) |inv_a|
-// with S_a = max |coordinate| of the scene box on that axis.  The near distances are lowered and
-// the far distances raised by E_a (folded into the fma addend), so a box is never pruned when the
-// fp64 triangle test (triangle_mesh.cu:121-137) could accept a hit inside it; FMA contraction is
-// harmless here because only the bound matters, not the rounding.  Axes with |d_a| < 1e-20 are
-// ignored (always overlapping).  Closest hit = smallest fp32 t in (tmin, inf), ties to the lowest
-// global triangle id (rtPotentialIntersection semantics with a defined tie rule).
-__device__ __forceinline__ void traverse(const WaveParams &P, const Ray &r, float tmin_f, HitRec &best,
+// Packed fp32 pairs (sm_100a FFMA2 / FADD2): one instruction, two lanes, each lane rounded like the scalar op.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(u64 r, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// BVH traversal.  Boxes are tested in fp32, centre/half-extent form, with a rigorous error bound so
+// that the test is conservative with respect to the exact slab interval of the true fp64 ray (o, d).
+// Per axis a, for a box [c-h, c+h] (c, h exact fp32 values; the box contains the reference's leaf box):
+//   exact      near* = (c - o)/d - h/|d|          far* = (c - o)/d + h/|d|
+//   computed   T = fma(c, inv, -oi)               inv = fl32(1/d), oi = fl32(o/d)   (1/d, o/d evaluated in fp64)
+//              H = fma(h, |inv|, E)               E   = 2^-21 * 1.0001 * (S + |o|) * |inv|
+//              near = T - H                       far = T + H
+// With S = max |coordinate| of the scene box on the axis (|c| <= S, h <= S) and u = 1/|d|:
+//   |T - (c-o)/d| <= 2^-23 (S+|o|) u,  H >= (h u (1 - 2^-24) + E)(1 - 2^-24),  |fl(T -+ H) - (T -+ H)| <= 2^-24 (|T| + H)
+// so near <= near* and far >= far* whenever E >= 6 * 2^-24 (S+|o|) u = 0.75 * 2^-21 (S+|o|) u: a box is never
+// pruned when the fp64 triangle test (triangle_mesh.cu:121-137) could accept a hit inside it.  Only the bound
+// matters here, not bit-reproducibility, so fused multiply-adds are fine.  Axes with |d| < 1e-20 are ignored
+// (T = 0, H = inf: always overlapping).  The x,y lanes of one child and the z lanes of both children are packed
+// fp32 pairs, matching the BvhNode word order: 12 packed instructions test both child boxes.
+// Closest hit = smallest fp32 t in (tmin, inf), ties to the lowest global triangle id
+// (rtPotentialIntersection semantics with a defined tie rule).
+template <bool COUNT>
+__device__ __forceinline__ void traverse(const WaveParams &P, const d3 &o, const d3 &dir, float tmin_f, HitRec &best,
                                          unsigned &n_nodes, unsigned &n_tris, unsigned &stack_ovf)
 {
     best.pos = -1; best.t = RT_DEFAULT_MAX_F; best.id = 0xffffffffu;
     if (P.n_tris == 0) return;
-    const d3 o = mk3(r.ox, r.oy, r.oz), dir = mk3(r.dx, r.dy, r.dz);
-    float inv[3], cn[3], cf[3];
-    bool neg[3];
+    u64 inv_xy, noi_xy, ainv_xy, e_xy, inv_zz, noi_zz, ainv_zz, e_zz;
     {
         const double oo[3] = {o.x, o.y, o.z}, dd[3] = {dir.x, dir.y, dir.z};
+        float inv[3], noi[3], ainv[3], E[3];
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-            neg[a] = signbit(dd[a]);
             if (fabs(dd[a]) < 1e-20) {
-                inv[a] = 0.f; cn[a] = -CUDART_INF_F; cf[a] = CUDART_INF_F;
+                inv[a] = 0.f; noi[a] = 0.f; ainv[a] = 0.f; E[a] = CUDART_INF_F;
             } else {
                 const double id = 1.0 / dd[a];
                 inv[a] = (float)id;
-                const float oi = (float)(oo[a] * id);
-                const float E = 4.76837158203125e-07f * ((P.scene_abs[a] + fabsf((float)oo[a])) * fabsf(inv[a])) * 1.0001f + 1e-30f;
-                cn[a] = -oi - E;
-                cf[a] = -oi + E;
+                noi[a] = -(float)(oo[a] * id);
+                ainv[a] = fabsf(inv[a]);
+                E[a] = 4.76837158203125e-07f * ((P.scene_abs[a] + fabsf((float)oo[a])) * ainv[a]) * 1.0001f + 1e-30f;
             }
         }
+        inv_xy = pk2(inv[0], inv[1]); noi_xy = pk2(noi[0], noi[1]); ainv_xy = pk2(ainv[0], ainv[1]); e_xy = pk2(E[0], E[1]);
+        inv_zz = pk2(inv[2], inv[2]); noi_zz = pk2(noi[2], noi[2]); ainv_zz = pk2(ainv[2], ainv[2]); e_zz = pk2(E[2], E[2]);
     }
     const double tmin_d = (double)tmin_f, tmax_d = (double)RT_DEFAULT_MAX_F;
     float best_pad = CUDART_INF_F;
+    // "while-while" (Aila & Laine 2009): each lane descends internal nodes until it stands on a leaf (or has
+    // nothing left); the warp reconverges at the end of the inner loop, so the fp64 triangle code below runs on
+    // as full a warp as the rays allow instead of being replayed for a few lanes per iteration.
+    constexpr int SENT = 0x7fffffff;       // empty stack; node indices are < 2^28
     int stack[RTS_STACK_DEPTH];
     int sp = 0;
     int cur = P.root_ref;
-    for (;;) {
-        if (cur >= 0) {
-            n_nodes++;
-            const float4 *np = reinterpret_cast<const float4 *>(P.nodes + cur);
-            const float4 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-            const int4 q3 = __ldg(reinterpret_cast<const int4 *>(np + 3));
-            // child 0: lo (q0.x q0.y q0.z) hi (q0.w q1.x q1.y); child 1: lo (q1.z q1.w q2.x) hi (q2.y q2.z q2.w)
-            const float tn0 = fmaxf(fmaxf(__fmaf_rn(neg[0] ? q0.w : q0.x, inv[0], cn[0]), __fmaf_rn(neg[1] ? q1.x : q0.y, inv[1], cn[1])),
-                                    __fmaf_rn(neg[2] ? q1.y : q0.z, inv[2], cn[2]));
-            const float tf0 = fminf(fminf(__fmaf_rn(neg[0] ? q0.x : q0.w, inv[0], cf[0]), __fmaf_rn(neg[1] ? q0.y : q1.x, inv[1], cf[1])),
-                                    __fmaf_rn(neg[2] ? q0.z : q1.y, inv[2], cf[2]));
-            const float tn1 = fmaxf(fmaxf(__fmaf_rn(neg[0] ? q2.y : q1.z, inv[0], cn[0]), __fmaf_rn(neg[1] ? q2.z : q1.w, inv[1], cn[1])),
-                                    __fmaf_rn(neg[2] ? q2.w : q2.x, inv[2], cn[2]));
-            const float tf1 = fminf(fminf(__fmaf_rn(neg[0] ? q1.z : q2.y, inv[0], cf[0]), __fmaf_rn(neg[1] ? q1.w : q2.z, inv[1], cf[1])),
-                                    __fmaf_rn(neg[2] ? q2.x : q2.w, inv[2], cf[2]));
-            const bool h0 = (tn0 <= tf0) & (tf0 >= 0.f) & (tn0 <= best_pad);
-            const bool h1 = (tn1 <= tf1) & (tf1 >= 0.f) & (tn1 <= best_pad);
+    while (cur != SENT) {
+        while ((unsigned)cur < (unsigned)SENT) {
+            if (COUNT) n_nodes++;
+            const ulonglong2 *np = reinterpret_cast<const ulonglong2 *>(P.nodes + cur);
+            const ulonglong2 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);   // (c0xy,h0xy) (c1xy,h1xy) (czz,hzz)
+            const int2 refs = __ldg(reinterpret_cast<const int2 *>(np + 3));
+            const u64 T0 = fma2(q0.x, inv_xy, noi_xy), H0 = fma2(q0.y, ainv_xy, e_xy);
+            const u64 T1 = fma2(q1.x, inv_xy, noi_xy), H1 = fma2(q1.y, ainv_xy, e_xy);
+            const u64 Tz = fma2(q2.x, inv_zz, noi_zz), Hz = fma2(q2.y, ainv_zz, e_zz);
+            float n0x, n0y, f0x, f0y, n1x, n1y, f1x, f1y, nz0, nz1, fz0, fz1;
+            upk2(sub2(T0, H0), n0x, n0y); upk2(add2(T0, H0), f0x, f0y);
+            upk2(sub2(T1, H1), n1x, n1y); upk2(add2(T1, H1), f1x, f1y);
+            upk2(sub2(Tz, Hz), nz0, nz1); upk2(add2(Tz, Hz), fz0, fz1);
+            const float tn0 = fmaxf(fmaxf(n0x, n0y), nz0), tf0 = fminf(fminf(f0x, f0y), fz0);
+            const float tn1 = fmaxf(fmaxf(n1x, n1y), nz1), tf1 = fminf(fminf(f1x, f1y), fz1);
+            // overlap of [tn, tf] with [0, best_pad]
+            const bool h0 = fmaxf(tn0, 0.f) <= fminf(tf0, best_pad);
+            const bool h1 = fmaxf(tn1, 0.f) <= fminf(tf1, best_pad);
             if (h0 & h1) {
                 const bool swap = tn1 < tn0;
-                if (sp < RTS_STACK_DEPTH) stack[sp++] = swap ? q3.x : q3.y;
+                if (sp < RTS_STACK_DEPTH) stack[sp++] = swap ? refs.x : refs.y;
                 else stack_ovf++;
-                cur = swap ? q3.y : q3.x;
-                continue;
-            }
-            if (h0) { cur = q3.x; continue; }
-            if (h1) { cur = q3.y; continue; }
-        } else {
+                cur = swap ? refs.y : refs.x;
+            } else if (h0) cur = refs.x;
+            else if (h1) cur = refs.y;
+            else cur = sp ? stack[--sp] : SENT;
+        }
+        if (cur < 0) {
             const int code = ~cur;
             const int first = code >> 3, cnt = (code & 7) + 1;
             for (int k = 0; k < cnt; k++) {
-                n_tris++;
+                if (COUNT) n_tris++;
                 const Tri T = load_tri(P.trirec, first + k);
                 double t;
                 if (tri_accept(T, o, dir, tmin_d, tmax_d, t)) {
@@ -230,9 +248,8 @@ __device__ __forceinline__ void traverse(const WaveParams &P, const Ray &r, floa
                     }
                 }
             }
+            cur = sp ? stack[--sp] : SENT;
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
     }
 }
 
@@ -260,7 +277,17 @@ __device__ __forceinline__ void cart_to_sph(d3 in, double &azi, double &ele) // 
     ele = atan2(in.z, sqrt(in.x * in.x + in.y * in.y));
 }
 
-struct Local { unsigned long long segments, hits, shaded, captured, multi, edge, refracted, nodes, tris, overflow; };
+// Per-thread event counters, packed three 21-bit fields to a register pair so they do not crowd the
+// traversal loop: a thread can see at most 2^26 / 32 rays per launch (queue capacity 3 * 2^24 < 2^26 rays,
+// claimed 32 at a time by its warp), so no field can overflow.
+struct Local {
+    unsigned long long a;        // hits | shaded << 21 | captured << 42
+    unsigned long long b;        // multi | edge << 21 | refracted << 42
+    unsigned long long nodes, tris;   // only touched by the COUNT instantiation
+    unsigned overflow;
+};
+constexpr unsigned long long C_HIT = 1ull, C_SHADED = 1ull << 21, C_CAPTURED = 1ull << 42;
+constexpr unsigned long long C_MULTI = 1ull, C_EDGE = 1ull << 21, C_REFRACTED = 1ull << 42;
 
 // normal_shader.cu:128-340
 template <bool RECORDS>
@@ -281,14 +308,14 @@ __device__ __forceinline__ void shade(const WaveParams &P, Ray &r, const HitRec 
         finish_chain<RECORDS>(P, r, -1);
         return;
     }
-    L.shaded++;
+    L.a += C_SHADED;
 
     // the winner's attributes, recomputed with the same arithmetic as during traversal
     d3 o = mk3(r.ox, r.oy, r.oz), dir = mk3(r.dx, r.dy, r.dz);
     d3 n;
     double tt, beta, gamma;
     tri_test(T, o, dir, 0.0, 0.0, n, tt, beta, gamma);
-    if (fmin(fmin(beta, gamma), 1 - beta - gamma) < EDGE_EPS) L.edge++;
+    if (fmin(fmin(beta, gamma), 1 - beta - gamma) < EDGE_EPS) L.b += C_EDGE;
     const uint32_t targ = T.target;
     d3 normal;
     if (P.interpolate) { // triangle_mesh.cu:177-190
@@ -365,7 +392,7 @@ __device__ __forceinline__ void shade(const WaveParams &P, Ray &r, const HitRec 
         const float ratio = (float)(pr_n1 / pr_n0);
         f3 nd;
         if (optix_refract(nd, rdir, nf, ratio)) {
-            L.refracted++;
+            L.b += C_REFRACTED;
             const uint32_t cslot = slot + 1;
             const unsigned long long crow = (unsigned long long)r.ray + (unsigned long long)cslot * P.R3;
             Ray c = r;
@@ -522,7 +549,7 @@ __device__ __forceinline__ int miss(const WaveParams &P, Ray &r, Local &L)
                 }
             }
         }
-        if (captures > 1) L.multi++;
+        if (captures > 1) L.b += C_MULTI;
     }
     // Earth (ray_tracer.cu:438-477): only observable through rayLength of unreceived records
     if (RECORDS && end == false) {
@@ -585,23 +612,36 @@ __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r
     }
 }
 
-template <bool PRIMARY, bool RECORDS>
+template <bool PRIMARY, bool RECORDS, bool COUNT>
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_PRIMARY : RTS_WAVE_MIN_BLOCKS) k_wave(const __grid_constant__ WaveParams P)
 {
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned long long n_in = PRIMARY ? P.n_primary : *P.in_count;
-    Local L = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.wave_segs + P.wave_index, n_in);
+    // queue capacity and batch size are < 2^26, so 32-bit indices and a 32-bit work counter suffice
+    const unsigned n_in = PRIMARY ? (unsigned)P.n_primary : (unsigned)*P.in_count;
+    unsigned *work = reinterpret_cast<unsigned *>(P.work_counter);
+    Local L = {0, 0, 0, 0, 0};
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(P.wave_segs + P.wave_index, (unsigned long long)n_in);
+        atomicAdd(&P.counters->segments, (unsigned long long)n_in);   // one closest-hit query per queue entry
+    }
     for (;;) {
-        unsigned long long base = 0;
-        if (lane == 0) base = atomicAdd(P.work_counter, 32ull);
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_in) break;
-        const unsigned long long idx = base + lane;
+        const unsigned idx = base + lane;
         if (idx >= n_in) continue;
         Ray r;
+        unsigned long long rayIndex = 0;
         if (PRIMARY) {
-            const unsigned long long rayIndex = P.ray_begin + idx * P.ray_stride;
+            // shard-local index -> launch index; whole 8x4 tiles of the (y,z) plane per warp where the shape allows
+            unsigned long long g = P.batch_base + idx;
+            if (g < P.swz_limit) {
+                const unsigned tile = (unsigned)(g >> 5), w = (unsigned)g & 31u, tpr = P.swz_w >> 3;
+                const unsigned ty = tile / tpr, tx = tile - ty * tpr;
+                g = (unsigned long long)(ty * 4u + (w >> 3)) * P.swz_w + tx * 8u + (w & 7u);
+            }
+            rayIndex = P.ray_begin + g * P.ray_stride;
             const unsigned long long nxy = (unsigned long long)P.nx * P.ny;
             const uint32_t iz = (uint32_t)(rayIndex / nxy);
             const uint32_t iy = (uint32_t)((rayIndex % nxy) / P.nx);
@@ -613,37 +653,47 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
         } else {
             load_ray_geom(P.in, idx, r);
         }
-        L.segments++;
         HitRec h;
-        unsigned nn = 0, nt = 0, so = 0;
-        traverse(P, r, SCENE_EPS, h, nn, nt, so); // SCENE_EPS == SCENE_EPS_R (ray_tracer.h:9-10)
-        L.nodes += nn; L.tris += nt; L.overflow += so;
+        unsigned nn = 0, nt = 0;
+        traverse<COUNT>(P, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz), SCENE_EPS, h, nn, nt, L.overflow); // SCENE_EPS == SCENE_EPS_R (ray_tracer.h:9-10)
+        if (COUNT) { L.nodes += nn; L.tris += nt; }
         if (PRIMARY) {
             r.len = 0; r.pw = 0; r.dop = 0; r.fx = 0; r.fy = 0; r.fz = 0; r.n0 = 1; r.n1 = 1;
-            r.key = 0; r.ray = (uint32_t)(P.ray_begin + idx * P.ray_stride);
+            r.key = 0; r.ray = (uint32_t)rayIndex;
         } else {
             load_ray_rest(P.in, idx, r);
         }
         if (h.pos >= 0) {
-            L.hits++;
+            L.a += C_HIT;
             shade<RECORDS>(P, r, h, L);
         } else {
             const int received = miss<RECORDS>(P, r, L);
             if (received >= 0) {
-                L.captured++;
+                L.a += C_CAPTURED;
                 if (P.flags & RTS_OUT_BINS) accumulate_bin(P, r, received);
             }
         }
     }
-    // counters: warp reduce, one atomic per warp per counter
+    // counters: unpack, warp reduce (redux.sync), one atomic per warp per non-zero counter
     unsigned long long *c = reinterpret_cast<unsigned long long *>(P.counters);
-    unsigned long long v[10] = {L.segments, L.hits, L.shaded, L.captured, L.multi, L.edge, L.refracted, L.nodes, L.tris, L.overflow};
+    const unsigned f[7] = {(unsigned)(L.a & 0x1fffff), (unsigned)((L.a >> 21) & 0x1fffff), (unsigned)(L.a >> 42),
+                           (unsigned)(L.b & 0x1fffff), (unsigned)((L.b >> 21) & 0x1fffff), (unsigned)(L.b >> 42), L.overflow};
+    // Counters layout: segments, hits, shaded, captured, multi, edge, refracted, nodes, tris, overflow
+    const int slot[7] = {1, 2, 3, 4, 5, 6, 9};
 #pragma unroll
-    for (int k = 0; k < 10; k++) {
-        unsigned long long x = v[k];
+    for (int k = 0; k < 7; k++) {
+        const unsigned x = __reduce_add_sync(0xffffffffu, f[k]);
+        if (lane == 0 && x) atomicAdd(c + slot[k], (unsigned long long)x);
+    }
+    if (COUNT) {
+        unsigned long long v[2] = {L.nodes, L.tris};
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-        if (lane == 0 && x) atomicAdd(c + k, x);
+        for (int k = 0; k < 2; k++) {
+            unsigned long long x = v[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0 && x) atomicAdd(c + 7 + k, x);
+        }
     }
 }
 
@@ -652,27 +702,33 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
 int trace_wave_grid(rts_engine *e)
 {
     if (e->wave_grid) return e->wave_grid;
-    int occ = 0, best = 1 << 30;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wave<true, false>, RTS_WAVE_BLOCK, 0);
-    best = occ > 0 ? occ : 1;
-    e->wave_grid_primary = e->num_sms * best;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wave<false, false>, RTS_WAVE_BLOCK, 0);
-    best = occ > 0 ? occ : 1;
-    e->wave_grid = e->num_sms * best;
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wave<true, false, false>, RTS_WAVE_BLOCK, 0);
+    e->wave_grid_primary = e->num_sms * (occ > 0 ? occ : 1);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wave<false, false, false>, RTS_WAVE_BLOCK, 0);
+    e->wave_grid = e->num_sms * (occ > 0 ? occ : 1);
     return e->wave_grid;
+}
+
+template <bool PRIMARY>
+static void launch_variant(int grid, cudaStream_t st, const WaveParams &p, bool records, bool count)
+{
+    if (records) {
+        if (count) k_wave<PRIMARY, true, true><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        else k_wave<PRIMARY, true, false><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+    } else {
+        if (count) k_wave<PRIMARY, false, true><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        else k_wave<PRIMARY, false, false><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+    }
 }
 
 int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool records)
 {
     trace_wave_grid(e);
     const int grid = primary ? e->wave_grid_primary : e->wave_grid;   // persistent: resident CTAs per SM x SMs
-    if (primary) {
-        if (records) k_wave<true, true><<<grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
-        else k_wave<true, false><<<grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
-    } else {
-        if (records) k_wave<false, true><<<grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
-        else k_wave<false, false><<<grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
-    }
+    const bool count = (p.flags & RTS_COUNT_NODES) != 0;
+    if (primary) launch_variant<true>(grid, e->stream, p, records, count);
+    else launch_variant<false>(grid, e->stream, p, records, count);
     RTS_CUDA(cudaGetLastError());
     e->launches++;
     return RTS_OK;

@@ -44,10 +44,10 @@ for r in rows[2:]:
             i = hdr.index(w)
             d[w] = r[i] + (" " + units[i] if units[i] else "")
     summ.append(d)
-stall = [h for h in hdr if "warp_issue_stalled" in h and h.endswith("per_warp_active.pct")]
+stall = [h for h in hdr if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio")]
 for d, r in zip(summ, rows[2:]):
-    st = sorted(((float(r[hdr.index(h)] or 0), h.split("stalled_")[1].replace("_per_warp_active.pct", "")) for h in stall), reverse=True)[:6]
-    d["top_stalls_pct_of_warp_active"] = {n: round(v, 1) for v, n in st}
+    st = sorted(((float(r[hdr.index(h)] or 0), h.split("stalled_")[1].replace("_per_issue_active.ratio", "")) for h in stall), reverse=True)[:8]
+    d["warps_stalled_per_issue_active"] = {n: round(v, 2) for v, n in st}
 json.dump(summ, open(os.path.join(out_dir, f"{tag}_k_wave_ncu_full.json"), "w"), indent=1)
 for d in summ[:2]:
     print(json.dumps(d, indent=1))
