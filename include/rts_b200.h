@@ -32,6 +32,7 @@ extern "C" {
 #define RTS_COUNT_NODES   4u  /* fill rts_stats.nodes_visited / tris_tested (slower)                 */
 #define RTS_NO_FINALISE   8u  /* leave bins un-finalised (caller reduces across GPUs, then rts_finalise_bins) */
 #define RTS_NO_RCS_ANGLES 16u /* records mode: skip the four atan2 per bounce, leave rcs_angle at -1e6 */
+#define RTS_ASYNC         32u /* return once the pulse is enqueued on the engine's stream; rts_sync / any getter waits */
 
 typedef struct rts_engine rts_engine;
 
@@ -115,6 +116,8 @@ int rts_scene_check_bvh(rts_engine *e, uint64_t *violations);
 
 /* ---- one pulse (replaces rtContextLaunch3D + the result hand-off, ray_tracer.cpp:1165-1258) ---- */
 int rts_trace_pulse(rts_engine *e, const rts_pulse *pulse, uint32_t flags);
+/* Wait for everything enqueued on the engine's stream (RTS_ASYNC pulses, pose updates) and report a deferred error. */
+int rts_sync(rts_engine *e);
 int rts_get_stats(rts_engine *e, rts_stats *out);
 /* Per-bounce-wave profile of the last pulse: device milliseconds (CUDA events on the engine's stream) and
  * the number of ray segments each wave traced, summed over ray batches.  *n = number of waves. */

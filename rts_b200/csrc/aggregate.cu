@@ -237,10 +237,12 @@ int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
     if (!nb || !n_rx) { if (n) *n = 0; return RTS_OK; }
     const uint64_t per_rx = nb / n_rx;
     // receiver totals
-    double *rx_sums = nullptr;
-    unsigned long long *rx_mins = nullptr;
-    RTS_CUDA(cudaMalloc(&rx_sums, sizeof(double) * 5 * n_rx));
-    RTS_CUDA(cudaMalloc(&rx_mins, sizeof(unsigned long long) * n_rx));
+    if (!e->d_rx_sums) {
+        RTS_CUDA(cudaMalloc(&e->d_rx_sums, sizeof(double) * 5 * RTS_MAX_RX));
+        RTS_CUDA(cudaMalloc(&e->d_rx_mins, sizeof(unsigned long long) * RTS_MAX_RX));
+    }
+    double *rx_sums = e->d_rx_sums;
+    unsigned long long *rx_mins = e->d_rx_mins;
     RTS_CUDA(cudaMemsetAsync(rx_sums, 0, sizeof(double) * 5 * n_rx, e->stream));
     RTS_CUDA(cudaMemsetAsync(rx_mins, 0xff, sizeof(unsigned long long) * n_rx, e->stream));
     dim3 grid((unsigned)std::min<uint64_t>(64, (per_rx + 255) / 256), n_rx);
@@ -271,8 +273,6 @@ int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
             return false;
         });
     }
-    cudaFree(rx_sums);
-    cudaFree(rx_mins);
     if (n) *n = count;
     e->stats.n_bins = count;
     return RTS_OK;

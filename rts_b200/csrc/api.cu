@@ -84,6 +84,13 @@ extern "C" int rts_create(int device, rts_engine **out)
     if (const char *lm = getenv("RTS_LEAF_MAX")) { int v = atoi(lm); if (v >= 1 && v <= 8) e->leaf_max = v; }
     for (auto &ev : e->ev) cudaEventCreate(&ev);
     for (auto &ev : e->wave_ev) cudaEventCreate(&ev);
+    for (auto &s : e->stage) cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&e->sah_ev, cudaEventDisableTiming);
+    if (cudaMallocHost((void **)&e->h_rb, sizeof(Readback)) != cudaSuccess) {
+        rts_destroy(e);
+        return rts_fail(RTS_ERR_CUDA, "cudaMallocHost failed");
+    }
+    memset(e->h_rb, 0, sizeof(Readback));
     cudaMalloc(&e->d_wave_segs, sizeof(unsigned long long) * 32);
     cudaMalloc(&e->d_counts, sizeof(unsigned long long) * 64);
     cudaMalloc(&e->d_counters, sizeof(Counters));
@@ -114,14 +121,40 @@ extern "C" void rts_destroy(rts_engine *e)
     cudaStreamSynchronize(e->stream);
     free_scene(e);
     for (int k = 0; k < 2; k++) if (e->q_slab[k]) cudaFree(e->q_slab[k]);
-    void *ptrs[] = {e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count,
+    void *ptrs[] = {e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count, e->d_rx_sums, e->d_rx_mins,
                     e->d_results, e->d_targ_intersect, e->d_tri_path, e->d_rcs_angle};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->wave_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &s : e->stage) { if (s.done) cudaEventDestroy(s.done); if (s.host) cudaFreeHost(s.host); }
+    if (e->sah_ev) cudaEventDestroy(e->sah_ev);
+    if (e->h_rb) cudaFreeHost(e->h_rb);
     if (e->d_wave_segs) cudaFree(e->d_wave_segs);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
+}
+
+// ---- pinned staging ring: the caller's small per-pulse arrays are copied here, then to the device
+// asynchronously, so that no entry point has to wait for a pageable-memory copy ----
+char *stage_acquire(rts_engine *e, size_t bytes)
+{
+    StageSlot &s = e->stage[e->stage_next];
+    if (s.in_flight) { cudaEventSynchronize(s.done); s.in_flight = false; }
+    if (s.cap < bytes) {
+        if (s.host) cudaFreeHost(s.host);
+        s.host = nullptr; s.cap = 0;
+        const size_t cap = std::max<size_t>(bytes, 16384);
+        if (cudaMallocHost((void **)&s.host, cap) != cudaSuccess) return nullptr;
+        s.cap = cap;
+    }
+    return s.host;
+}
+void stage_release(rts_engine *e)
+{
+    StageSlot &s = e->stage[e->stage_next];
+    cudaEventRecord(s.done, e->stream);
+    s.in_flight = true;
+    e->stage_next = (e->stage_next + 1) % 8;
 }
 
 extern "C" int rts_set_stream(rts_engine *e, void *cuda_stream)
@@ -201,10 +234,19 @@ extern "C" int rts_scene_set_targets(rts_engine *e, const rts_target_mesh *targe
     if ((rc = upload(&e->d_t_vel, vel))) return rc;
     if ((rc = upload(&e->d_t_rcs, refl))) return rc;   // sized [n_targets]; filled per pulse when targ_rcs is given
     if ((rc = upload(&e->d_poses, poses))) return rc;
+    e->h_poses = poses;
+    e->moving.assign(n_targets, 0);
     if ((rc = bvh_alloc(e))) return rc;
     if ((rc = bvh_build(e))) return rc;
     e->scene_ready = true;
     return RTS_OK;
+}
+
+static bool same_pose(const rts_pose &a, const rts_pose &b)
+{
+    if ((a.has_rotation != 0) != (b.has_rotation != 0)) return false;
+    if (memcmp(a.t, b.t, sizeof(a.t)) != 0) return false;
+    return !a.has_rotation || memcmp(a.R, b.R, sizeof(a.R)) == 0;
 }
 
 extern "C" int rts_scene_set_poses(rts_engine *e, const rts_pose *poses, uint32_t n_targets)
@@ -213,15 +255,37 @@ extern "C" int rts_scene_set_poses(rts_engine *e, const rts_pose *poses, uint32_
     if (!e->scene_ready) return rts_fail(RTS_ERR_STATE, "no scene committed");
     if (n_targets != e->n_targets) return rts_fail(RTS_ERR_ARG, "%u poses for %u targets", n_targets, e->n_targets);
     RTS_CUDA(cudaSetDevice(e->device));
+    // a target counts as moving from the first pose that differs from the one it had before
+    bool changed = false, grew = false;
+    for (uint32_t k = 0; k < n_targets; k++) {
+        if (!same_pose(poses[k], e->h_poses[k])) {
+            changed = true;
+            if (!e->moving[k]) { e->moving[k] = 1; grew = true; }
+        }
+        e->h_poses[k] = poses[k];
+    }
+    if (grew) e->partial_ready = false;
+    if (!changed) { e->refit_timed = false; e->bvh_info.ms_refit = 0.f; return RTS_OK; }
     cudaEventRecord(e->ev[4], e->stream);
-    RTS_CUDA(cudaMemcpyAsync(e->d_poses, poses, sizeof(rts_pose) * n_targets, cudaMemcpyHostToDevice, e->stream));
+    char *st = stage_acquire(e, sizeof(rts_pose) * n_targets);
+    if (!st) return rts_fail(RTS_ERR_CUDA, "pinned staging allocation failed");
+    memcpy(st, poses, sizeof(rts_pose) * n_targets);
+    RTS_CUDA(cudaMemcpyAsync(e->d_poses, st, sizeof(rts_pose) * n_targets, cudaMemcpyHostToDevice, e->stream));
+    stage_release(e);
     int rc = bvh_refit(e);
     if (rc) return rc;
     cudaEventRecord(e->ev[5], e->stream);
-    // the pose array is caller-owned pageable memory: make the copy complete before returning
-    RTS_CUDA(cudaStreamSynchronize(e->stream));
-    cudaEventElapsedTime(&e->bvh_info.ms_refit, e->ev[4], e->ev[5]);
-    return RTS_OK;
+    e->refit_timed = true;
+    return RTS_OK;   // nothing waited for: the transform and refit run on the engine's stream
+}
+
+static void collect_refit_time(rts_engine *e)
+{
+    if (!e->refit_timed) return;
+    cudaEventSynchronize(e->ev[5]);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]) == cudaSuccess) e->bvh_info.ms_refit = ms;
+    e->refit_timed = false;
 }
 
 extern "C" int rts_scene_rebuild(rts_engine *e)
@@ -235,6 +299,13 @@ extern "C" int rts_scene_rebuild(rts_engine *e)
 extern "C" int rts_scene_bvh_info(rts_engine *e, rts_bvh_info *out)
 {
     if (!e || !out) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    if (e->scene_ready) {
+        RTS_CUDA(cudaSetDevice(e->device));
+        collect_refit_time(e);
+        bvh_sync_info(e);
+        int rc = bvh_read_scene_box(e);
+        if (rc) return rc;
+    }
     *out = e->bvh_info;
     out->sah_at_build = e->sah_at_build;
     out->builds = e->builds;
@@ -345,7 +416,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     WaveParams P;
     memset(&P, 0, sizeof(P));
     P.nodes = e->d_nodes; P.trirec = e->d_trirec; P.root_ref = e->root_ref; P.n_tris = e->n_tris;
-    for (int a = 0; a < 3; a++) P.scene_abs[a] = e->scene_abs[a];
+    P.scene_abs = e->d_scene_abs;
     P.world_normals = e->d_world_normals; P.tris = e->d_tris;
     P.t_norm_off = e->d_t_norm_off; P.t_tri_off = e->d_t_tri_off; P.t_per_face = e->d_t_per_face;
     P.t_refl = e->d_t_refl; P.t_refr = e->d_t_refr; P.t_vel = e->d_t_vel;
@@ -377,22 +448,31 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     P.key_all = 0;
     for (uint32_t c = 0; c < sz.depth_total; c++) P.key_all += P.powB[c];
     P.flags = flags;
+    P.chain_below = getenv("RTS_NO_CHAIN") ? 0u : (1u << 18);
 
-    // receivers, target velocities
+    // receivers, target velocities, per-target RCS: through the pinned staging ring, no waiting
     {
-        RxDev rx[RTS_MAX_RX];
+        const size_t rx_bytes = sizeof(RxDev) * p->n_rx, vel_bytes = sizeof(double) * 3 * p->n_targets;
+        const size_t rcs_bytes = p->targ_rcs ? sizeof(double) * p->n_targets : 0;
+        char *stg = stage_acquire(e, rx_bytes + vel_bytes + rcs_bytes + 64);
+        if (!stg) return rts_fail(RTS_ERR_CUDA, "pinned staging allocation failed");
+        RxDev *rx = reinterpret_cast<RxDev *>(stg);
         for (uint32_t j = 0; j < p->n_rx; j++) {
             rx[j].cx = p->rx[j].centre[0]; rx[j].cy = p->rx[j].centre[1]; rx[j].cz = p->rx[j].centre[2];
             rx[j].radius = p->rx[j].radius;
             rx[j].min_theta = p->rx[j].min_theta; rx[j].max_theta = p->rx[j].max_theta;
             rx[j].min_phi = p->rx[j].min_phi; rx[j].max_phi = p->rx[j].max_phi;
         }
-        if (p->n_rx) RTS_CUDA(cudaMemcpyAsync(e->d_rx, rx, sizeof(RxDev) * p->n_rx, cudaMemcpyHostToDevice, st));
-        if (p->n_targets)
-            RTS_CUDA(cudaMemcpyAsync(e->d_t_vel, p->targ_vel, sizeof(double) * 3 * p->n_targets, cudaMemcpyHostToDevice, st));
-        if (p->n_targets && p->targ_rcs)
-            RTS_CUDA(cudaMemcpyAsync(e->d_t_rcs, p->targ_rcs, sizeof(double) * p->n_targets, cudaMemcpyHostToDevice, st));
-        RTS_CUDA(cudaStreamSynchronize(st)); // rx[] is a stack array, targ_vel is caller-owned
+        if (p->n_rx) RTS_CUDA(cudaMemcpyAsync(e->d_rx, rx, rx_bytes, cudaMemcpyHostToDevice, st));
+        if (p->n_targets) {
+            memcpy(stg + rx_bytes, p->targ_vel, vel_bytes);
+            RTS_CUDA(cudaMemcpyAsync(e->d_t_vel, stg + rx_bytes, vel_bytes, cudaMemcpyHostToDevice, st));
+        }
+        if (rcs_bytes) {
+            memcpy(stg + rx_bytes + vel_bytes, p->targ_rcs, rcs_bytes);
+            RTS_CUDA(cudaMemcpyAsync(e->d_t_rcs, stg + rx_bytes + vel_bytes, rcs_bytes, cudaMemcpyHostToDevice, st));
+        }
+        stage_release(e);
     }
 
     // bins
@@ -476,39 +556,65 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
         if (single_batch) cudaEventRecord(e->wave_ev[e->n_waves], st);
     }
     cudaEventRecord(e->ev[1], st);
-    Counters c;
-    RTS_CUDA(cudaMemcpyAsync(&c, e->d_counters, sizeof(c), cudaMemcpyDeviceToHost, st));
-    RTS_CUDA(cudaStreamSynchronize(st));
-    float ms = 0;
-    cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
-    RTS_CUDA(cudaMemcpy(e->wave_segs, e->d_wave_segs, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost));
-    if (single_batch && n_primary_total)
-        for (uint32_t w = 0; w < e->n_waves; w++) cudaEventElapsedTime(&e->wave_ms[w], e->wave_ev[w], e->wave_ev[w + 1]);
-
-    rts_stats &s = e->stats;
-    memset(&s, 0, sizeof(s));
-    s.primary_rays = n_primary_total; s.segments = c.segments; s.hits = c.hits; s.shaded_hits = c.shaded;
-    s.captured = c.captured; s.multi_captured = c.multi; s.edge_rays = c.edge; s.refracted = c.refracted;
-    s.nodes_visited = c.nodes; s.tris_tested = c.tris; s.waves = waves;
-    s.ms_trace = ms; s.ms_update = e->bvh_info.ms_refit; s.ms_total = ms;
+    // read-back of the counters into pinned memory; folded into the stats by pulse_collect()
+    RTS_CUDA(cudaMemcpyAsync(&e->h_rb->counters, e->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    RTS_CUDA(cudaMemcpyAsync(e->h_rb->wave_segs, e->d_wave_segs, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost, st));
+    e->pulse_pending = true;
+    e->pulse_single_batch = single_batch && n_primary_total;
+    e->pulse_primary = n_primary_total; e->pulse_waves = waves;
     e->have_pulse = true; e->last_flags = flags; e->last_sizes = sz;
     e->last_B = (uint32_t)B; e->last_D = sz.depth_total; e->last_nrx = p->n_rx;
     e->bins_finalised = !(flags & RTS_NO_FINALISE);
+    if (flags & RTS_ASYNC) return RTS_OK;
+    return pulse_collect(e);
+}
+
+// Wait for the pulse in flight and fold its read-back into e->stats / the wave profile.
+int pulse_collect(rts_engine *e)
+{
+    if (!e->pulse_pending) return RTS_OK;
+    RTS_CUDA(cudaStreamSynchronize(e->stream));
+    e->pulse_pending = false;
+    const Counters c = e->h_rb->counters;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+    memcpy(e->wave_segs, e->h_rb->wave_segs, sizeof(e->wave_segs));
+    for (int w = 0; w < 32; w++) e->wave_ms[w] = 0.f;
+    if (e->pulse_single_batch)
+        for (uint32_t w = 0; w < e->n_waves; w++) cudaEventElapsedTime(&e->wave_ms[w], e->wave_ev[w], e->wave_ev[w + 1]);
+    collect_refit_time(e);
+    rts_stats &s = e->stats;
+    memset(&s, 0, sizeof(s));
+    s.primary_rays = e->pulse_primary; s.segments = c.segments; s.hits = c.hits; s.shaded_hits = c.shaded;
+    s.captured = c.captured; s.multi_captured = c.multi; s.edge_rays = c.edge; s.refracted = c.refracted;
+    s.nodes_visited = c.nodes; s.tris_tested = c.tris; s.waves = e->pulse_waves;
+    s.ms_trace = ms; s.ms_update = e->bvh_info.ms_refit; s.ms_total = ms;
     if (c.overflow) return rts_fail(RTS_ERR_CAPACITY, "%llu ray states dropped (queue/stack overflow)", (unsigned long long)c.overflow);
+    return RTS_OK;
+}
+
+extern "C" int rts_sync(rts_engine *e)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    RTS_CUDA(cudaSetDevice(e->device));
+    if (e->pulse_pending) return pulse_collect(e);
+    RTS_CUDA(cudaStreamSynchronize(e->stream));
     return RTS_OK;
 }
 
 extern "C" int rts_get_stats(rts_engine *e, rts_stats *out)
 {
     if (!e || !out) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    int rc = pulse_collect(e);
     *out = e->stats;
-    return RTS_OK;
+    return rc;
 }
 
 extern "C" int rts_get_wave_profile(rts_engine *e, uint32_t cap, float *ms, uint64_t *segments, uint32_t *n)
 {
     if (!e || !n) return rts_fail(RTS_ERR_ARG, "NULL argument");
     if (!e->have_pulse) return rts_fail(RTS_ERR_STATE, "no pulse traced yet");
+    pulse_collect(e);
     *n = e->n_waves;
     for (uint32_t w = 0; w < e->n_waves && w < cap; w++) {
         if (ms) ms[w] = e->wave_ms[w];
@@ -529,6 +635,8 @@ extern "C" int rts_get_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t 
     if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
     if (!e->have_pulse || !(e->last_flags & RTS_OUT_BINS)) return rts_fail(RTS_ERR_STATE, "last pulse did not produce bins");
     RTS_CUDA(cudaSetDevice(e->device));
+    int rc = pulse_collect(e);
+    if (rc) return rc;
     return agg_collect_bins(e, out, cap, n);
 }
 
@@ -545,7 +653,9 @@ extern "C" int rts_get_responses(rts_engine *e, rts_response *out, uint32_t cap,
     if (!e->bins_finalised) return rts_fail(RTS_ERR_STATE, "bins are not finalised (RTS_NO_FINALISE without rts_finalise_bins)");
     RTS_CUDA(cudaSetDevice(e->device));
     uint32_t nb = 0;
-    int rc = agg_collect_bins(e, nullptr, 0, &nb);
+    int rc = pulse_collect(e);
+    if (rc) return rc;
+    rc = agg_collect_bins(e, nullptr, 0, &nb);
     if (rc) return rc;
     std::vector<rts_bin> bins(nb ? nb : 1);
     if (nb && (rc = agg_collect_bins(e, bins.data(), nb, &nb))) return rc;
@@ -590,6 +700,10 @@ extern "C" int rts_get_records(rts_engine *e, rts_ray_record *results, int32_t *
     if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
     if (!e->have_pulse || !(e->last_flags & RTS_OUT_RECORDS)) return rts_fail(RTS_ERR_STATE, "last pulse did not produce records");
     RTS_CUDA(cudaSetDevice(e->device));
+    {
+        int rc = pulse_collect(e);
+        if (rc) return rc;
+    }
     RTS_CUDA(cudaStreamSynchronize(e->stream));
     const rts_sizes &sz = e->last_sizes;
     const size_t n = sz.ray_total, D = sz.depth_total, W = sz.tri_cols;

@@ -34,12 +34,14 @@ __device__ __forceinline__ float ord2f(unsigned u)
 
 // world = (has_rotation ? R*base : base) + t ; normals: rotation only.  Accumulation order of
 // matrix_multiply (ray_tracer.cpp:120-137): ((0 + R[i][0]*v0) + R[i][1]*v1) + R[i][2]*v2.
+// `list` (optional) restricts the kernel to the elements it names — the vertices of the targets that move.
 __global__ void k_transform(const double *__restrict__ base, double *__restrict__ world,
                             const uint32_t *__restrict__ owner, const rts_pose *__restrict__ poses, uint32_t n,
-                            int translate)
+                            int translate, const uint32_t *__restrict__ list)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (list) i = list[i];
     const rts_pose &P = poses[owner[i]];
     double v0 = base[3 * (size_t)i], v1 = base[3 * (size_t)i + 1], v2 = base[3 * (size_t)i + 2];
     double w0 = v0, w1 = v1, w2 = v2;
@@ -57,11 +59,13 @@ __global__ void k_transform(const double *__restrict__ base, double *__restrict_
 // triangle_mesh.cu:204-233: fp64 min/max, narrowed with directed rounding.
 __global__ void k_tri_boxes(const double *__restrict__ world, const uint32_t *__restrict__ tris,
                             const uint32_t *__restrict__ tri_target, const uint32_t *__restrict__ t_vert_off,
-                            float *__restrict__ tri_box, unsigned *__restrict__ scene_box, uint32_t n)
+                            float *__restrict__ tri_box, unsigned *__restrict__ scene_box, uint32_t n,
+                            const uint32_t *__restrict__ list)
 {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
     if (i < n) {
+        if (list) i = list[i];
         const uint32_t voff = t_vert_off[tri_target[i]];
         double mn[3], mx[3];
 #pragma unroll
@@ -181,11 +185,14 @@ __global__ void k_leaf_of_tri(const uint32_t *__restrict__ order, uint32_t *__re
 // Leaf-ordered triangle records: one thread per leaf position, 5 x 128-bit stores.
 __global__ void k_tri_records(const double *__restrict__ world, const uint32_t *__restrict__ tris,
                               const uint32_t *__restrict__ tri_target, const uint32_t *__restrict__ t_vert_off,
-                              const uint32_t *__restrict__ order, TriRec *__restrict__ rec, uint32_t n)
+                              const uint32_t *__restrict__ order, TriRec *__restrict__ rec, uint32_t n,
+                              const uint32_t *__restrict__ list, const uint32_t *__restrict__ leaf_of_tri)
 {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
-    const uint32_t id = order[p];
+    uint32_t id;
+    if (list) { id = list[p]; p = leaf_of_tri[id]; }   // one thread per moving triangle
+    else id = order[p];                                 // one thread per leaf position
     const uint32_t targ = tri_target[id];
     const uint32_t voff = t_vert_off[targ];
     double v[9];
@@ -209,17 +216,23 @@ __device__ __forceinline__ void load_box(const float *p, float b[6])
     for (int a = 0; a < 6; a++) b[a] = __ldcg(p + a);
 }
 
-// Bottom-up fit: the second thread to arrive at a node unions its children and carries on.
+// Bottom-up fit: the last thread to arrive at a node unions its children and carries on.  Full refit: one thread
+// per leaf, two arrivals per node.  Partial refit: one thread per moving triangle (`list`), and a node waits for as
+// many arrivals as it has children with a moving triangle below them (`mark`, two bits per node); the boxes of
+// untouched children are still valid.
 __global__ void k_fit(const int2 *__restrict__ children, const int32_t *__restrict__ parent,
                       const uint32_t *__restrict__ order, const float *tri_box, float *node_box,
-                      uint32_t *__restrict__ flags, int n)
+                      uint32_t *__restrict__ flags, int n, int count, const uint32_t *__restrict__ list,
+                      const uint32_t *__restrict__ leaf_of_tri, const uint32_t *__restrict__ mark)
 {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
+    if (p >= count) return;
+    if (list) p = (int)leaf_of_tri[list[p]];
     int cur = parent[(n - 1) + p];
     while (cur >= 0) {
         __threadfence();
-        if (atomicAdd(flags + cur, 1u) == 0u) return;
+        const unsigned need = mark ? (unsigned)__popc(mark[cur] & 3u) : 2u;
+        if (atomicAdd(flags + cur, 1u) + 1u < need) return;
         const int2 ch = children[cur];
         float a[6], b[6];
         load_box(ch.x >= 0 ? node_box + 6 * (size_t)ch.x : tri_box + 6 * (size_t)order[~ch.x], a);
@@ -235,9 +248,13 @@ __global__ void k_fit(const int2 *__restrict__ children, const int32_t *__restri
 
 __global__ void k_pack(const int2 *__restrict__ children, const int2 *__restrict__ range,
                        const uint32_t *__restrict__ order, const float *__restrict__ tri_box,
-                       const float *__restrict__ node_box, BvhNode *__restrict__ nodes, int n, double *sah, int leaf_max)
+                       const float *__restrict__ node_box, BvhNode *__restrict__ nodes, int n, double *sah, int leaf_max,
+                       int count, const uint32_t *__restrict__ list, uint32_t *__restrict__ flags)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < count;
+    if (live && list) { i = (int)list[i]; flags[i] = 0u; }   // partial refit: re-arm the node's arrival counter
+    if (!live) i = n;
     // surface-area-heuristic cost of the tree = sum of internal-node box areas (relative to the root's):
     // warp-reduced, one fp64 atomic per warp
     double area = 0.0;
@@ -287,6 +304,97 @@ __global__ void k_pack(const int2 *__restrict__ children, const int2 *__restrict
     dst[0] = s4[0]; dst[1] = s4[1]; dst[2] = s4[2]; dst[3] = s4[3];
 }
 
+// ---- partial refit set-up (run when the set of moving targets changes) ----
+// Elements owned by a moving target, appended in arbitrary order (one atomic per warp).
+__global__ void k_select_owned(const uint32_t *__restrict__ owner, const uint32_t *__restrict__ moving, uint32_t n,
+                               uint32_t *__restrict__ out, uint32_t *__restrict__ count)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool take = i < n && moving[owner[i]] != 0u;
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (!m) return;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (take) out[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
+// mark[node] bit 0 / bit 1: child 0 / child 1 has a moving triangle below it.
+__global__ void k_mark_paths(const uint32_t *__restrict__ list, uint32_t count, const uint32_t *__restrict__ leaf_of_tri,
+                             const int2 *__restrict__ children, const int32_t *__restrict__ parent, int n,
+                             uint32_t *__restrict__ mark)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= count) return;
+    const int p = (int)leaf_of_tri[list[k]];
+    int from = ~p;
+    int cur = parent[(n - 1) + p];
+    while (cur >= 0) {
+        const unsigned bit = children[cur].x == from ? 1u : 2u;
+        if (atomicOr(mark + cur, bit) & bit) return;   // whoever set it first carries on upward
+        from = cur;
+        cur = parent[cur];
+    }
+}
+__global__ void k_select_marked(const uint32_t *__restrict__ mark, uint32_t n, uint32_t *__restrict__ out,
+                                uint32_t *__restrict__ count)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool take = i < n && mark[i] != 0u;
+    const unsigned m = __ballot_sync(0xffffffffu, take);
+    if (!m) return;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t base = 0;
+    if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(count, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (take) out[base + __popc(m & ((1u << lane) - 1u))] = i;
+}
+// Scene bounds of the triangles that never move and SAH area of the nodes no moving triangle touches.
+__global__ void k_static_box(const float *__restrict__ tri_box, const uint32_t *__restrict__ tri_target,
+                             const uint32_t *__restrict__ moving, uint32_t n, unsigned *__restrict__ box)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, hi[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+    if (i < n && moving[tri_target[i]] == 0u) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) { lo[a] = tri_box[6 * (size_t)i + a]; hi[a] = tri_box[6 * (size_t)i + 3 + a]; }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        float l = lo[a], h = hi[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            l = fminf(l, __shfl_xor_sync(0xffffffffu, l, o));
+            h = fmaxf(h, __shfl_xor_sync(0xffffffffu, h, o));
+        }
+        if ((threadIdx.x & 31) == 0 && l <= h) {
+            atomicMin(box + a, f2ord(l));
+            atomicMax(box + 3 + a, f2ord(h));
+        }
+    }
+}
+__global__ void k_static_sah(const float *__restrict__ node_box, const uint32_t *__restrict__ mark, int n, double *sah)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double area = 0.0;
+    if (i < n - 1 && mark[i] == 0u) {
+        const float *b = node_box + 6 * (size_t)i;
+        const double dx = (double)b[3] - b[0], dy = (double)b[4] - b[1], dz = (double)b[5] - b[2];
+        area = dx * dy + dy * dz + dz * dx;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(0xffffffffu, area, o);
+    if ((threadIdx.x & 31) == 0 && area > 0.0) atomicAdd(sah, area);
+}
+// max |coordinate| of the scene box per axis, for the slab-test error bound of the traversal (trace.cu)
+__global__ void k_scene_abs(const unsigned *__restrict__ box, float *__restrict__ out, uint32_t n_tris)
+{
+    const int a = threadIdx.x;
+    if (a >= 3) return;
+    const float m = fmaxf(fabsf(ord2f(box[a])), fabsf(ord2f(box[3 + a])));
+    out[a] = (n_tris && m < 3.0e38f) ? m : 0.f;
+}
+
 // Invariant check: every triangle box inside all of its ancestors' boxes.
 __global__ void k_check(const int32_t *__restrict__ parent, const uint32_t *__restrict__ order,
                         const float *__restrict__ tri_box, const float *__restrict__ node_box, int n,
@@ -324,11 +432,16 @@ void bvh_free(rts_engine *e)
     void **ptrs[] = {(void **)&e->d_morton, (void **)&e->d_morton_sorted, (void **)&e->d_order_in, (void **)&e->d_order,
                      (void **)&e->d_leaf_of_tri, (void **)&e->d_tri_box, (void **)&e->d_node_box, (void **)&e->d_scene_box,
                      (void **)&e->d_parent, (void **)&e->d_children, (void **)&e->d_range, (void **)&e->d_fit_flags,
-                     (void **)&e->d_nodes, (void **)&e->d_trirec, (void **)&e->d_cub_temp, (void **)&e->d_violations, (void **)&e->d_sah};
+                     (void **)&e->d_nodes, (void **)&e->d_trirec, (void **)&e->d_cub_temp, (void **)&e->d_violations, (void **)&e->d_sah,
+                     (void **)&e->d_moving, (void **)&e->d_vlist, (void **)&e->d_nlist, (void **)&e->d_tlist, (void **)&e->d_nodelist,
+                     (void **)&e->d_list_counts, (void **)&e->d_mark, (void **)&e->d_static_box, (void **)&e->d_sah_static,
+                     (void **)&e->d_scene_abs};
     for (void **p : ptrs) {
         if (*p) cudaFree(*p);
         *p = nullptr;
     }
+    e->partial_ready = false;
+    e->sah_pending = false;
 }
 
 int bvh_alloc(rts_engine *e)
@@ -351,6 +464,18 @@ int bvh_alloc(rts_engine *e)
     if ((rc = dalloc(&e->d_trirec, T))) return rc;
     if ((rc = dalloc(&e->d_violations, (size_t)1))) return rc;
     if ((rc = dalloc(&e->d_sah, (size_t)1))) return rc;
+    // partial refit (only the targets that move)
+    if ((rc = dalloc(&e->d_moving, (size_t)e->n_targets))) return rc;
+    if ((rc = dalloc(&e->d_vlist, (size_t)e->n_verts))) return rc;
+    if ((rc = dalloc(&e->d_nlist, (size_t)e->n_normals))) return rc;
+    if ((rc = dalloc(&e->d_tlist, T))) return rc;
+    if ((rc = dalloc(&e->d_nodelist, T))) return rc;
+    if ((rc = dalloc(&e->d_list_counts, (size_t)4))) return rc;
+    if ((rc = dalloc(&e->d_mark, T))) return rc;
+    if ((rc = dalloc(&e->d_static_box, (size_t)6))) return rc;
+    if ((rc = dalloc(&e->d_sah_static, (size_t)1))) return rc;
+    if ((rc = dalloc(&e->d_scene_abs, (size_t)4))) return rc;
+    RTS_CUDA(cudaMemsetAsync(e->d_scene_abs, 0, sizeof(float) * 4, e->stream));
     size_t bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, e->d_morton, e->d_morton_sorted, e->d_order_in, e->d_order, (int)T, 0,
                                     63, e->stream);
@@ -360,22 +485,24 @@ int bvh_alloc(rts_engine *e)
     return RTS_OK;
 }
 
+static const unsigned kEmptyBox[6] = {0xff800000u, 0xff800000u, 0xff800000u, 0x007fffffu, 0x007fffffu, 0x007fffffu}; // lo = +inf, hi = -inf (ordered encoding)
+
+// Every vertex, normal and leaf box from the current poses (all targets).
 int bvh_update_world(rts_engine *e)
 {
     const unsigned bs = 256;
     if (e->n_verts)
         { k_transform<<<blocks_for(e->n_verts, bs), bs, 0, e->stream>>>(e->d_base_verts, e->d_world_verts, e->d_vert_target,
-                                                                     e->d_poses, e->n_verts, 1); e->launches++; }
+                                                                     e->d_poses, e->n_verts, 1, nullptr); e->launches++; }
     if (e->n_normals)
         { k_transform<<<blocks_for(e->n_normals, bs), bs, 0, e->stream>>>(e->d_base_normals, e->d_world_normals,
-                                                                       e->d_norm_target, e->d_poses, e->n_normals, 0); e->launches++; }
-    // scene box reset: lo = +inf, hi = -inf in ordered encoding
-    static const unsigned init_box[6] = {0xff800000u, 0xff800000u, 0xff800000u, 0x007fffffu, 0x007fffffu, 0x007fffffu};
-    RTS_CUDA(cudaMemcpyAsync(e->d_scene_box, init_box, sizeof(init_box), cudaMemcpyHostToDevice, e->stream));
+                                                                       e->d_norm_target, e->d_poses, e->n_normals, 0, nullptr); e->launches++; }
+    RTS_CUDA(cudaMemcpyAsync(e->d_scene_box, kEmptyBox, sizeof(kEmptyBox), cudaMemcpyHostToDevice, e->stream));
     if (e->n_tris)
         { k_tri_boxes<<<blocks_for(e->n_tris, bs), bs, 0, e->stream>>>(e->d_world_verts, e->d_tris, e->d_tri_target,
                                                                     e->d_t_vert_off, e->d_tri_box,
-                                                                    (unsigned *)e->d_scene_box, e->n_tris); e->launches++; }
+                                                                    (unsigned *)e->d_scene_box, e->n_tris, nullptr); e->launches++; }
+    { k_scene_abs<<<1, 32, 0, e->stream>>>((const unsigned *)e->d_scene_box, e->d_scene_abs, e->n_tris); e->launches++; }
     RTS_CUDA(cudaGetLastError());
     return RTS_OK;
 }
@@ -386,21 +513,76 @@ static int fit_and_pack(rts_engine *e)
     const int n = (int)e->n_tris;
     if (n == 0) { e->root_ref = 0; return RTS_OK; }
     { k_tri_records<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_world_verts, e->d_tris, e->d_tri_target, e->d_t_vert_off,
-                                                          e->d_order, e->d_trirec, n); e->launches++; }
+                                                          e->d_order, e->d_trirec, n, nullptr, nullptr); e->launches++; }
     if (n >= 2) {
         RTS_CUDA(cudaMemsetAsync(e->d_fit_flags, 0, sizeof(uint32_t) * (size_t)n, e->stream));
         { k_fit<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_children, e->d_parent, e->d_order, e->d_tri_box, e->d_node_box,
-                                                      e->d_fit_flags, n); e->launches++; }
+                                                      e->d_fit_flags, n, n, nullptr, nullptr, nullptr); e->launches++; }
+        RTS_CUDA(cudaMemsetAsync(e->d_fit_flags, 0, sizeof(uint32_t) * (size_t)n, e->stream));   // armed for partial refits
         RTS_CUDA(cudaMemsetAsync(e->d_sah, 0, sizeof(double), e->stream));
         { k_pack<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_children, e->d_range, e->d_order, e->d_tri_box,
-                                                           e->d_node_box, e->d_nodes, n, e->d_sah, e->leaf_max); e->launches++; }
+                                                           e->d_node_box, e->d_nodes, n, e->d_sah, e->leaf_max, n - 1, nullptr,
+                                                           nullptr); e->launches++; }
     }
     RTS_CUDA(cudaGetLastError());
     e->root_ref = n <= e->leaf_max ? ~((0 << 3) | (n - 1)) : 0;
     return RTS_OK;
 }
 
-static int read_scene_box(rts_engine *e)
+// Lists and constants of the partial refit for the current set of moving targets (e->moving).  Runs when that set
+// changes or the topology was rebuilt; synchronises (it reads four counts back).
+static int prepare_partial(rts_engine *e)
+{
+    const unsigned bs = 256;
+    const int n = (int)e->n_tris;
+    std::vector<uint32_t> mv(e->n_targets);
+    for (uint32_t k = 0; k < e->n_targets; k++) mv[k] = e->moving[k] ? 1u : 0u;
+    RTS_CUDA(cudaMemcpyAsync(e->d_moving, mv.data(), sizeof(uint32_t) * e->n_targets, cudaMemcpyHostToDevice, e->stream));
+    RTS_CUDA(cudaMemsetAsync(e->d_list_counts, 0, sizeof(uint32_t) * 4, e->stream));
+    RTS_CUDA(cudaMemsetAsync(e->d_mark, 0, sizeof(uint32_t) * (size_t)n, e->stream));
+    RTS_CUDA(cudaMemsetAsync(e->d_sah_static, 0, sizeof(double), e->stream));
+    RTS_CUDA(cudaMemcpyAsync(e->d_static_box, kEmptyBox, sizeof(kEmptyBox), cudaMemcpyHostToDevice, e->stream));
+    if (e->n_verts) { k_select_owned<<<blocks_for(e->n_verts, bs), bs, 0, e->stream>>>(e->d_vert_target, e->d_moving, e->n_verts, e->d_vlist, e->d_list_counts + 0); e->launches++; }
+    if (e->n_normals) { k_select_owned<<<blocks_for(e->n_normals, bs), bs, 0, e->stream>>>(e->d_norm_target, e->d_moving, e->n_normals, e->d_nlist, e->d_list_counts + 1); e->launches++; }
+    { k_select_owned<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_tri_target, e->d_moving, n, e->d_tlist, e->d_list_counts + 2); e->launches++; }
+    uint32_t counts[4] = {0, 0, 0, 0};
+    RTS_CUDA(cudaMemcpyAsync(counts, e->d_list_counts, sizeof(uint32_t) * 3, cudaMemcpyDeviceToHost, e->stream));
+    RTS_CUDA(cudaStreamSynchronize(e->stream));   // also makes mv[] safe to drop
+    e->n_dv = counts[0]; e->n_dn = counts[1]; e->n_dt = counts[2];
+    if (e->n_dt) { k_mark_paths<<<blocks_for(e->n_dt, bs), bs, 0, e->stream>>>(e->d_tlist, e->n_dt, e->d_leaf_of_tri, e->d_children, e->d_parent, n, e->d_mark); e->launches++; }
+    { k_select_marked<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_mark, n - 1, e->d_nodelist, e->d_list_counts + 3); e->launches++; }
+    { k_static_box<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_tri_box, e->d_tri_target, e->d_moving, n, (unsigned *)e->d_static_box); e->launches++; }
+    { k_static_sah<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_node_box, e->d_mark, n, e->d_sah_static); e->launches++; }
+    RTS_CUDA(cudaGetLastError());
+    RTS_CUDA(cudaMemcpyAsync(counts + 3, e->d_list_counts + 3, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    RTS_CUDA(cudaStreamSynchronize(e->stream));
+    e->n_dnode = counts[3];
+    e->partial_ready = true;
+    return RTS_OK;
+}
+
+// Only the moving targets: their vertices, normals, leaf boxes and triangle records, then the tree paths above them.
+static int partial_update(rts_engine *e)
+{
+    const unsigned bs = 256;
+    const int n = (int)e->n_tris;
+    if (e->n_dv) { k_transform<<<blocks_for(e->n_dv, bs), bs, 0, e->stream>>>(e->d_base_verts, e->d_world_verts, e->d_vert_target, e->d_poses, e->n_dv, 1, e->d_vlist); e->launches++; }
+    if (e->n_dn) { k_transform<<<blocks_for(e->n_dn, bs), bs, 0, e->stream>>>(e->d_base_normals, e->d_world_normals, e->d_norm_target, e->d_poses, e->n_dn, 0, e->d_nlist); e->launches++; }
+    RTS_CUDA(cudaMemcpyAsync(e->d_scene_box, e->d_static_box, sizeof(unsigned) * 6, cudaMemcpyDeviceToDevice, e->stream));
+    RTS_CUDA(cudaMemcpyAsync(e->d_sah, e->d_sah_static, sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    if (e->n_dt) {
+        { k_tri_boxes<<<blocks_for(e->n_dt, bs), bs, 0, e->stream>>>(e->d_world_verts, e->d_tris, e->d_tri_target, e->d_t_vert_off, e->d_tri_box, (unsigned *)e->d_scene_box, e->n_dt, e->d_tlist); e->launches++; }
+        { k_tri_records<<<blocks_for(e->n_dt, bs), bs, 0, e->stream>>>(e->d_world_verts, e->d_tris, e->d_tri_target, e->d_t_vert_off, e->d_order, e->d_trirec, e->n_dt, e->d_tlist, e->d_leaf_of_tri); e->launches++; }
+        { k_fit<<<blocks_for(e->n_dt, bs), bs, 0, e->stream>>>(e->d_children, e->d_parent, e->d_order, e->d_tri_box, e->d_node_box, e->d_fit_flags, n, (int)e->n_dt, e->d_tlist, e->d_leaf_of_tri, e->d_mark); e->launches++; }
+    }
+    if (e->n_dnode) { k_pack<<<blocks_for(e->n_dnode, bs), bs, 0, e->stream>>>(e->d_children, e->d_range, e->d_order, e->d_tri_box, e->d_node_box, e->d_nodes, n, e->d_sah, e->leaf_max, (int)e->n_dnode, e->d_nodelist, e->d_fit_flags); e->launches++; }
+    { k_scene_abs<<<1, 32, 0, e->stream>>>((const unsigned *)e->d_scene_box, e->d_scene_abs, e->n_tris); e->launches++; }
+    RTS_CUDA(cudaGetLastError());
+    return RTS_OK;
+}
+
+// Scene box of the current geometry into bvh_info (synchronises; diagnostics only — the kernels read d_scene_abs).
+int bvh_read_scene_box(rts_engine *e)
 {
     unsigned sb[6];
     RTS_CUDA(cudaMemcpyAsync(sb, e->d_scene_box, sizeof(sb), cudaMemcpyDeviceToHost, e->stream));
@@ -411,8 +593,6 @@ static int read_scene_box(rts_engine *e)
         const uint32_t l = (lo & 0x80000000u) ? (lo & 0x7fffffffu) : ~lo, h = (hi & 0x80000000u) ? (hi & 0x7fffffffu) : ~hi;
         memcpy(&bi.scene_lo[a], &l, 4);
         memcpy(&bi.scene_hi[a], &h, 4);
-        const float m = fmaxf(fabsf(bi.scene_lo[a]), fabsf(bi.scene_hi[a]));
-        e->scene_abs[a] = (e->n_tris && m < 3.0e38f) ? m : 0.f;
     }
     return RTS_OK;
 }
@@ -421,6 +601,8 @@ int bvh_build(rts_engine *e)
 {
     const unsigned bs = 256;
     const int n = (int)e->n_tris;
+    e->partial_ready = false;
+    e->sah_pending = false;
     cudaEventRecord(e->ev[4], e->stream);
     int rc = bvh_update_world(e);
     if (rc) return rc;
@@ -442,7 +624,7 @@ int bvh_build(rts_engine *e)
     RTS_CUDA(cudaStreamSynchronize(e->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, e->ev[4], e->ev[5]);
-    if ((rc = read_scene_box(e))) return rc;
+    if ((rc = bvh_read_scene_box(e))) return rc;
     rts_bvh_info &bi = e->bvh_info;
     bi.n_tris = e->n_tris;
     bi.n_nodes = n >= 2 ? n - 1 : 0;
@@ -454,26 +636,58 @@ int bvh_build(rts_engine *e)
     bi.sah_cost = sah;
     e->sah_at_build = sah;
     e->builds++;
+    e->refits_since_build = 0;
     return RTS_OK;
 }
 
-// Refit; when the tree's SAH cost has drifted more than RTS_REBUILD_RATIO above the cost it had when
-// its topology was built (targets moved far from where they were clustered), rebuild instead.
+// Collect the SAH cost the previous refit left in the pinned read-back block, if it has arrived.
+static void collect_sah(rts_engine *e, bool wait)
+{
+    if (!e->sah_pending) return;
+    if (wait) cudaEventSynchronize(e->sah_ev);
+    else if (cudaEventQuery(e->sah_ev) != cudaSuccess) return;
+    e->bvh_info.sah_cost = e->h_rb->sah;
+    e->sah_pending = false;
+}
+
+// Per-pulse update for the poses already in d_poses: device transform + refit, without host synchronisation.
+// Only targets that have moved since the scene was committed are touched (e->moving); the SAH cost of the
+// refitted tree comes back asynchronously and is examined at the next call: when it has drifted more than
+// RTS_REBUILD_RATIO above the cost the topology had when it was built (targets far from where they were
+// clustered), the tree is rebuilt at the new poses instead of refitted.
 int bvh_refit(rts_engine *e)
 {
-    int rc = bvh_update_world(e);
-    if (rc) return rc;
-    if ((rc = fit_and_pack(e))) return rc;
-    if ((rc = read_scene_box(e))) return rc;
+    int rc;
+    collect_sah(e, false);
+    if (e->n_tris >= 2 && e->sah_at_build > 0 && e->bvh_info.sah_cost > RTS_REBUILD_RATIO * e->sah_at_build) return bvh_build(e);
+    uint32_t n_moving = 0;
+    for (uint32_t k = 0; k < e->n_targets; k++) n_moving += e->moving[k] ? 1u : 0u;
+    if (n_moving == 0) return RTS_OK;
+    if (n_moving == e->n_targets || e->n_tris < 4096) {
+        if ((rc = bvh_update_world(e))) return rc;
+        if ((rc = fit_and_pack(e))) return rc;
+    } else {
+        if (!e->partial_ready && (rc = prepare_partial(e))) return rc;
+        if ((rc = partial_update(e))) return rc;
+    }
     if (e->n_tris >= 2) {
-        double sah = 0;
-        RTS_CUDA(cudaMemcpyAsync(&sah, e->d_sah, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-        RTS_CUDA(cudaStreamSynchronize(e->stream));
-        e->bvh_info.sah_cost = sah;
-        if (sah > RTS_REBUILD_RATIO * e->sah_at_build) return bvh_build(e);
+        collect_sah(e, true);   // one read-back slot: the previous one has long arrived
+        RTS_CUDA(cudaMemcpyAsync(&e->h_rb->sah, e->d_sah, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        cudaEventRecord(e->sah_ev, e->stream);
+        e->sah_pending = true;
+        // The first refits after a build are examined at once: committing base meshes and then placing the
+        // targets (the usual first call) can move them arbitrarily far from where the topology clustered them.
+        if (e->refits_since_build < 2) {
+            e->refits_since_build++;
+            collect_sah(e, true);
+            if (e->sah_at_build > 0 && e->bvh_info.sah_cost > RTS_REBUILD_RATIO * e->sah_at_build) return bvh_build(e);
+        }
     }
     return RTS_OK;
 }
+
+// Wait for the last refit's SAH cost (diagnostics: rts_scene_bvh_info).
+void bvh_sync_info(rts_engine *e) { collect_sah(e, true); }
 
 int bvh_check(rts_engine *e, uint64_t *violations)
 {

@@ -66,7 +66,7 @@ struct WaveParams {
     const TriRec *trirec;
     int32_t root_ref;
     uint32_t n_tris;
-    float scene_abs[3];             // max |coordinate| of the scene box per axis (slab error bound)
+    const float *scene_abs;         // [3] device: max |coordinate| of the scene box per axis (slab error bound)
     const double *world_normals;    // [Nn*3]
     const uint32_t *tris;           // [T*3] local vertex indices
     const uint32_t *t_norm_off;     // per target
@@ -120,9 +120,25 @@ struct WaveParams {
     Counters *counters;
     unsigned long long *wave_segs;  // [32] segments traced per wave index
     uint32_t wave_index;
+    uint32_t chain_below;           // later waves with fewer queued rays than this follow reflections in place
 };
 
 // ---- engine ---------------------------------------------------------------------------------
+// Pinned host block the device writes results of the pulse in flight into (asynchronous read-back).
+struct Readback {
+    Counters counters;
+    unsigned long long wave_segs[32];
+    double sah;
+};
+
+// One slot of the pinned staging ring for small per-pulse host arrays (poses, receivers, velocities, RCS).
+struct StageSlot {
+    char *host = nullptr;
+    size_t cap = 0;
+    cudaEvent_t done = nullptr;
+    bool in_flight = false;
+};
+
 struct rts_engine {
     int device = 0;
     int num_sms = 0;
@@ -161,7 +177,19 @@ struct rts_engine {
     int32_t root_ref = 0;
     int leaf_max = RTS_LEAF_MAX;       // 1..8; RTS_LEAF_MAX env var overrides (tuning)
     rts_bvh_info bvh_info = {};
-    float scene_abs[3] = {0, 0, 0};
+    float *d_scene_abs = nullptr;      // [3] max |coordinate| of the scene box per axis, refreshed by every update
+    // partial refit: only the targets that have moved since the scene was committed
+    std::vector<rts_pose> h_poses;     // poses last applied
+    std::vector<uint8_t> moving;       // per target: pose has differed from the committed one at least once
+    bool partial_ready = false;
+    uint32_t *d_moving = nullptr, *d_vlist = nullptr, *d_nlist = nullptr, *d_tlist = nullptr, *d_nodelist = nullptr;
+    uint32_t *d_list_counts = nullptr, *d_mark = nullptr;
+    float *d_static_box = nullptr;     // ordered-uint encoded, like d_scene_box
+    double *d_sah_static = nullptr;
+    uint32_t n_dv = 0, n_dn = 0, n_dt = 0, n_dnode = 0;
+    bool sah_pending = false, refit_timed = false;
+    uint32_t refits_since_build = 0;
+    cudaEvent_t sah_ev = nullptr;
     unsigned long long *d_violations = nullptr;
     double *d_sah = nullptr;
     double sah_at_build = 0;
@@ -181,12 +209,22 @@ struct rts_engine {
     unsigned long long *d_bin_mins = nullptr;
     uint64_t n_bins_dense = 0, bins_alloc = 0;
     rts_bin *d_bins_out = nullptr;
+    double *d_rx_sums = nullptr;
+    unsigned long long *d_rx_mins = nullptr;
     uint32_t *d_bins_out_count = nullptr;
     uint64_t bins_out_alloc = 0;
     rts_ray_record *d_results = nullptr;
     int32_t *d_targ_intersect = nullptr, *d_tri_path = nullptr;
     double *d_rcs_angle = nullptr;
     uint64_t rec_alloc_rays = 0, rec_alloc_D = 0, rec_alloc_W = 0;
+
+    // asynchronous plumbing
+    StageSlot stage[8];
+    int stage_next = 0;
+    Readback *h_rb = nullptr;          // pinned
+    bool pulse_pending = false;        // a pulse was enqueued and its read-back not yet folded into `stats`
+    bool pulse_single_batch = false;
+    uint64_t pulse_primary = 0, pulse_waves = 0;
 
     // last pulse
     bool have_pulse = false, bins_finalised = false;
@@ -212,6 +250,13 @@ int bvh_update_world(rts_engine *e);          // transform + tri boxes (+ tri re
 int bvh_build(rts_engine *e);                 // full LBVH build at current world geometry
 int bvh_refit(rts_engine *e);                 // bottom-up refit + repack
 int bvh_check(rts_engine *e, uint64_t *violations);
+int bvh_read_scene_box(rts_engine *e);        // fills bvh_info.scene_lo/hi (synchronises)
+void bvh_sync_info(rts_engine *e);            // waits for the last refit's SAH cost
+
+// api.cu: pinned staging for host arrays that are copied to the device asynchronously
+char *stage_acquire(rts_engine *e, size_t bytes);   // pinned pointer valid until stage_release
+void stage_release(rts_engine *e);                  // call after enqueuing the copies that read it
+int pulse_collect(rts_engine *e);                   // fold the read-back of an asynchronous pulse into e->stats (synchronises)
 
 // trace.cu
 int trace_alloc_queues(rts_engine *e, uint64_t capacity);

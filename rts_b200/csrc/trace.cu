@@ -226,8 +226,12 @@ __device__ __forceinline__ void traverse(const WaveParams &P, const d3 &o, const
             const bool h1 = fmaxf(tn1, 0.f) <= fminf(tf1, best_pad);
             if (h0 & h1) {
                 const bool swap = tn1 < tn0;
-                if (sp < RTS_STACK_DEPTH) stack[sp++] = swap ? refs.x : refs.y;
+                const int far_ref = swap ? refs.x : refs.y;
+                if (sp < RTS_STACK_DEPTH) stack[sp++] = far_ref;
                 else stack_ovf++;
+#ifdef RTS_PREFETCH_FAR
+                if (far_ref >= 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(P.nodes + far_ref));
+#endif
                 cur = swap ? refs.y : refs.x;
             } else if (h0) cur = refs.x;
             else if (h1) cur = refs.y;
@@ -290,8 +294,10 @@ constexpr unsigned long long C_HIT = 1ull, C_SHADED = 1ull << 21, C_CAPTURED = 1
 constexpr unsigned long long C_MULTI = 1ull, C_EDGE = 1ull << 21, C_REFRACTED = 1ull << 42;
 
 // normal_shader.cu:128-340
+// Returns true when `chain` is set and the reflected ray is to be followed at once by the caller (r holds it)
+// instead of being queued for the next wave.
 template <bool RECORDS>
-__device__ __forceinline__ void shade(const WaveParams &P, Ray &r, const HitRec &h, Local &L)
+__device__ __forceinline__ bool shade(const WaveParams &P, Ray &r, const HitRec &h, Local &L, bool chain)
 {
     const uint32_t dMax = P.dMax, rMax = P.rMax;
     uint32_t reflDepth = m_refl(r.meta), refrDepth = m_refr(r.meta);
@@ -306,7 +312,7 @@ __device__ __forceinline__ void shade(const WaveParams &P, Ray &r, const HitRec 
     // guard, :134 — an absorbed hit changes nothing
     if (!((end == false) && ((refrDepth < rMax) || (reflDepth < (dMax - 1))))) {
         finish_chain<RECORDS>(P, r, -1);
-        return;
+        return false;
     }
     L.a += C_SHADED;
 
@@ -459,11 +465,13 @@ __device__ __forceinline__ void shade(const WaveParams &P, Ray &r, const HitRec 
         }
         }
         r.meta = m_make(reflDepth, refrDepth, slot, end, false, col + 1);
+        if (chain) return true;
         push_ray(P, r, L.overflow); // :332
     } else {
         r.meta = m_make(reflDepth, refrDepth, slot, end, false, col + 1);
         finish_chain<RECORDS>(P, r, -1);
     }
+    return false;
 }
 
 // ray_tracer.cu:260-478.  Returns the receiver index or -1.
@@ -612,7 +620,7 @@ __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r
     }
 }
 
-template <bool PRIMARY, bool RECORDS, bool COUNT>
+template <bool PRIMARY, bool RECORDS, bool COUNT, bool CHAIN>
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_PRIMARY : RTS_WAVE_MIN_BLOCKS) k_wave(const __grid_constant__ WaveParams P)
 {
     const unsigned lane = threadIdx.x & 31u;
@@ -620,6 +628,11 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
     const unsigned n_in = PRIMARY ? (unsigned)P.n_primary : (unsigned)*P.in_count;
     unsigned *work = reinterpret_cast<unsigned *>(P.work_counter);
     Local L = {0, 0, 0, 0, 0};
+    // Thin late waves (a few thousand rays whose latency, not throughput, sets the launch time) follow their
+    // reflections in place instead of paying one more launch per bounce; refracted children are still queued.
+    // A separate instantiation (CHAIN, used from the third wave on) so the bulk waves keep their register budget.
+    const bool chain = CHAIN && !PRIMARY && n_in < P.chain_below;
+    unsigned chained = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(P.wave_segs + P.wave_index, (unsigned long long)n_in);
         atomicAdd(&P.counters->segments, (unsigned long long)n_in);   // one closest-hit query per queue entry
@@ -653,25 +666,37 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
         } else {
             load_ray_geom(P.in, idx, r);
         }
-        HitRec h;
-        unsigned nn = 0, nt = 0;
-        traverse<COUNT>(P, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz), SCENE_EPS, h, nn, nt, L.overflow); // SCENE_EPS == SCENE_EPS_R (ray_tracer.h:9-10)
-        if (COUNT) { L.nodes += nn; L.tris += nt; }
-        if (PRIMARY) {
-            r.len = 0; r.pw = 0; r.dop = 0; r.fx = 0; r.fy = 0; r.fz = 0; r.n0 = 1; r.n1 = 1;
-            r.key = 0; r.ray = (uint32_t)rayIndex;
-        } else {
-            load_ray_rest(P.in, idx, r);
-        }
-        if (h.pos >= 0) {
-            L.a += C_HIT;
-            shade<RECORDS>(P, r, h, L);
-        } else {
-            const int received = miss<RECORDS>(P, r, L);
-            if (received >= 0) {
-                L.a += C_CAPTURED;
-                if (P.flags & RTS_OUT_BINS) accumulate_bin(P, r, received);
+        for (bool first = true;; first = false) {
+            HitRec h;
+            unsigned nn = 0, nt = 0;
+            traverse<COUNT>(P, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz), SCENE_EPS, h, nn, nt, L.overflow); // SCENE_EPS == SCENE_EPS_R (ray_tracer.h:9-10)
+            if (COUNT) { L.nodes += nn; L.tris += nt; }
+            if (PRIMARY) {
+                r.len = 0; r.pw = 0; r.dop = 0; r.fx = 0; r.fy = 0; r.fz = 0; r.n0 = 1; r.n1 = 1;
+                r.key = 0; r.ray = (uint32_t)rayIndex;
+            } else if (first) {
+                load_ray_rest(P.in, idx, r);
             }
+            bool follow = false;
+            if (h.pos >= 0) {
+                L.a += C_HIT;
+                follow = shade<RECORDS>(P, r, h, L, chain);
+            } else {
+                const int received = miss<RECORDS>(P, r, L);
+                if (received >= 0) {
+                    L.a += C_CAPTURED;
+                    if (P.flags & RTS_OUT_BINS) accumulate_bin(P, r, received);
+                }
+            }
+            if (PRIMARY || !CHAIN || !follow) break;
+            chained++;
+        }
+    }
+    if (!PRIMARY && CHAIN) {   // segments traced in place belong to this launch
+        const unsigned x = __reduce_add_sync(0xffffffffu, chained);
+        if (lane == 0 && x) {
+            atomicAdd(P.wave_segs + P.wave_index, (unsigned long long)x);
+            atomicAdd(&P.counters->segments, (unsigned long long)x);
         }
     }
     // counters: unpack, warp reduce (redux.sync), one atomic per warp per non-zero counter
@@ -703,22 +728,22 @@ int trace_wave_grid(rts_engine *e)
 {
     if (e->wave_grid) return e->wave_grid;
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wave<true, false, false>, RTS_WAVE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wave<true, false, false, false>, RTS_WAVE_BLOCK, 0);
     e->wave_grid_primary = e->num_sms * (occ > 0 ? occ : 1);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wave<false, false, false>, RTS_WAVE_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_wave<false, false, false, false>, RTS_WAVE_BLOCK, 0);
     e->wave_grid = e->num_sms * (occ > 0 ? occ : 1);
     return e->wave_grid;
 }
 
-template <bool PRIMARY>
+template <bool PRIMARY, bool CHAIN>
 static void launch_variant(int grid, cudaStream_t st, const WaveParams &p, bool records, bool count)
 {
     if (records) {
-        if (count) k_wave<PRIMARY, true, true><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
-        else k_wave<PRIMARY, true, false><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        if (count) k_wave<PRIMARY, true, true, CHAIN><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        else k_wave<PRIMARY, true, false, CHAIN><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
     } else {
-        if (count) k_wave<PRIMARY, false, true><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
-        else k_wave<PRIMARY, false, false><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        if (count) k_wave<PRIMARY, false, true, CHAIN><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        else k_wave<PRIMARY, false, false, CHAIN><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
     }
 }
 
@@ -727,8 +752,9 @@ int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool rec
     trace_wave_grid(e);
     const int grid = primary ? e->wave_grid_primary : e->wave_grid;   // persistent: resident CTAs per SM x SMs
     const bool count = (p.flags & RTS_COUNT_NODES) != 0;
-    if (primary) launch_variant<true>(grid, e->stream, p, records, count);
-    else launch_variant<false>(grid, e->stream, p, records, count);
+    if (primary) launch_variant<true, false>(grid, e->stream, p, records, count);
+    else if (p.wave_index >= 2 && p.chain_below) launch_variant<false, true>(grid, e->stream, p, records, count);
+    else launch_variant<false, false>(grid, e->stream, p, records, count);
     RTS_CUDA(cudaGetLastError());
     e->launches++;
     return RTS_OK;

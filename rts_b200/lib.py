@@ -19,6 +19,7 @@ RTS_OUT_RECORDS = 2
 RTS_COUNT_NODES = 4
 RTS_NO_FINALISE = 8
 RTS_NO_RCS_ANGLES = 16
+RTS_ASYNC = 32
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RTS_B200_LIB", os.path.join(_HERE, "librts_b200.so"))   # override: tuning builds only
@@ -49,7 +50,7 @@ EXPORTS = [
     "rts_rx_sphere_from_desc", "rts_result_sizes", "rts_rect_mesh", "rts_sphere_mesh", "rts_file_mesh",
     "rts_rotation_matrix", "rts_scene_set_targets", "rts_scene_set_poses", "rts_scene_rebuild", "rts_scene_bvh_info",
     "rts_scene_get_world_vertices", "rts_scene_get_tri_bounds", "rts_scene_check_bvh", "rts_trace_pulse",
-    "rts_get_stats", "rts_get_wave_profile", "rts_kernel_launches", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_bins_device", "rts_finalise_bins", "rts_aggregate",
+    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_kernel_launches", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_bins_device", "rts_finalise_bins", "rts_aggregate",
 ]
 
 _lib = None
@@ -89,6 +90,7 @@ def load() -> C.CDLL:
     lib.rts_scene_get_tri_bounds.argtypes = [vp, P(C.c_float)]
     lib.rts_scene_check_bvh.argtypes = [vp, P(u64)]
     lib.rts_trace_pulse.argtypes = [vp, P(RtsPulse), u32]
+    lib.rts_sync.argtypes = [vp]
     lib.rts_get_stats.argtypes = [vp, P(RtsStats)]
     lib.rts_get_wave_profile.argtypes = [vp, u32, P(C.c_float), P(u64), P(u32)]
     lib.rts_kernel_launches.argtypes = [vp, P(u64)]
@@ -228,10 +230,17 @@ class Engine:
         return int(v.value)
 
     # pulse -------------------------------------------------------------------------------
-    def trace(self, spec: PulseSpec, flags: int = RTS_OUT_BINS) -> dict:
+    def trace(self, spec: PulseSpec, flags: int = RTS_OUT_BINS) -> Optional[dict]:
+        """One pulse.  With RTS_ASYNC the call returns as soon as the pulse is enqueued (None); stats() / bins() /
+        sync() wait for it."""
         self._pulse = CPulse(spec, self._scene.n if self._scene else 0)
         _check(self._lib.rts_trace_pulse(self._h, C.byref(self._pulse.c), int(flags)))
+        if flags & RTS_ASYNC:
+            return None
         return self.stats()
+
+    def sync(self):
+        _check(self._lib.rts_sync(self._h))
 
     def stats(self) -> dict:
         s = RtsStats()
@@ -251,9 +260,12 @@ class Engine:
 
     def bins(self) -> np.ndarray:
         n = C.c_uint32()
-        _check(self._lib.rts_get_bins(self._h, None, 0, C.byref(n)))
-        out = np.zeros(max(1, n.value), dtype=BIN_DTYPE)
-        _check(self._lib.rts_get_bins(self._h, out.ctypes.data_as(C.POINTER(RtsBin)), n.value, C.byref(n)))
+        cap = 1024                                   # one call in the common case; *n reports the total
+        out = np.zeros(cap, dtype=BIN_DTYPE)
+        _check(self._lib.rts_get_bins(self._h, out.ctypes.data_as(C.POINTER(RtsBin)), cap, C.byref(n)))
+        if n.value > cap:
+            out = np.zeros(n.value, dtype=BIN_DTYPE)
+            _check(self._lib.rts_get_bins(self._h, out.ctypes.data_as(C.POINTER(RtsBin)), n.value, C.byref(n)))
         return out[: n.value]
 
     def responses(self) -> np.ndarray:

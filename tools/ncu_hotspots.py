@@ -3,8 +3,8 @@ aggregate executed instructions / stall samples per source line and per function
     python tools/ncu_hotspots.py [kernel-substring] [kernel-instance-index]"""
 import csv, os, re, subprocess, sys, collections, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-pat = sys.argv[1] if len(sys.argv) > 1 else "k_wave<(bool)1, (bool)0, (bool)0>"
-mangled = sys.argv[2] if len(sys.argv) > 2 else "k_waveILb1ELb0ELb0"
+pat = sys.argv[1] if len(sys.argv) > 1 else "k_wave<(bool)1, (bool)0, (bool)0, (bool)0>"
+mangled = sys.argv[2] if len(sys.argv) > 2 else "k_waveILb1ELb0ELb0ELb0"
 rep = os.path.join(ROOT, "gpurun_out", "prof.ncu-rep")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", os.path.join(ROOT, "rts_b200", "csrc", "trace.o")], cwd=tmp, capture_output=True)
