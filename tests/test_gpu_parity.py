@@ -228,3 +228,72 @@ def test_C4_terrain_1M_triangles(engine):
     again = engine.bins()
     assert np.array_equal(again["npath"], bins_full["npath"]) and np.array_equal(again["min_slot"], bins_full["min_slot"])
     assert np.allclose(again["sum_sqrt_power"], bins_full["sum_sqrt_power"], rtol=1e-12)
+
+
+def test_async_pulses_equal_synchronous(engine):
+    """RTS_ASYNC: pulses and pose updates are only enqueued; getters / rts_sync wait.  Same bins and stats as the
+    synchronous calls, pulse after pulse (pinned staging ring reuse included: more pulses than ring slots)."""
+    ms = scenes.terrain_scene(n=96, cells_x=80, cells_y=40, movers=6, n_rx=2)
+    engine.set_targets(ms.base)
+    want = []
+    for pulse in range(12):
+        engine.set_poses(*ms.poses(pulse))
+        st = engine.trace(ms.spec_for(pulse), L.RTS_OUT_BINS)
+        want.append((st, engine.bins().copy()))
+    engine.set_targets(ms.base)
+    for pulse in range(12):
+        engine.set_poses(*ms.poses(pulse))
+        assert engine.trace(ms.spec_for(pulse), L.RTS_OUT_BINS | L.RTS_ASYNC) is None
+        if pulse % 3 == 2:          # read only some of them back; the others are overtaken by the next pulse
+            got = engine.bins()
+            st = engine.stats()
+            for k in ("primary_rays", "segments", "hits", "shaded_hits", "captured"):
+                assert st[k] == want[pulse][0][k], (pulse, k)
+            parity.assert_bins_close(parity.compare_bins(got, want[pulse][1]), rtol=1e-12)
+    engine.sync()
+
+
+def test_targets_that_start_moving_later_and_drift_rebuild(engine):
+    """Partial refit bookkeeping: a target joins the moving set at a later pulse, a pose repeated verbatim is a
+    no-op, and a large displacement triggers the SAH-drift rebuild; hits always equal a fresh rebuild's."""
+    ms = scenes.terrain_scene(n=128, cells_x=80, cells_y=40, movers=6, n_rx=1)
+    engine.set_targets(ms.world_targets(0))             # committed at the pulse-0 poses: nothing moves at first
+    K = len(ms.base)
+    ident = ([None] * K, [(0.0, 0.0, 0.0)] * K)
+    spec = ms.spec_for(0)
+
+    from rts_b200.abi import Target
+    committed = ms.world_targets(0)
+
+    def hits_now(trans):
+        """records after refit == records after a fresh rebuild == oracle on the translated meshes"""
+        engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_NO_RCS_ANGLES)
+        a = engine.records(rcs=False)
+        engine.rebuild()
+        engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_NO_RCS_ANGLES)
+        b = engine.records(rcs=False)
+        assert np.array_equal(a[3], b[3]) and a[0].tobytes() == b[0].tobytes()
+        assert engine.check_bvh() == 0
+        world = [Target(t.verts + np.asarray(d), t.tris, t.normals, t.refl_coeff, t.refr_index) for t, d in zip(committed, trans)]
+        orc = O.trace(world, spec, use_bvh=True)
+        assert np.array_equal(a[3], orc["tri_path"]) and np.array_equal(a[1], orc["targ_intersect"])
+        return a
+
+    engine.set_poses(*ident)                            # no-op
+    hits_now(ident[1])
+    trans = [list(t) for t in ident[1]]
+    trans[2] = (15.0, -4.0, 6.0)                        # one mover starts moving
+    engine.set_poses(ident[0], trans)
+    hits_now(trans)
+    trans[4] = (-9.0, 12.0, 3.0)                        # a second one joins later
+    engine.set_poses(ident[0], trans)
+    hits_now(trans)
+    engine.set_poses(ident[0], trans)                   # verbatim repeat
+    builds = engine.bvh_info().builds
+    trans[2] = (2500.0, 900.0, 400.0)                   # far away: the refitted tree degrades, a rebuild follows
+    engine.set_poses(ident[0], trans)
+    engine.set_poses(ident[0], trans)
+    trans[2] = (2501.0, 900.0, 400.0)
+    engine.set_poses(ident[0], trans)
+    hits_now(trans)
+    assert engine.bvh_info().builds > builds
