@@ -52,20 +52,24 @@ __device__ __forceinline__ void load_ray_geom(const RayQueue &q, unsigned long l
     r.dx = q.f[F_DX][i]; r.dy = q.f[F_DY][i]; r.dz = q.f[F_DZ][i];
     r.meta = q.meta[i];
 }
-__device__ __forceinline__ void load_ray_rest(const RayQueue &q, unsigned long long i, Ray &r)
+// The first hit point is only ever reported through the records, the refractive indices only matter with a
+// refraction budget: those five columns are skipped otherwise (88 instead of 128 bytes per queued ray).
+__device__ __forceinline__ void load_ray_rest(const RayQueue &q, unsigned long long i, Ray &r, bool records, bool refr)
 {
     r.len = q.f[F_LEN][i]; r.pw = q.f[F_PW][i]; r.dop = q.f[F_DOP][i];
-    r.fx = q.f[F_FX][i]; r.fy = q.f[F_FY][i]; r.fz = q.f[F_FZ][i];
-    r.n0 = q.f[F_N0][i]; r.n1 = q.f[F_N1][i];
+    if (records) { r.fx = q.f[F_FX][i]; r.fy = q.f[F_FY][i]; r.fz = q.f[F_FZ][i]; }
+    else { r.fx = 0; r.fy = 0; r.fz = 0; }
+    if (refr) { r.n0 = q.f[F_N0][i]; r.n1 = q.f[F_N1][i]; }
+    else { r.n0 = 1; r.n1 = 1; }
     r.key = q.key[i]; r.ray = q.ray[i];
 }
-__device__ __forceinline__ void store_ray(const RayQueue &q, unsigned long long i, const Ray &r)
+__device__ __forceinline__ void store_ray(const RayQueue &q, unsigned long long i, const Ray &r, bool records, bool refr)
 {
     q.f[F_OX][i] = r.ox; q.f[F_OY][i] = r.oy; q.f[F_OZ][i] = r.oz;
     q.f[F_DX][i] = r.dx; q.f[F_DY][i] = r.dy; q.f[F_DZ][i] = r.dz;
     q.f[F_LEN][i] = r.len; q.f[F_PW][i] = r.pw; q.f[F_DOP][i] = r.dop;
-    q.f[F_FX][i] = r.fx; q.f[F_FY][i] = r.fy; q.f[F_FZ][i] = r.fz;
-    q.f[F_N0][i] = r.n0; q.f[F_N1][i] = r.n1;
+    if (records) { q.f[F_FX][i] = r.fx; q.f[F_FY][i] = r.fy; q.f[F_FZ][i] = r.fz; }
+    if (refr) { q.f[F_N0][i] = r.n0; q.f[F_N1][i] = r.n1; }
     q.key[i] = r.key; q.ray[i] = r.ray; q.meta[i] = r.meta;
 }
 
@@ -77,7 +81,7 @@ __device__ __forceinline__ void push_ray(const WaveParams &P, const Ray &r, unsi
     if (g.thread_rank() == 0) base = atomicAdd(P.out_count, (unsigned long long)g.size());
     base = g.shfl(base, 0);
     const unsigned long long i = base + g.thread_rank();
-    if (i < P.out_capacity) store_ray(P.out, i, r);
+    if (i < P.out_capacity) store_ray(P.out, i, r, (P.flags & RTS_OUT_RECORDS) != 0, P.rMax != 0);
     else overflow++;
 }
 
@@ -675,7 +679,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
                 r.len = 0; r.pw = 0; r.dop = 0; r.fx = 0; r.fy = 0; r.fz = 0; r.n0 = 1; r.n1 = 1;
                 r.key = 0; r.ray = (uint32_t)rayIndex;
             } else if (first) {
-                load_ray_rest(P.in, idx, r);
+                load_ray_rest(P.in, idx, r, RECORDS, P.rMax != 0);
             }
             bool follow = false;
             if (h.pos >= 0) {
