@@ -137,6 +137,14 @@ int rts_get_responses(rts_engine *e, rts_response *out, uint32_t cap, uint32_t *
 int rts_get_records(rts_engine *e, rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle,
                     int32_t *tri_path);
 
+/* RTS_OUT_RECORDS: only the received rays (received >= 0), compacted on the device in result-slot order — the
+ * h_rx_results / h_rx_intersects arrays the reference's host loop collects (ray_tracer.cpp:1190-1221) before it applies
+ * the Target::GetRCS / GetGain callbacks (:1226-1247), plus each ray's result-slot index and its rcs_angle row.
+ * Call with cap = 0 for the count; then results[cap], targ_intersect[cap*D], rcs_angle[cap*D*2], slots[cap] (any may be
+ * NULL).  Feed the scaled records to rts_aggregate / rs::kernel_wrapper. */
+int rts_get_received(rts_engine *e, uint64_t cap, uint64_t *n, uint64_t *slots, rts_ray_record *results,
+                     int32_t *targ_intersect, double *rcs_angle);
+
 /* ---- multi-GPU plumbing: raw bin accumulators for an external reduction (NCCL all-reduce) ----
  * sums_device: double[n_bins_dense*5] {npath, Σ√P, Σdelay, Σphase, ΣDoppler}  (reduce with SUM)
  * mins_device: uint64[n_bins_dense]   smallest result-slot index; empty bins hold 0x7f7f7f7f7f7f7f7f, so a MIN

@@ -10,6 +10,8 @@
 #include <cooperative_groups/reduce.h>
 #include <algorithm>
 #include <math_constants.h>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -106,6 +108,31 @@ __global__ void k_emit_bins(const double *__restrict__ sums, const unsigned long
     b.doppler = b.sum_doppler / b.npath;
     const uint32_t at = atomicAdd(out_count, 1u);
     if (at < cap) out[at] = b;
+}
+
+// ---- received rays, compacted (first half of the host loop ray_tracer.cpp:1190-1258) ----
+struct IsReceived {
+    const rts_ray_record *res;
+    __device__ bool operator()(unsigned i) const { return res[i].received >= 0; }
+};
+// one thread per 16-byte piece of a record (9 per ray); rows and angles by the first piece's thread
+__global__ void k_gather_received(const unsigned *__restrict__ idx, unsigned n, uint32_t D, const rts_ray_record *__restrict__ res,
+                                  const int32_t *__restrict__ ti, const double *__restrict__ rcs, rts_ray_record *__restrict__ o_res,
+                                  int32_t *__restrict__ o_ti, double *__restrict__ o_rcs, unsigned long long *__restrict__ o_slot)
+{
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned k = (unsigned)(t / 9), piece = (unsigned)(t % 9);
+    if (k >= n) return;
+    const unsigned src = idx[k];
+    reinterpret_cast<double2 *>(o_res + k)[piece] = reinterpret_cast<const double2 *>(res + src)[piece];
+    if (piece == 0) {
+        o_slot[k] = src;
+        for (uint32_t c = 0; c < D; c++) {
+            o_ti[(size_t)k * D + c] = ti[(size_t)src * D + c];
+            o_rcs[((size_t)k * D + c) * 2] = rcs[((size_t)src * D + c) * 2];
+            o_rcs[((size_t)k * D + c) * 2 + 1] = rcs[((size_t)src * D + c) * 2 + 1];
+        }
+    }
 }
 
 // ---- drop-in aggregator (rs::kernel_wrapper) ----
@@ -348,5 +375,64 @@ done:
 #undef AGG_CUDA
     cudaFree(d_res); cudaFree(d_rows); cudaFree(d_pm); cudaFree(d_table); cudaFree(d_slot); cudaFree(d_gmin);
     cudaFree(d_rmin); cudaFree(d_gs); cudaFree(d_rs); cudaFree(d_acc);
+    return rc;
+}
+
+// Received rays of the last RTS_OUT_RECORDS pulse in result-slot order (ray_tracer.cpp:1190-1221 without the
+// callbacks): stream compaction of the slot indices, then a gather of record, path row and RCS-angle row.
+int agg_get_received(rts_engine *e, uint64_t cap, uint64_t *n, uint64_t *slots, rts_ray_record *results, int32_t *targ_intersect,
+                     double *rcs_angle)
+{
+    const uint64_t total = e->last_sizes.ray_total;
+    const uint32_t D = e->last_sizes.depth_total;
+    if (total >= (1ull << 31)) return rts_fail(RTS_ERR_CAPACITY, "%llu result slots exceed 2^31", (unsigned long long)total);
+    cudaStream_t st = e->stream;
+    unsigned *d_idx = nullptr, *d_num = nullptr;
+    void *d_tmp = nullptr;
+    rts_ray_record *o_res = nullptr;
+    int32_t *o_ti = nullptr;
+    double *o_rcs = nullptr;
+    unsigned long long *o_slot = nullptr;
+    int rc = RTS_OK;
+    unsigned count = 0;
+    size_t tmp_bytes = 0;
+    const IsReceived pred{e->d_results};
+    thrust::counting_iterator<unsigned> first(0u);
+#define REC_CUDA(call)                                                                                          \
+    do {                                                                                                        \
+        cudaError_t _e = (call);                                                                                \
+        if (_e != cudaSuccess) {                                                                                \
+            rc = rts_fail(RTS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            goto done;                                                                                          \
+        }                                                                                                       \
+    } while (0)
+    REC_CUDA(cudaMalloc(&d_idx, sizeof(unsigned) * std::max<uint64_t>(1, total)));
+    REC_CUDA(cudaMalloc(&d_num, sizeof(unsigned)));
+    REC_CUDA(cub::DeviceSelect::If(nullptr, tmp_bytes, first, d_idx, d_num, (int)total, pred, st));
+    REC_CUDA(cudaMalloc(&d_tmp, std::max<size_t>(16, tmp_bytes)));
+    REC_CUDA(cub::DeviceSelect::If(d_tmp, tmp_bytes, first, d_idx, d_num, (int)total, pred, st));
+    e->launches += 2;
+    REC_CUDA(cudaMemcpyAsync(&count, d_num, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    REC_CUDA(cudaStreamSynchronize(st));
+    if (n) *n = count;
+    if (count && cap) {
+        const unsigned take = (unsigned)std::min<uint64_t>(count, cap);
+        const size_t Dn = std::max<uint32_t>(1, D);
+        REC_CUDA(cudaMalloc(&o_res, sizeof(rts_ray_record) * take));
+        REC_CUDA(cudaMalloc(&o_ti, sizeof(int32_t) * take * Dn));
+        REC_CUDA(cudaMalloc(&o_rcs, sizeof(double) * 2 * take * Dn));
+        REC_CUDA(cudaMalloc(&o_slot, sizeof(unsigned long long) * take));
+        { k_gather_received<<<blocks_for((uint64_t)take * 9, 256), 256, 0, st>>>(d_idx, take, D, e->d_results, e->d_targ_intersect,
+                                                                             e->d_rcs_angle, o_res, o_ti, o_rcs, o_slot); e->launches++; }
+        REC_CUDA(cudaGetLastError());
+        if (results) REC_CUDA(cudaMemcpyAsync(results, o_res, sizeof(rts_ray_record) * take, cudaMemcpyDeviceToHost, st));
+        if (targ_intersect && D) REC_CUDA(cudaMemcpyAsync(targ_intersect, o_ti, sizeof(int32_t) * take * D, cudaMemcpyDeviceToHost, st));
+        if (rcs_angle && D) REC_CUDA(cudaMemcpyAsync(rcs_angle, o_rcs, sizeof(double) * 2 * take * D, cudaMemcpyDeviceToHost, st));
+        if (slots) REC_CUDA(cudaMemcpyAsync(slots, o_slot, sizeof(unsigned long long) * take, cudaMemcpyDeviceToHost, st));
+        REC_CUDA(cudaStreamSynchronize(st));
+    }
+done:
+#undef REC_CUDA
+    cudaFree(d_idx); cudaFree(d_num); cudaFree(d_tmp); cudaFree(o_res); cudaFree(o_ti); cudaFree(o_rcs); cudaFree(o_slot);
     return rc;
 }

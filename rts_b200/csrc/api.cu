@@ -714,6 +714,17 @@ extern "C" int rts_get_records(rts_engine *e, rts_ray_record *results, int32_t *
     return RTS_OK;
 }
 
+extern "C" int rts_get_received(rts_engine *e, uint64_t cap, uint64_t *n, uint64_t *slots, rts_ray_record *results,
+                                int32_t *targ_intersect, double *rcs_angle)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    if (!e->have_pulse || !(e->last_flags & RTS_OUT_RECORDS)) return rts_fail(RTS_ERR_STATE, "last pulse did not produce records");
+    RTS_CUDA(cudaSetDevice(e->device));
+    int rc = pulse_collect(e);
+    if (rc) return rc;
+    return agg_get_received(e, cap, n, slots, results, targ_intersect, rcs_angle);
+}
+
 extern "C" int rts_aggregate(rts_engine *e, rts_ray_record *rx_results, const int32_t *rx_intersects, uint32_t received,
                              uint32_t depth_total, double cspeed, double carrier, double *npath, double *power,
                              double *doppler, double *delay, double *phase, int32_t *path_match)

@@ -267,6 +267,8 @@ int trace_wave_grid(rts_engine *e);
 int agg_finalise_bins(rts_engine *e);
 int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n);
 int agg_fill_records(rts_engine *e, uint64_t ray_total, uint32_t D, uint32_t W);
+int agg_get_received(rts_engine *e, uint64_t cap, uint64_t *n, uint64_t *slots, rts_ray_record *results, int32_t *targ_intersect,
+                     double *rcs_angle);
 int agg_kernel_wrapper(rts_engine *e, rts_ray_record *rx_results, const int32_t *rx_intersects, uint32_t received,
                        uint32_t depth_total, double cspeed, double carrier, double *npath, double *power,
                        double *doppler, double *delay, double *phase, int32_t *path_match);

@@ -50,7 +50,7 @@ EXPORTS = [
     "rts_rx_sphere_from_desc", "rts_result_sizes", "rts_rect_mesh", "rts_sphere_mesh", "rts_file_mesh",
     "rts_rotation_matrix", "rts_scene_set_targets", "rts_scene_set_poses", "rts_scene_rebuild", "rts_scene_bvh_info",
     "rts_scene_get_world_vertices", "rts_scene_get_tri_bounds", "rts_scene_check_bvh", "rts_trace_pulse",
-    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_kernel_launches", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_bins_device", "rts_finalise_bins", "rts_aggregate",
+    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_kernel_launches", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_get_received", "rts_bins_device", "rts_finalise_bins", "rts_aggregate",
 ]
 
 _lib = None
@@ -97,6 +97,7 @@ def load() -> C.CDLL:
     lib.rts_get_bins.argtypes = [vp, P(RtsBin), u32, P(u32)]
     lib.rts_get_responses.argtypes = [vp, P(RtsResponse), u32, P(u32)]
     lib.rts_get_records.argtypes = [vp, vp, P(i32), P(dbl), P(i32)]
+    lib.rts_get_received.argtypes = [vp, u64, P(u64), P(u64), vp, P(i32), P(dbl)]
     lib.rts_bins_device.argtypes = [vp, P(vp), P(u64), P(vp), P(u64)]
     lib.rts_finalise_bins.argtypes = [vp]
     lib.rts_aggregate.argtypes = [vp, vp, P(i32), u32, u32, dbl, dbl, P(dbl), P(dbl), P(dbl), P(dbl), P(dbl), P(i32)]
@@ -288,6 +289,24 @@ class Engine:
             rc.ctypes.data_as(C.POINTER(C.c_double)) if rcs else None,
             tp.ctypes.data_as(C.POINTER(C.c_int32)) if tri_path else None))
         return res, ti[:, :D], (rc[:, :D] if rcs else None), tp
+
+    def received(self):
+        """Received rays only, in slot order: (results, targ_intersect [R,D], rcs_angle [R,D,2], slots [R])
+        — ray_tracer.cpp:1190-1221 before the RCS / gain callbacks."""
+        D = self._pulse.spec.depth_total
+        n = C.c_uint64()
+        _check(self._lib.rts_get_received(self._h, 0, C.byref(n), None, None, None, None))
+        R = int(n.value)
+        res = np.zeros(max(1, R), dtype=RAY_RECORD)
+        ti = np.zeros((max(1, R), max(D, 1)), dtype=np.int32)
+        rc = np.zeros((max(1, R), max(D, 1), 2))
+        sl = np.zeros(max(1, R), dtype=np.uint64)
+        if R:
+            _check(self._lib.rts_get_received(self._h, R, C.byref(n), sl.ctypes.data_as(C.POINTER(C.c_uint64)), res.ctypes.data_as(C.c_void_p),
+                                              ti.ctypes.data_as(C.POINTER(C.c_int32)), rc.ctypes.data_as(C.POINTER(C.c_double))))
+        if D == 0:
+            return res[:R], ti[:R, :0], rc[:R, :0], sl[:R]
+        return res[:R], ti[:R], rc[:R], sl[:R]
 
     def bins_device(self):
         """(sums_ptr, n_doubles, mins_ptr, n_u64) of the raw bin accumulators, for an external all-reduce."""

@@ -139,3 +139,32 @@ def test_fused_rcs_gains_and_responses(engine, scene):
     assert np.array_equal(got["rx"], want["rx"]) and np.array_equal(got["slot"], want["slot"])
     for f in ("power", "delay", "doppler", "phase"):
         assert np.allclose(got[f], want[f], rtol=1e-5, atol=1e-300), f
+
+
+@pytest.mark.parametrize("scene", ["slab", "direct+", "empty"])
+def test_received_rays_compacted_on_the_device(engine, scene):
+    """rts_get_received == the received slots of the full reference-shaped arrays, in slot order
+    (ray_tracer.cpp:1190-1221), and feeding them through the callbacks + rts_aggregate reproduces the fused bins."""
+    from rts_b200 import lib as L
+    if scene == "slab":
+        targets, spec = scenes.slab(n=64)
+    elif scene == "direct+":
+        targets, spec = scenes.direct_and_plate(n=96, side=1)
+    else:
+        targets, spec = scenes.flat_plate(n=32)
+        spec.rx = [L.rx_sphere_from_desc((0.0, 500.0, 0.0), 0.0, 0.0, 1.0, 0.1, 0.1)]   # nothing is received
+    engine.set_targets(targets)
+    engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_OUT_BINS)
+    res, ti, rcs, _ = engine.records(tri_path=False)
+    got_res, got_ti, got_rcs, got_slots = engine.received()
+    keep = np.nonzero(res["received"] >= 0)[0]
+    assert np.array_equal(got_slots, keep.astype(np.uint64))
+    for f in res.dtype.names:                                        # field by field: numpy does not copy padding bytes
+        assert got_res[f].tobytes() == res[keep][f].tobytes(), f
+    assert np.array_equal(got_ti, ti[keep]) and got_rcs.tobytes() == rcs[keep].tobytes()
+    if len(keep):
+        rx_res, rx_rows, rx_slots = O.postprocess(res, ti, spec)      # RCS = gains = 1 callbacks + Doppler conversion
+        a = engine.aggregate(rx_res, rx_rows, spec.cspeed, spec.carrier, ray_total=spec.ray_total)
+        want = O.responses(a, rx_slots)
+        got = engine.responses()
+        assert np.array_equal(got["slot"], want["slot"]) and np.allclose(got["power"], want["power"], rtol=1e-10)
