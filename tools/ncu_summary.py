@@ -55,7 +55,7 @@ for d in summ[:2]:
 def gb(s):
     v, u = s.split()
     return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
-prim = [d for d in summ if "k_wave<1, 0>" in d["Kernel Name"]]
+prim = [d for d in summ if "k_wave<1, 0" in d["Kernel Name"]]
 if prim:
     t = gb(prim[0]["dram__bytes_read.sum"]) + gb(prim[0]["dram__bytes_write.sum"])
     json.dump({"k_wave_primary_dram_bytes_per_launch": t, "source": f"profiles/{tag}_k_wave_ncu_full.json (ncu --set full, one launch)"},
