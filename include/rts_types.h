@@ -147,7 +147,7 @@ typedef struct rts_stats {
     uint64_t tris_tested;       /* triangle tests executed (same flag) */
     uint64_t waves;             /* wavefront launches */
     uint32_t n_bins;            /* non-empty bins */
-    uint32_t _pad;
+    uint32_t primary_projected; /* 1 when the primary wave of the last batch ran by projection (RTS_RASTER=1) rather than BVH traversal */
     float    ms_update;         /* scene update + refit */
     float    ms_trace;          /* all bounce waves */
     float    ms_finalise;       /* bin finalisation */

@@ -121,7 +121,7 @@ extern "C" void rts_destroy(rts_engine *e)
     cudaStreamSynchronize(e->stream);
     free_scene(e);
     for (int k = 0; k < 2; k++) if (e->q_slab[k]) cudaFree(e->q_slab[k]);
-    void *ptrs[] = {e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count, e->d_rx_sums, e->d_rx_mins,
+    void *ptrs[] = {e->d_dirs, e->d_hits, e->d_raster_ctl, e->d_raster_items, e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count, e->d_rx_sums, e->d_rx_mins,
                     e->d_results, e->d_targ_intersect, e->d_tri_path, e->d_rcs_angle};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -369,6 +369,13 @@ static void fill_launch_constants(WaveParams &P, const rts_pulse *p)
                             oy * ox * (1 - c) - oz * s, c + oy * oy * (1 - c), oy * oz * (1 - c) + ox * s,
                             oz * ox * (1 - c) + oy * s, oz * oy * (1 - c) - ox * s, c + oz * oz * (1 - c)};
     memcpy(P.Rot1, Rot1, sizeof(Rot1));
+    // A = Rot1 * Rot takes the beam-frame direction to the world; its transpose takes world offsets back (raster.cuh)
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+            double a = 0;
+            for (int k = 0; k < 3; k++) a += Rot1[3 * i + k] * Rot[3 * k + j];
+            P.AT[3 * j + i] = a;
+        }
     sph_to_cart(az, el, P.boresight);
     P.single_ray = (p->nx == 1 && p->ny == 1 && p->nz == 1) ? 1 : 0;
 }
@@ -513,6 +520,15 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
         int rc = trace_alloc_queues(e, cap);
         if (rc) return rc;
     }
+    // primary visibility by projection (opt-in, RTS_RASTER=1: measured equal to the BVH primary wave on the 1M-triangle
+    // workload): launches whose rays form one image (nx == 1) with a forward image plane
+    const bool use_raster = p->nx == 1 && !P.single_ray && e->n_tris > 0 && !(flags & RTS_COUNT_NODES) && getenv("RTS_RASTER") &&
+                            P.beamStart[0] > 1e-6 && (p->ny == 1 || P.slope[1] != 0.0) && (p->nz == 1 || P.slope[2] != 0.0) &&
+                            n_primary_total > 0;
+    if (use_raster) {
+        int rc = trace_raster_alloc(e, batch);
+        if (rc) return rc;
+    }
     P.out_capacity = e->q_capacity;
     P.counters = e->d_counters;
     RTS_CUDA(cudaMemsetAsync(e->d_counters, 0, sizeof(Counters), st));
@@ -549,6 +565,10 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
             Q.work_counter = e->d_counts + 32 + w;
             Q.wave_index = w;
             if (single_batch) cudaEventRecord(e->wave_ev[w], st);
+            if (w == 0 && use_raster) {   // projected primary wave; the BVH one behind it runs only if the guard trips
+                int rr = trace_launch_raster(e, Q, records);
+                if (rr) return rr;
+            }
             int rc = trace_launch_wave(e, Q, w == 0, records);
             if (rc) return rc;
             waves++;
@@ -559,6 +579,8 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     // read-back of the counters into pinned memory; folded into the stats by pulse_collect()
     RTS_CUDA(cudaMemcpyAsync(&e->h_rb->counters, e->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     RTS_CUDA(cudaMemcpyAsync(e->h_rb->wave_segs, e->d_wave_segs, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost, st));
+    e->pulse_raster = use_raster;
+    if (use_raster) RTS_CUDA(cudaMemcpyAsync(&e->h_rb->raster, e->d_raster_ctl, sizeof(RasterCtl), cudaMemcpyDeviceToHost, st));
     e->pulse_pending = true;
     e->pulse_single_batch = single_batch && n_primary_total;
     e->pulse_primary = n_primary_total; e->pulse_waves = waves;
@@ -589,6 +611,10 @@ int pulse_collect(rts_engine *e)
     s.captured = c.captured; s.multi_captured = c.multi; s.edge_rays = c.edge; s.refracted = c.refracted;
     s.nodes_visited = c.nodes; s.tris_tested = c.tris; s.waves = e->pulse_waves;
     s.ms_trace = ms; s.ms_update = e->bvh_info.ms_refit; s.ms_total = ms;
+    // the guard of raster.cuh, evaluated on the last batch's control block (16 candidates per ray)
+    s.primary_projected = (e->pulse_raster && e->h_rb->raster.area <= 16ull * std::min<uint64_t>(e->pulse_primary, 1ull << 24)) ? 1u : 0u;
+    if (getenv("RTS_DEBUG_RASTER") && e->pulse_raster)
+        fprintf(stderr, "[raster] candidates %llu, %u row chunks, projected %u\n", e->h_rb->raster.area, e->h_rb->raster.n_items, s.primary_projected);
     if (c.overflow) return rts_fail(RTS_ERR_CAPACITY, "%llu ray states dropped (queue/stack overflow)", (unsigned long long)c.overflow);
     return RTS_OK;
 }

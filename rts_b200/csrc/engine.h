@@ -53,6 +53,14 @@ struct RayQueue {
     uint32_t *meta;            // reflDepth[0:8) refrDepth[8:10) slot[10:14) end[14] primary[15] col[16:20)
 };
 
+// control block and work items of the projected primary wave (raster.cuh)
+struct RasterCtl {
+    unsigned long long area;   // summed footprint (candidate ray/triangle pairs) of this batch
+    unsigned n_items;          // row chunks of large footprints
+    unsigned pad;
+};
+struct RasterItem { unsigned pos, z0, z1, pad; };
+
 struct Counters {              // device-side, accumulated with atomics
     unsigned long long segments, hits, shaded, captured, multi, edge, refracted, nodes, tris, overflow;
 };
@@ -121,6 +129,14 @@ struct WaveParams {
     unsigned long long *wave_segs;  // [32] segments traced per wave index
     uint32_t wave_index;
     uint32_t chain_below;           // later waves with fewer queued rays than this follow reflections in place
+    // primary visibility by projection (raster.cuh); raster_ctl == nullptr: off
+    double AT[9];                   // transpose of Rot1*Rot: world offset from the Tx -> beam frame
+    double *dirs[3];                // [batch] primary ray directions (struct of arrays)
+    unsigned long long *hits;       // [batch] (fp32 t bits << 32 | triangle id), ~0 = none
+    RasterCtl *raster_ctl;
+    RasterItem *raster_items;
+    uint32_t raster_item_cap;
+    const uint32_t *leaf_of_tri;
 };
 
 // ---- engine ---------------------------------------------------------------------------------
@@ -129,6 +145,7 @@ struct Readback {
     Counters counters;
     unsigned long long wave_segs[32];
     double sah;
+    RasterCtl raster;
 };
 
 // One slot of the pinned staging ring for small per-pulse host arrays (poses, receivers, velocities, RCS).
@@ -204,6 +221,12 @@ struct rts_engine {
     RxDev *d_rx = nullptr;
     int wave_grid = 0, wave_grid_primary = 0;
 
+    // primary visibility by projection
+    double *d_dirs = nullptr;
+    unsigned long long *d_hits = nullptr;
+    void *d_raster_ctl = nullptr, *d_raster_items = nullptr;
+    uint64_t raster_alloc = 0;
+
     // outputs
     double *d_bin_sums = nullptr;
     unsigned long long *d_bin_mins = nullptr;
@@ -223,7 +246,7 @@ struct rts_engine {
     int stage_next = 0;
     Readback *h_rb = nullptr;          // pinned
     bool pulse_pending = false;        // a pulse was enqueued and its read-back not yet folded into `stats`
-    bool pulse_single_batch = false;
+    bool pulse_single_batch = false, pulse_raster = false;
     uint64_t pulse_primary = 0, pulse_waves = 0;
 
     // last pulse
@@ -261,6 +284,8 @@ int pulse_collect(rts_engine *e);                   // fold the read-back of an 
 // trace.cu
 int trace_alloc_queues(rts_engine *e, uint64_t capacity);
 int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool records);
+int trace_raster_alloc(rts_engine *e, uint64_t batch);     // buffers of the projected primary wave
+int trace_launch_raster(rts_engine *e, WaveParams &p, bool records);   // enqueue it (before the BVH primary wave)
 int trace_wave_grid(rts_engine *e);
 
 // aggregate.cu

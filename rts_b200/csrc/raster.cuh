@@ -1,0 +1,315 @@
+// raster.cuh — primary visibility by projection (included inside trace.cu's anonymous namespace).
+//
+// Every primary ray leaves the transmitter origin, and before its two rotations the reference's ray direction is
+// linear in the launch index (ray_tracer.cu:167-169): d0 = (bs.x, bs.y + sy*iy, bs.z + sz*iz) — a pinhole camera with
+// image plane x = bs.x in the beam frame.  So instead of walking the BVH once per primary ray, each triangle is
+// projected into the launch grid, and only the rays inside its (padded) footprint run the reference's fp64 test
+// (triangle_mesh.cu:121-137) against it — with the very same ray direction the wave kernel would use (k_primary_dirs
+// evaluates primary_direction once per ray) and the same operations in the same order, so t, beta and gamma are
+// bit-identical.  The closest hit is an atomicMin over (fp32 t bits << 32 | triangle id): smallest fp32 t, ties to the
+// lowest global triangle id — the rule of traverse().  The footprint only has to be conservative: projection is done
+// in fp64 (errors ~1e-10 pixel) and padded by 1.5 pixels.
+//
+// STATUS: opt-in (environment variable RTS_RASTER=1).  Bit-identical results to the BVH primary wave on every parity
+// test, but on the 1M-triangle benchmark it only ties it (1.70 ms vs 1.66 ms per 16.8M-ray pulse: footprint walk
+// 0.91 ms at 46 % SIMT efficiency, direction pass 0.18 ms, shading pass 0.60 ms bound by the latency of the scattered
+// triangle-record fetch), so the BVH wave stays the default.
+//
+// Work distribution: one thread per triangle walks small footprints (k_raster_small); large ones are cut into row
+// chunks taken by warps (k_raster_big).  A device-side guard turns the whole path off for launches where the summed
+// footprint exceeds RTS_RASTER_LIMIT candidates per ray (huge overlapping triangles); the BVH primary wave, launched
+// right behind with the same control block, then does the work instead.  No host synchronisation either way.
+
+#ifndef RTS_SHADE_MIN_BLOCKS
+#define RTS_SHADE_MIN_BLOCKS 6
+#endif
+#define RTS_RASTER_SMALL 768u          // footprints up to this many candidates are walked by their own thread
+#define RTS_RASTER_CHUNK 2048u         // candidates per row chunk of a large footprint
+#define RTS_RASTER_LIMIT 16ull         // candidates per primary ray beyond which the BVH primary wave is used
+
+__device__ __forceinline__ bool raster_on(const WaveParams &P) { return P.raster_ctl->area <= RTS_RASTER_LIMIT * P.n_primary; }
+
+// shard-local index (relative to the batch) of launch-grid pixel (iy, iz), nx == 1
+__device__ __forceinline__ bool pixel_local(const WaveParams &P, unsigned iy, unsigned iz, unsigned &rel)
+{
+    const unsigned long long rayIndex = (unsigned long long)iz * P.ny + iy;
+    if (rayIndex < P.ray_begin) return false;
+    unsigned long long off = rayIndex - P.ray_begin;
+    if (P.ray_stride > 1) {
+        if (off % P.ray_stride) return false;
+        off /= P.ray_stride;
+    }
+    if (off < P.batch_base || off >= P.batch_base + P.n_primary) return false;
+    rel = (unsigned)(off - P.batch_base);
+    return true;
+}
+
+// ray directions of the batch, exactly as the wave kernel generates them, and the empty hit buffer
+__global__ void k_primary_dirs(const __grid_constant__ WaveParams P)
+{
+    for (unsigned long long rel = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; rel < P.n_primary;
+         rel += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long rayIndex = P.ray_begin + (P.batch_base + rel) * P.ray_stride;
+        const uint32_t iz = (uint32_t)(rayIndex / P.ny), iy = (uint32_t)(rayIndex % P.ny);
+        const d3 d = primary_direction(P, 0, iy, iz);
+        P.dirs[0][rel] = d.x; P.dirs[1][rel] = d.y; P.dirs[2][rel] = d.z;
+        P.hits[rel] = ~0ull;
+    }
+}
+
+struct TriFoot {
+    d3 e0, e1, n, pmo;          // hoisted terms of the reference test: p1-p0, p0-p2, e1 x e0, p0-o
+    uint32_t id;
+    int y0, y1, z0, z1;         // inclusive pixel bounds, already clamped to the grid; y0 > y1: no coverage
+    int ystep;                  // this shard's columns: y0 is on the shard's lattice, step = stride (or 1)
+    float ea[3], eb[3], ec[3];  // padded 2D edge functions relative to (y0, z0): inside iff all >= 0
+    bool use2d;
+};
+
+__device__ __forceinline__ double clampd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+
+// Footprint of the triangle at leaf position `pos`.  Returns false when no ray of the grid can hit it.
+__device__ __forceinline__ bool tri_footprint(const WaveParams &P, unsigned pos, TriFoot &F)
+{
+    const Tri T = load_tri(P.trirec, pos);
+    const d3 o = mk3(P.origin[0], P.origin[1], P.origin[2]);
+    F.e0 = T.p1 - T.p0;
+    F.e1 = T.p0 - T.p2;
+    F.n = cross3(F.e1, F.e0);
+    F.pmo = T.p0 - o;
+    F.id = T.id;
+    // beam-frame coordinates q = A^T (p - o); pixel u = (q.y * bs.x / q.x - bs.y) / sy, w likewise
+    const d3 v[3] = {T.p0 - o, T.p1 - o, T.p2 - o};
+    d3 q[3];
+    double scale = 0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        q[k].x = P.AT[0] * v[k].x + P.AT[1] * v[k].y + P.AT[2] * v[k].z;
+        q[k].y = P.AT[3] * v[k].x + P.AT[4] * v[k].y + P.AT[5] * v[k].z;
+        q[k].z = P.AT[6] * v[k].x + P.AT[7] * v[k].y + P.AT[8] * v[k].z;
+        scale = fmax(scale, fabs(q[k].x) + fabs(q[k].y) + fabs(q[k].z));
+    }
+    const double eps = 1e-9 * scale + 1e-300;      // near plane: hits are at t >= SCENE_EPS in front of the origin
+    const bool front[3] = {q[0].x > eps, q[1].x > eps, q[2].x > eps};
+    const int n_front = (int)front[0] + (int)front[1] + (int)front[2];
+    if (n_front == 0) return false;
+    const double bx = P.beamStart[0];
+    const double isy = P.ny > 1 ? 1.0 / P.slope[1] : 0.0, isz = P.nz > 1 ? 1.0 / P.slope[2] : 0.0;
+    double umin = 1e300, umax = -1e300, wmin = 1e300, wmax = -1e300;
+    double pu[3] = {0, 0, 0}, pw[3] = {0, 0, 0};
+    auto project = [&](const d3 &c, double &u, double &w) {
+        const double lam = bx / c.x;
+        u = (c.y * lam - P.beamStart[1]) * isy;
+        w = (c.z * lam - P.beamStart[2]) * isz;
+        umin = fmin(umin, u); umax = fmax(umax, u); wmin = fmin(wmin, w); wmax = fmax(wmax, w);
+    };
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        if (front[k]) project(q[k], pu[k], pw[k]);
+    if (n_front < 3) {
+        // clip against the near plane: the crossing points project far out, the grid clamp below takes care of them
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const int a = k, b = (k + 1) % 3;
+            if (front[a] != front[b]) {
+                const double s = (eps - q[a].x) / (q[b].x - q[a].x);
+                d3 c = mk3(eps, q[a].y + s * (q[b].y - q[a].y), q[a].z + s * (q[b].z - q[a].z));
+                double u, w;
+                project(c, u, w);
+            }
+        }
+    }
+    if (!(umin <= umax) || !(wmin <= wmax)) return false;   // NaN guard
+    const double big = 2.0e9;
+    int y0 = P.ny > 1 ? (int)clampd(floor(umin) - 1.0, -big, big) : 0, y1 = P.ny > 1 ? (int)clampd(ceil(umax) + 1.0, -big, big) : 0;
+    int z0 = P.nz > 1 ? (int)clampd(floor(wmin) - 1.0, -big, big) : 0, z1 = P.nz > 1 ? (int)clampd(ceil(wmax) + 1.0, -big, big) : 0;
+    y0 = max(y0, 0); y1 = min(y1, (int)P.ny - 1); z0 = max(z0, 0); z1 = min(z1, (int)P.nz - 1);
+    // rows of this batch only (a batch is a contiguous range of shard-local indices, i.e. of rows up to one partial row)
+    {
+        const unsigned long long first = P.ray_begin + P.batch_base * P.ray_stride;
+        const unsigned long long last = P.ray_begin + (P.batch_base + P.n_primary - 1) * P.ray_stride;
+        z0 = max(z0, (int)(first / P.ny)); z1 = min(z1, (int)(last / P.ny));
+    }
+    // columns of this shard only, when they form a lattice (stride divides the row length)
+    F.ystep = 1;
+    if (P.ray_stride > 1 && P.ny % P.ray_stride == 0) {
+        const int s = (int)P.ray_stride, c0 = (int)(P.ray_begin % P.ray_stride);
+        y0 += ((c0 - y0 % s) + s) % s;
+        F.ystep = s;
+    }
+    F.y0 = y0; F.y1 = y1; F.z0 = z0; F.z1 = z1;
+    if (y0 > y1 || z0 > z1) return false;
+    // padded edge functions (only for triangles entirely in front)
+    F.use2d = false;
+    if (n_front == 3 && P.ny > 1 && P.nz > 1) {
+        const double ax = pu[0] - y0, ay = pw[0] - z0, bxx = pu[1] - y0, by = pw[1] - z0, cx = pu[2] - y0, cy = pw[2] - z0;
+        const double area2 = (bxx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+        if (fabs(area2) > 1e-6 && fabs(ax) < 1e6 && fabs(ay) < 1e6 && fabs(bxx) < 1e6 && fabs(by) < 1e6 && fabs(cx) < 1e6 && fabs(cy) < 1e6) {
+            const double sg = area2 > 0 ? 1.0 : -1.0;
+            const double xs[3] = {ax, bxx, cx}, ys[3] = {ay, by, cy};
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int a = k, b = (k + 1) % 3;
+                const double A = -(ys[b] - ys[a]) * sg, B = (xs[b] - xs[a]) * sg;
+                const double C = -(A * xs[a] + B * ys[a]) + 1.5 * (fabs(A) + fabs(B)) + 1e-3 * (fabs(A * xs[a]) + fabs(B * ys[a]));
+                F.ea[k] = (float)A; F.eb[k] = (float)B; F.ec[k] = (float)C;
+            }
+            F.use2d = true;
+        }
+    }
+    return true;
+}
+
+__device__ __forceinline__ unsigned long long foot_area(const TriFoot &F)
+{
+    return (unsigned long long)((F.y1 - F.y0) / F.ystep + 1) * (unsigned long long)(F.z1 - F.z0 + 1);
+}
+
+__device__ __forceinline__ bool foot_inside2d(const TriFoot &F, int y, int z)
+{
+    if (!F.use2d) return true;
+    const float fy = (float)(y - F.y0), fz = (float)(z - F.z0);
+    const float e0 = fmaf(F.ea[0], fy, fmaf(F.eb[0], fz, F.ec[0]));
+    const float e1 = fmaf(F.ea[1], fy, fmaf(F.eb[1], fz, F.ec[1]));
+    const float e2 = fmaf(F.ea[2], fy, fmaf(F.eb[2], fz, F.ec[2]));
+    return fminf(fminf(e0, e1), e2) >= 0.f;
+}
+
+// The reference test for one ray of the footprint; same operations and order as tri_accept().
+__device__ __forceinline__ void foot_test(const WaveParams &P, const TriFoot &F, unsigned rel)
+{
+    const d3 dir = mk3(P.dirs[0][rel], P.dirs[1][rel], P.dirs[2][rel]);
+    const d3 e2 = (1 / dot3(F.n, dir)) * F.pmo;
+    const double t = dot3(F.n, e2);
+    if (!((t < (double)RT_DEFAULT_MAX_F) & (t > (double)SCENE_EPS))) return;
+    const d3 i = cross3(dir, e2);
+    const double beta = dot3(i, F.e1);
+    const double gamma = dot3(i, F.e0);
+    if (!((beta >= 0.0f) & (gamma >= 0.0f) & (beta + gamma <= 1))) return;
+    const float tf = (float)t;
+    if (!(tf > SCENE_EPS)) return;
+    atomicMin(P.hits + rel, ((unsigned long long)__float_as_uint(tf) << 32) | (unsigned long long)F.id);
+}
+
+// Pass 1: summed footprint (the guard) and the row chunks of the large footprints.
+__global__ void k_raster_setup(const __grid_constant__ WaveParams P)
+{
+    const unsigned pos = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long area = 0;
+    if (pos < P.n_tris) {
+        TriFoot F;
+        if (tri_footprint(P, pos, F)) {
+            area = foot_area(F);
+            if (area > RTS_RASTER_SMALL) {
+                const unsigned per_row = (unsigned)((F.y1 - F.y0) / F.ystep + 1);
+                const unsigned rows = max(1u, RTS_RASTER_CHUNK / per_row);
+                for (int z = F.z0; z <= F.z1; z += (int)rows) {
+                    const unsigned at = atomicAdd(&P.raster_ctl->n_items, 1u);
+                    if (at < P.raster_item_cap) {
+                        RasterItem it; it.pos = pos; it.z0 = (unsigned)z; it.z1 = (unsigned)min(F.z1, z + (int)rows - 1); it.pad = 0;
+                        P.raster_items[at] = it;
+                    } else {
+                        area = 1ull << 56;   // too many chunks: turn the path off
+                        break;
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(0xffffffffu, area, o);
+    if ((threadIdx.x & 31) == 0 && area) atomicAdd(&P.raster_ctl->area, area);
+}
+
+// Pass 2a: one thread per triangle with a small footprint.  Each lane first scans forward to its next candidate
+// that passes the cheap 2D test, then the warp runs the fp64 test together.
+__global__ void k_raster_small(const __grid_constant__ WaveParams P)
+{
+    if (!raster_on(P)) return;
+    const unsigned pos = blockIdx.x * blockDim.x + threadIdx.x;
+    TriFoot F;
+    bool have = pos < P.n_tris && tri_footprint(P, pos, F) && foot_area(F) <= RTS_RASTER_SMALL;
+    int y = have ? F.y0 : 0, z = have ? F.z0 : 1;
+    const int z1 = have ? F.z1 : 0;
+    while (__any_sync(0xffffffffu, z <= z1)) {
+        unsigned rel = 0;
+        bool found = false;
+        while (z <= z1) {
+            const bool ok = foot_inside2d(F, y, z) && pixel_local(P, (unsigned)y, (unsigned)z, rel);
+            y += F.ystep;
+            if (y > F.y1) { y = F.y0; z++; }
+            if (ok) { found = true; break; }
+        }
+        if (found) foot_test(P, F, rel);
+    }
+}
+
+// Pass 2b: one warp per row chunk of a large footprint, lanes stride along the row.
+__global__ void k_raster_big(const __grid_constant__ WaveParams P)
+{
+    if (!raster_on(P)) return;
+    const unsigned n_items = min(P.raster_ctl->n_items, P.raster_item_cap);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (unsigned it = warp; it < n_items; it += n_warps) {
+        const RasterItem I = P.raster_items[it];
+        TriFoot F;
+        if (!tri_footprint(P, I.pos, F)) continue;
+        for (int z = (int)I.z0; z <= (int)I.z1; z++)
+            for (int y = F.y0 + (int)lane * F.ystep; y <= F.y1; y += 32 * F.ystep) {
+                unsigned rel;
+                if (foot_inside2d(F, y, z) && pixel_local(P, (unsigned)y, (unsigned)z, rel)) foot_test(P, F, rel);
+            }
+    }
+}
+
+// Pass 3: the primary wave without traversal — the closest hit comes from the hit buffer.
+template <bool RECORDS>
+__global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_primary_shade(const __grid_constant__ WaveParams P)
+{
+    if (!raster_on(P)) return;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned n_in = (unsigned)P.n_primary;
+    unsigned *work = reinterpret_cast<unsigned *>(P.work_counter);
+    Local L = {0, 0, 0, 0, 0};
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(P.wave_segs + P.wave_index, (unsigned long long)n_in);
+        atomicAdd(&P.counters->segments, (unsigned long long)n_in);
+    }
+    for (;;) {
+        unsigned base = 0;
+        if (lane == 0) base = atomicAdd(work, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n_in) break;
+        const unsigned rel = base + lane;
+        if (rel >= n_in) continue;
+        Ray r;
+        r.ox = P.origin[0]; r.oy = P.origin[1]; r.oz = P.origin[2];
+        r.dx = P.dirs[0][rel]; r.dy = P.dirs[1][rel]; r.dz = P.dirs[2][rel];
+        r.meta = m_make(0, 0, 0, false, true, 0);
+        r.len = 0; r.pw = 0; r.dop = 0; r.fx = 0; r.fy = 0; r.fz = 0; r.n0 = 1; r.n1 = 1;
+        r.key = 0; r.ray = (uint32_t)(P.ray_begin + (P.batch_base + rel) * P.ray_stride);
+        const unsigned long long hit = P.hits[rel];
+        if (hit != ~0ull) {
+            HitRec h;
+            h.id = (uint32_t)hit; h.t = __uint_as_float((unsigned)(hit >> 32)); h.pos = (int)P.leaf_of_tri[h.id];
+            L.a += C_HIT;
+            shade<RECORDS>(P, r, h, L, false);
+        } else {
+            const int received = miss<RECORDS>(P, r, L);
+            if (received >= 0) {
+                L.a += C_CAPTURED;
+                if (P.flags & RTS_OUT_BINS) accumulate_bin(P, r, received);
+            }
+        }
+    }
+    unsigned long long *c = reinterpret_cast<unsigned long long *>(P.counters);
+    const unsigned f[7] = {(unsigned)(L.a & 0x1fffff), (unsigned)((L.a >> 21) & 0x1fffff), (unsigned)(L.a >> 42),
+                           (unsigned)(L.b & 0x1fffff), (unsigned)((L.b >> 21) & 0x1fffff), (unsigned)(L.b >> 42), L.overflow};
+    const int slot[7] = {1, 2, 3, 4, 5, 6, 9};
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        const unsigned x = __reduce_add_sync(0xffffffffu, f[k]);
+        if (lane == 0 && x) atomicAdd(c + slot[k], (unsigned long long)x);
+    }
+}

@@ -624,9 +624,12 @@ __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r
     }
 }
 
+#include "raster.cuh"
+
 template <bool PRIMARY, bool RECORDS, bool COUNT, bool CHAIN>
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_PRIMARY : RTS_WAVE_MIN_BLOCKS) k_wave(const __grid_constant__ WaveParams P)
 {
+    if (PRIMARY && P.raster_ctl && raster_on(P)) return;   // the projected primary wave (raster.cuh) did this batch
     const unsigned lane = threadIdx.x & 31u;
     // queue capacity and batch size are < 2^26, so 32-bit indices and a 32-bit work counter suffice
     const unsigned n_in = PRIMARY ? (unsigned)P.n_primary : (unsigned)*P.in_count;
@@ -761,6 +764,45 @@ int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool rec
     else launch_variant<false, false>(grid, e->stream, p, records, count);
     RTS_CUDA(cudaGetLastError());
     e->launches++;
+    return RTS_OK;
+}
+
+#define RTS_RASTER_ITEM_CAP (1u << 20)
+
+int trace_raster_alloc(rts_engine *e, uint64_t batch)
+{
+    if (e->raster_alloc >= batch) return RTS_OK;
+    void **ptrs[] = {(void **)&e->d_dirs, (void **)&e->d_hits, &e->d_raster_ctl, &e->d_raster_items};
+    for (void **p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+    e->raster_alloc = 0;
+    RTS_CUDA(cudaMalloc(&e->d_dirs, sizeof(double) * 3 * batch));
+    RTS_CUDA(cudaMalloc(&e->d_hits, sizeof(unsigned long long) * batch));
+    RTS_CUDA(cudaMalloc(&e->d_raster_ctl, sizeof(RasterCtl)));
+    RTS_CUDA(cudaMalloc(&e->d_raster_items, sizeof(RasterItem) * (size_t)RTS_RASTER_ITEM_CAP));
+    e->raster_alloc = batch;
+    return RTS_OK;
+}
+
+int trace_launch_raster(rts_engine *e, WaveParams &p, bool records)
+{
+    cudaStream_t st = e->stream;
+    for (int a = 0; a < 3; a++) p.dirs[a] = e->d_dirs + (size_t)a * e->raster_alloc;
+    p.hits = e->d_hits;
+    p.raster_ctl = (RasterCtl *)e->d_raster_ctl;
+    p.raster_items = (RasterItem *)e->d_raster_items;
+    p.raster_item_cap = RTS_RASTER_ITEM_CAP;
+    p.leaf_of_tri = e->d_leaf_of_tri;
+    RTS_CUDA(cudaMemsetAsync(e->d_raster_ctl, 0, sizeof(RasterCtl), st));
+    const unsigned bs = 128;
+    const unsigned tri_blocks = (p.n_tris + bs - 1) / bs;
+    k_primary_dirs<<<e->num_sms * 16, 256, 0, st>>>(p);
+    k_raster_setup<<<tri_blocks, bs, 0, st>>>(p);
+    k_raster_small<<<tri_blocks, bs, 0, st>>>(p);
+    k_raster_big<<<e->num_sms * 8, bs, 0, st>>>(p);
+    if (records) k_primary_shade<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
+    else k_primary_shade<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
+    RTS_CUDA(cudaGetLastError());
+    e->launches += 5;
     return RTS_OK;
 }
 

@@ -297,3 +297,35 @@ def test_targets_that_start_moving_later_and_drift_rebuild(engine):
     engine.set_poses(ident[0], trans)
     hits_now(trans)
     assert engine.bvh_info().builds > builds
+
+
+@pytest.mark.parametrize("name", ["plate", "trihedral", "slab", "terrain"])
+def test_projected_primary_wave_is_bit_identical(engine, name, monkeypatch):
+    """RTS_RASTER=1 (rts_b200/csrc/raster.cuh): primary visibility by projecting the triangles into the launch grid
+    instead of walking the BVH per ray — same closest hits, hence the same records bit for bit, also for a shard."""
+    if name == "plate":
+        targets, spec = scenes.flat_plate(n=256)
+    elif name == "trihedral":
+        targets, spec = scenes.trihedral(n=300)
+    elif name == "slab":
+        targets, spec = scenes.slab(n=96)
+    else:
+        ms = scenes.terrain_scene(n=256, cells_x=100, cells_y=50, movers=6, n_rx=2)
+        targets, spec = ms.world_targets(3), ms.spec_for(3)
+    engine.set_targets(targets)
+    for shard in ((0, 0, 0), (1, 0, 4)):
+        spec.ray_begin, spec.ray_count, spec.ray_stride = shard
+        monkeypatch.delenv("RTS_RASTER", raising=False)
+        st0 = engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_OUT_BINS)
+        a, bins_a = engine.records(), engine.bins()
+        monkeypatch.setenv("RTS_RASTER", "1")
+        st1 = engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_OUT_BINS)
+        b, bins_b = engine.records(), engine.bins()
+        for k in ("segments", "hits", "shaded_hits", "captured", "edge_rays"):
+            assert st0[k] == st1[k], (name, shard, k)
+        assert st0["primary_projected"] == 0 and st1["primary_projected"] == 1
+        assert np.array_equal(a[3], b[3]) and np.array_equal(a[1], b[1])
+        for f in a[0].dtype.names:
+            assert a[0][f].tobytes() == b[0][f].tobytes(), (name, shard, f)
+        parity.assert_bins_close(parity.compare_bins(bins_b, bins_a), rtol=1e-12)
+    spec.ray_begin = spec.ray_count = spec.ray_stride = 0
