@@ -329,3 +329,51 @@ def test_projected_primary_wave_is_bit_identical(engine, name, monkeypatch):
             assert a[0][f].tobytes() == b[0][f].tobytes(), (name, shard, f)
         parity.assert_bins_close(parity.compare_bins(bins_b, bins_a), rtol=1e-12)
     spec.ray_begin = spec.ray_count = spec.ray_stride = 0
+
+
+def _raw_bins(engine):
+    import torch
+    from rts_b200 import dist as rdist
+    sums, mins = rdist.bins_as_tensors(engine, torch.device("cuda:0"))
+    return sums.cpu().numpy().reshape(-1, 5).copy(), mins.cpu().numpy().view(np.uint64).copy()
+
+
+def test_C5_multistatic_eight_shards_and_batched_launch(engine):
+    """C5 shape at reduced ray count: 1M-triangle terrain + movers, 8 receivers, rays dealt round-robin to 8 shards
+    (what the 8 ranks of bench.py trace) — the reduced bins equal the single launch's.  Then a launch larger than
+    one 2^24-ray batch: equal to the sum of its two halves traced separately."""
+    from rts_b200 import dist as rdist
+    ms = scenes.terrain_scene(n=2048, n_rx=8)
+    engine.set_targets(ms.base)
+    pulse = 5
+    engine.set_poses(*ms.poses(pulse))
+    spec = ms.spec_for(pulse)
+    st_full = engine.trace(spec, L.RTS_OUT_BINS | L.RTS_NO_FINALISE)
+    full = _raw_bins(engine)
+    parts, seg = [], 0
+    for r in range(8):
+        spec.ray_begin, spec.ray_count, spec.ray_stride = r, 0, 8
+        st = engine.trace(spec, L.RTS_OUT_BINS | L.RTS_NO_FINALISE)
+        seg += st["segments"]
+        parts.append(_raw_bins(engine))
+    msum, mmin = rdist.merge_bins_numpy(parts)
+    assert seg == st_full["segments"]
+    assert np.array_equal(msum[:, 0], full[0][:, 0]) and np.array_equal(mmin, full[1])
+    assert np.allclose(msum, full[0], rtol=1e-11, atol=0)
+    assert (full[0][:, 0] > 0).sum() >= 8          # every receiver got something
+    # batching: (1, 8192, 4096) = 2 x 2^24 primaries
+    big = ms.spec_for(pulse)
+    big.grid = (1, 8192, 4096)
+    big.ray_begin = big.ray_count = big.ray_stride = 0
+    st_big = engine.trace(big, L.RTS_OUT_BINS | L.RTS_NO_FINALISE)
+    whole = _raw_bins(engine)
+    halves, seg = [], 0
+    for h in range(2):
+        big.ray_begin, big.ray_count = h << 24, 1 << 24
+        st = engine.trace(big, L.RTS_OUT_BINS | L.RTS_NO_FINALISE)
+        seg += st["segments"]
+        halves.append(_raw_bins(engine))
+    hsum, hmin = rdist.merge_bins_numpy(halves)
+    assert st_big["primary_rays"] == 2 << 24 and seg == st_big["segments"]
+    assert np.array_equal(hsum[:, 0], whole[0][:, 0]) and np.array_equal(hmin, whole[1])
+    assert np.allclose(hsum, whole[0], rtol=1e-11, atol=0)
