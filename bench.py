@@ -150,7 +150,9 @@ def run_ours(args):
                 waves.append(eng.wave_profile())
                 segs += st["segments"]
                 caps += st["captured"]
-                d2h += bins.nbytes
+                # device -> pinned host per step: the emitted-bin block (256 x sizeof(rts_bin)), its count, the
+                # counters and per-wave segment counts of the read-back block, and the SAH cost of the refit
+                d2h += 256 * bins.dtype.itemsize + 4 + 80 + 256 + 8
         e1.record(stream)
         barrier()
         wall = time.perf_counter() - t0

@@ -151,6 +151,8 @@ int rts_get_received(rts_engine *e, uint64_t cap, uint64_t *n, uint64_t *slots, 
  *              reduction over either uint64 or int64 views is correct */
 int rts_bins_device(rts_engine *e, void **sums_device, uint64_t *n_sum_doubles, void **mins_device,
                     uint64_t *n_mins);
+/* Marks the (externally reduced) bins final and enqueues their emission on the engine's stream: call it after the
+ * reduction has been enqueued on that same stream (rts_set_stream) or has completed. */
 int rts_finalise_bins(rts_engine *e);
 
 /* ---- aggregation of caller-supplied received rays: the C form of rs::kernel_wrapper

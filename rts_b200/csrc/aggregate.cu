@@ -9,6 +9,8 @@
 #include <cooperative_groups.h>
 #include <cooperative_groups/reduce.h>
 #include <algorithm>
+#include <cstring>
+#include <vector>
 #include <math_constants.h>
 #include <cub/device/device_select.cuh>
 #include <thrust/iterator/counting_iterator.h>
@@ -257,24 +259,30 @@ int agg_fill_records(rts_engine *e, uint64_t ray_total, uint32_t D, uint32_t W)
     return RTS_OK;
 }
 
-int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
+static void sort_bins(rts_bin *out, uint32_t got)
+{
+    std::sort(out, out + got, [](const rts_bin &a, const rts_bin &b) {
+        if (a.rx != b.rx) return a.rx < b.rx;
+        for (uint32_t c = 0; c < RTS_MAX_DEPTH; c++)
+            if (a.path[c] != b.path[c]) return a.path[c] < b.path[c];
+        return false;
+    });
+}
+
+// receiver totals (direct-ray rule) + myKernel2 + compaction of the non-empty bins into d_bins_out, enqueued
+static int enqueue_emit(rts_engine *e, uint32_t cap)
 {
     const uint64_t nb = e->n_bins_dense;
     const uint32_t n_rx = e->last_nrx, B = e->last_B, D = e->last_D;
-    if (!nb || !n_rx) { if (n) *n = 0; return RTS_OK; }
     const uint64_t per_rx = nb / n_rx;
-    // receiver totals
     if (!e->d_rx_sums) {
         RTS_CUDA(cudaMalloc(&e->d_rx_sums, sizeof(double) * 5 * RTS_MAX_RX));
         RTS_CUDA(cudaMalloc(&e->d_rx_mins, sizeof(unsigned long long) * RTS_MAX_RX));
     }
-    double *rx_sums = e->d_rx_sums;
-    unsigned long long *rx_mins = e->d_rx_mins;
-    RTS_CUDA(cudaMemsetAsync(rx_sums, 0, sizeof(double) * 5 * n_rx, e->stream));
-    RTS_CUDA(cudaMemsetAsync(rx_mins, 0xff, sizeof(unsigned long long) * n_rx, e->stream));
+    RTS_CUDA(cudaMemsetAsync(e->d_rx_sums, 0, sizeof(double) * 5 * n_rx, e->stream));
+    RTS_CUDA(cudaMemsetAsync(e->d_rx_mins, 0xff, sizeof(unsigned long long) * n_rx, e->stream));
     dim3 grid((unsigned)std::min<uint64_t>(64, (per_rx + 255) / 256), n_rx);
-    { k_rx_totals<<<grid, 256, 0, e->stream>>>(e->d_bin_sums, e->d_bin_mins, per_rx, n_rx, rx_sums, rx_mins); e->launches++; }
-    // compact non-empty bins
+    { k_rx_totals<<<grid, 256, 0, e->stream>>>(e->d_bin_sums, e->d_bin_mins, per_rx, n_rx, e->d_rx_sums, e->d_rx_mins); e->launches++; }
     const uint64_t want = std::max<uint64_t>(cap, 1);
     if (e->bins_out_alloc < want) {
         if (e->d_bins_out) cudaFree(e->d_bins_out);
@@ -284,21 +292,56 @@ int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
     }
     if (!e->d_bins_out_count) RTS_CUDA(cudaMalloc(&e->d_bins_out_count, sizeof(uint32_t)));
     RTS_CUDA(cudaMemsetAsync(e->d_bins_out_count, 0, sizeof(uint32_t), e->stream));
-    { k_emit_bins<<<blocks_for(nb, 256), 256, 0, e->stream>>>(e->d_bin_sums, e->d_bin_mins, nb, per_rx, B, D, rx_sums, rx_mins,
+    { k_emit_bins<<<blocks_for(nb, 256), 256, 0, e->stream>>>(e->d_bin_sums, e->d_bin_mins, nb, per_rx, B, D, e->d_rx_sums, e->d_rx_mins,
                                                            e->d_bins_out, e->d_bins_out_count, cap); e->launches++; }
     RTS_CUDA(cudaGetLastError());
+    return RTS_OK;
+}
+
+// Emit the bins right behind the pulse (or the caller's reduction) and bring them to pinned host memory with the
+// rest of the read-back, so that rts_get_bins costs one wait instead of three.  Small tables only.
+int agg_emit_bins_async(rts_engine *e)
+{
+    e->bins_eager = false;
+    const uint64_t nb = e->n_bins_dense;
+    if (!nb || !e->last_nrx || nb > (1ull << 18)) return RTS_OK;
+    if (!e->h_bins && cudaMallocHost((void **)&e->h_bins, sizeof(rts_bin) * RTS_EAGER_BINS) != cudaSuccess) { e->h_bins = nullptr; return RTS_OK; }
+    int rc = enqueue_emit(e, RTS_EAGER_BINS);
+    if (rc) return rc;
+    RTS_CUDA(cudaMemcpyAsync(&e->h_rb->bins_count, e->d_bins_out_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    RTS_CUDA(cudaMemcpyAsync(e->h_bins, e->d_bins_out, sizeof(rts_bin) * RTS_EAGER_BINS, cudaMemcpyDeviceToHost, e->stream));
+    e->bins_eager = true;
+    return RTS_OK;
+}
+
+int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
+{
+    const uint64_t nb = e->n_bins_dense;
+    if (!nb || !e->last_nrx) { if (n) *n = 0; return RTS_OK; }
+    if (e->bins_eager) {   // already in pinned memory (the caller has waited for the stream)
+        RTS_CUDA(cudaStreamSynchronize(e->stream));
+        const uint32_t count = e->h_rb->bins_count;
+        if (count <= RTS_EAGER_BINS) {
+            const uint32_t got = std::min(count, cap);
+            if (out && got) {
+                std::vector<rts_bin> all(e->h_bins, e->h_bins + count);
+                sort_bins(all.data(), count);
+                memcpy(out, all.data(), sizeof(rts_bin) * got);
+            }
+            if (n) *n = count;
+            e->stats.n_bins = count;
+            return RTS_OK;
+        }
+    }
+    int rc = enqueue_emit(e, cap);
+    if (rc) return rc;
     uint32_t count = 0;
     RTS_CUDA(cudaMemcpyAsync(&count, e->d_bins_out_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     RTS_CUDA(cudaStreamSynchronize(e->stream));
     const uint32_t got = std::min(count, cap);
     if (out && got) {
         RTS_CUDA(cudaMemcpy(out, e->d_bins_out, sizeof(rts_bin) * got, cudaMemcpyDeviceToHost));
-        std::sort(out, out + got, [](const rts_bin &a, const rts_bin &b) {
-            if (a.rx != b.rx) return a.rx < b.rx;
-            for (uint32_t c = 0; c < RTS_MAX_DEPTH; c++)
-                if (a.path[c] != b.path[c]) return a.path[c] < b.path[c];
-            return false;
-        });
+        sort_bins(out, got);
     }
     if (n) *n = count;
     e->stats.n_bins = count;

@@ -129,6 +129,7 @@ extern "C" void rts_destroy(rts_engine *e)
     for (auto &s : e->stage) { if (s.done) cudaEventDestroy(s.done); if (s.host) cudaFreeHost(s.host); }
     if (e->sah_ev) cudaEventDestroy(e->sah_ev);
     if (e->h_rb) cudaFreeHost(e->h_rb);
+    if (e->h_bins) cudaFreeHost(e->h_bins);
     if (e->d_wave_segs) cudaFree(e->d_wave_segs);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -587,6 +588,11 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     e->have_pulse = true; e->last_flags = flags; e->last_sizes = sz;
     e->last_B = (uint32_t)B; e->last_D = sz.depth_total; e->last_nrx = p->n_rx;
     e->bins_finalised = !(flags & RTS_NO_FINALISE);
+    e->bins_eager = false;
+    if ((flags & RTS_OUT_BINS) && e->bins_finalised) {
+        int rc = agg_emit_bins_async(e);
+        if (rc) return rc;
+    }
     if (flags & RTS_ASYNC) return RTS_OK;
     return pulse_collect(e);
 }
@@ -716,8 +722,9 @@ extern "C" int rts_finalise_bins(rts_engine *e)
 {
     if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
     if (!e->have_pulse || !(e->last_flags & RTS_OUT_BINS)) return rts_fail(RTS_ERR_STATE, "last pulse did not produce bins");
-    e->bins_finalised = true; // myKernel2 is applied when bins are collected (agg_collect_bins)
-    return RTS_OK;
+    e->bins_finalised = true; // myKernel2 is applied when bins are emitted
+    RTS_CUDA(cudaSetDevice(e->device));
+    return agg_emit_bins_async(e);   // behind the caller's reduction, which runs on the engine's stream
 }
 
 extern "C" int rts_get_records(rts_engine *e, rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle,

@@ -17,6 +17,7 @@
 #define RTS_WAVE_MIN_BLOCKS_PRIMARY 8   // same, primary wave (its state is smaller)
 #endif
 #define RTS_MAX_RX 64
+#define RTS_EAGER_BINS 256u      // bins brought to pinned host memory right behind a pulse
 #define RTS_REBUILD_RATIO 1.2   // refit falls back to a rebuild when SAH cost exceeds this x the as-built cost
 
 // ---- device layouts -------------------------------------------------------------------------
@@ -146,6 +147,7 @@ struct Readback {
     unsigned long long wave_segs[32];
     double sah;
     RasterCtl raster;
+    uint32_t bins_count;
 };
 
 // One slot of the pinned staging ring for small per-pulse host arrays (poses, receivers, velocities, RCS).
@@ -231,7 +233,8 @@ struct rts_engine {
     double *d_bin_sums = nullptr;
     unsigned long long *d_bin_mins = nullptr;
     uint64_t n_bins_dense = 0, bins_alloc = 0;
-    rts_bin *d_bins_out = nullptr;
+    rts_bin *d_bins_out = nullptr, *h_bins = nullptr;   // h_bins: pinned
+    bool bins_eager = false;
     double *d_rx_sums = nullptr;
     unsigned long long *d_rx_mins = nullptr;
     uint32_t *d_bins_out_count = nullptr;
@@ -291,6 +294,7 @@ int trace_wave_grid(rts_engine *e);
 // aggregate.cu
 int agg_finalise_bins(rts_engine *e);
 int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n);
+int agg_emit_bins_async(rts_engine *e);
 int agg_fill_records(rts_engine *e, uint64_t ray_total, uint32_t D, uint32_t W);
 int agg_get_received(rts_engine *e, uint64_t cap, uint64_t *n, uint64_t *slots, rts_ray_record *results, int32_t *targ_intersect,
                      double *rcs_angle);
