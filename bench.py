@@ -220,7 +220,7 @@ def run_ours(args):
                                    + (f", launch grid (1,{N_GRID * world},{N_GRID}) ray-sharded round-robin, NCCL all-reduce of bins" if world > 1 else ""),
                        "triangles": int(sum(len(t.tris) for t in ms.base)), "rays_per_step": int(rays_per_step_total),
                        "segments_per_ray": round(seg_per_ray, 4), "captured_per_step": int(r_e2e["captured"] / args.steps),
-                       "l2_policy": "per-step working set (BVH 21 MB + triangles 81 MB + 2.4 GB ray queues written and re-read) exceeds the 126 MB L2",
+                       "l2_policy": "per-step working set (BVH 64 MB + triangle records 81 MB + 2.4 GB of ray queues written and re-read) exceeds the 126 MB L2; no flush needed",
                        "parallelism": f"ray-shard x{world}"},
             "e2e": {"value": round(e2e, 2), "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(r_e2e["d2h"] / args.steps),
                     "ms_per_step": round(r_e2e["ms"] / args.steps, 4)},

@@ -164,14 +164,16 @@ __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0,
 // that the test is conservative with respect to the exact slab interval of the true fp64 ray (o, d).
 // Per axis a, for a box [c-h, c+h] (c, h exact fp32 values; the box contains the reference's leaf box):
 //   exact      near* = (c - o)/d - h/|d|          far* = (c - o)/d + h/|d|
-//   computed   T = fma(c, inv, -oi)               inv = fl32(1/d), oi = fl32(o/d)   (1/d, o/d evaluated in fp64)
-//              H = fma(h, |inv|, E)               E   = 2^-21 * 1.0001 * (S + |o|) * |inv|
+//   computed   T = fma(c, inv, -oi)               inv = rcp.approx(fl32(d)), oi = fl32(fl32(o) * inv)   (all fp32)
+//              H = fma(h, |inv|, E)               E   = 2^-20 * (S + |o|) * |inv|
 //              near = T - H                       far = T + H
-// With S = max |coordinate| of the scene box on the axis (|c| <= S, h <= S) and u = 1/|d|:
-//   |T - (c-o)/d| <= 2^-23 (S+|o|) u,  H >= (h u (1 - 2^-24) + E)(1 - 2^-24),  |fl(T -+ H) - (T -+ H)| <= 2^-24 (|T| + H)
-// so near <= near* and far >= far* whenever E >= 6 * 2^-24 (S+|o|) u = 0.75 * 2^-21 (S+|o|) u: a box is never
+// With S = max |coordinate| of the scene box on the axis (|c| <= S, h <= S), u = 1/|d|, and the relative errors
+// |inv d - 1| <= 2^-24 + 2^-23 (narrowing + MUFU.RCP, PTX: max relative error 2^-23), |oi d/o - 1| <= 2.6 * 2^-23:
+//   |T - (c-o)/d| <= 2^-23 (2.1 |c| + 3.1 |o|) u,  H >= (h u (1 - 1.6 * 2^-23) + E)(1 - 2^-24),
+//   |fl(T -+ H) - (T -+ H)| <= 2^-24 (|T| + H)
+// so near <= near* and far >= far* whenever E >= 2^-23 (5.2 S + 3.6 |o|) u, i.e. 0.65 * 2^-20 (S+|o|) u: a box is never
 // pruned when the fp64 triangle test (triangle_mesh.cu:121-137) could accept a hit inside it.  Only the bound
-// matters here, not bit-reproducibility, so fused multiply-adds are fine.  Axes with |d| < 1e-20 are ignored
+// matters here, not bit-reproducibility, so fused multiply-adds are fine.  Axes with |fl32(d)| < 1e-20 are ignored
 // (T = 0, H = inf: always overlapping).  The x,y lanes of one child and the z lanes of both children are packed
 // fp32 pairs, matching the BvhNode word order: 12 packed instructions test both child boxes.
 // Closest hit = smallest fp32 t in (tmin, inf), ties to the lowest global triangle id
@@ -184,18 +186,19 @@ __device__ __forceinline__ void traverse(const WaveParams &P, const d3 &o, const
     if (P.n_tris == 0) return;
     u64 inv_xy, noi_xy, ainv_xy, e_xy, inv_zz, noi_zz, ainv_zz, e_zz;
     {
-        const double oo[3] = {o.x, o.y, o.z}, dd[3] = {dir.x, dir.y, dir.z};
+        const float oo[3] = {(float)o.x, (float)o.y, (float)o.z}, dd[3] = {(float)dir.x, (float)dir.y, (float)dir.z};
         float inv[3], noi[3], ainv[3], E[3];
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-            if (fabs(dd[a]) < 1e-20) {
+            if (!(fabsf(dd[a]) >= 1e-20f)) {
                 inv[a] = 0.f; noi[a] = 0.f; ainv[a] = 0.f; E[a] = CUDART_INF_F;
             } else {
-                const double id = 1.0 / dd[a];
-                inv[a] = (float)id;
-                noi[a] = -(float)(oo[a] * id);
-                ainv[a] = fabsf(inv[a]);
-                E[a] = 4.76837158203125e-07f * ((P.scene_abs[a] + fabsf((float)oo[a])) * ainv[a]) * 1.0001f + 1e-30f;
+                float r;
+                asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(dd[a]));
+                inv[a] = r;
+                noi[a] = -(oo[a] * r);
+                ainv[a] = fabsf(r);
+                E[a] = 9.5367431640625e-07f * ((P.scene_abs[a] + fabsf(oo[a])) * ainv[a]) + 1e-30f;
             }
         }
         inv_xy = pk2(inv[0], inv[1]); noi_xy = pk2(noi[0], noi[1]); ainv_xy = pk2(ainv[0], ainv[1]); e_xy = pk2(E[0], E[1]);
