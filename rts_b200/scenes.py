@@ -88,6 +88,23 @@ def direct_and_plate(n: int = 64, side: int = 1) -> Tuple[List[Target], PulseSpe
     return targets, spec
 
 
+def spheres(n: int = 96, interpolate: bool = True, max_refl: int = 2, max_refr: int = 2) -> Tuple[List[Target], PulseSpec]:
+    """Two moving dielectric `sphere` targets (subdivided icosahedra, vertex normals = unit positions) in front of a
+    metal back plate: exercises the barycentric normal interpolation of triangle_mesh.cu:186-190, Doppler from target
+    velocities (normal_shader.cu:251-256, 302-314) and refraction through curved surfaces."""
+    out = []
+    for centre, radius, sub, refl, refr in (((40.0, -5.0, 1.0), 4.0, 3, 0.5, 1.5), ((55.0, 6.0, -2.0), 5.0, 2, 0.7, 2.2)):
+        v, t, nrm = lib.sphere_mesh(sub, radius)
+        out.append(Target(v + np.array(centre), t, nrm, refl_coeff=refl, refr_index=refr))
+    v, t, fn = lib.rect_mesh(1.0, 60.0, 40.0)
+    out.append(Target(v + np.array([90.0, 0.0, 0.0]), t, fn, refl_coeff=1.0, refr_index=1.0))
+    rx = [_rx((0.0, 0.0, 0.0), 0.0, 0.0, 30.0, 2.5, 2.5), _rx((20.0, 50.0, 0.0), -1.2, 0.0, 25.0, 3.0, 3.0)]
+    spec = PulseSpec(grid=(1, n, n), max_refl=max_refl, max_refr=max_refr, interpolate_smooth=interpolate, tx_origin=(0, 0, 0),
+                     tx_dir=(0.0, 0.0), tx_span=(0.45, 0.3, 0.0), rx=rx,
+                     targ_vel=np.array([[30.0, -12.0, 4.0], [-25.0, 8.0, -3.0], [0.0, 0.0, 0.0]]))
+    return out, spec
+
+
 # ---- C3: dielectric "ship" -------------------------------------------------------------------
 
 def _superellipsoid(nu: int, nv: int, a: float, b: float, c: float, e1: float = 0.6, e2: float = 0.8):

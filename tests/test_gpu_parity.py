@@ -29,6 +29,8 @@ SMALL = {
     "slab_interp": lambda: scenes.slab(n=64, interpolate=True, refr_index=1.3, max_refl=3),
     "slab_thin": lambda: scenes.slab(n=64, thickness=0.004, max_refl=1),
     "ship_small": lambda: scenes.ship(n=96, hull_res=32),
+    "spheres_interp": lambda: scenes.spheres(n=96),
+    "spheres_flat": lambda: scenes.spheres(n=64, interpolate=False, max_refl=3, max_refr=0),
 }
 
 
