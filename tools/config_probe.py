@@ -1,0 +1,28 @@
+"""Throughput of the BASELINE.json configs C1-C3 at their full sizes on one GPU (run under gpurun); C4 is bench.py."""
+import json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from rts_b200 import scenes, lib as L
+
+def main():
+    eng = L.Engine(0)
+    cases = [("C1 flat plate 256x256, 1 bounce", scenes.flat_plate(n=256)),
+             ("C2 trihedral 1000x1000, 3 bounces", scenes.trihedral(n=1000)),
+             ("C2 trihedral cubic 100^3 (reference launch shape)", scenes.trihedral(n=100, cubic=True)),
+             ("C3 ship 100k triangles, refraction, 4096x4096, 4 Rx", scenes.ship(n=4096, hull_res=200))]
+    for name, (t, s) in cases:
+        eng.set_targets(t)
+        best = None
+        for rep in range(4):
+            st = eng.trace(s, L.RTS_OUT_BINS)
+            if best is None or st["ms_trace"] < best["ms_trace"]:
+                best = st
+        bins = eng.bins()
+        print(json.dumps({"config": name, "triangles": int(sum(len(x.tris) for x in t)), "rays": best["primary_rays"], "segments": best["segments"],
+                          "refracted": best["refracted"], "captured": best["captured"], "bins": len(bins), "ms_trace": round(best["ms_trace"], 3),
+                          "Mrays/s": round(best["primary_rays"] / best["ms_trace"] / 1e3, 1),
+                          "Msegments/s": round(best["segments"] / best["ms_trace"] / 1e3, 1),
+                          "waves": [(round(a, 3), b) for a, b in eng.wave_profile()]}))
+
+if __name__ == "__main__":
+    main()
