@@ -63,7 +63,7 @@ typedef struct rts_bvh_info {
     double   sah_cost;     /* sum of internal-node box areas of the current tree (m^2)                 */
     double   sah_at_build; /* the same when the topology was last built; refit rebuilds beyond 1.2 x   */
     uint32_t builds;       /* number of full builds so far                                             */
-    uint32_t _pad;
+    uint32_t builder;      /* topology of the current tree: 1 = Morton radix tree (LBVH), 2 = PLOC     */
 } rts_bvh_info;
 
 /* ---- life cycle (replaces rtContextCreate / rtContextDestroy, ray_tracer.cpp:532-534,1358) ---- */

@@ -81,6 +81,7 @@ extern "C" int rts_create(int device, rts_engine **out)
         return rts_fail(RTS_ERR_CUDA, "cudaStreamCreate failed");
     }
     e->stream = e->own_stream;
+    if (const char *b = getenv("RTS_BVH")) e->builder_forced = !strcmp(b, "ploc") ? 2 : (!strcmp(b, "lbvh") ? 1 : 0);
     if (const char *lm = getenv("RTS_LEAF_MAX")) { int v = atoi(lm); if (v >= 1 && v <= 8) e->leaf_max = v; }
     for (auto &ev : e->ev) cudaEventCreate(&ev);
     for (auto &ev : e->wave_ev) cudaEventCreate(&ev);
@@ -237,6 +238,7 @@ extern "C" int rts_scene_set_targets(rts_engine *e, const rts_target_mesh *targe
     if ((rc = upload(&e->d_poses, poses))) return rc;
     e->h_poses = poses;
     e->moving.assign(n_targets, 0);
+    e->builder = e->builder_forced;
     if ((rc = bvh_alloc(e))) return rc;
     if ((rc = bvh_build(e))) return rc;
     e->scene_ready = true;
@@ -310,7 +312,7 @@ extern "C" int rts_scene_bvh_info(rts_engine *e, rts_bvh_info *out)
     *out = e->bvh_info;
     out->sah_at_build = e->sah_at_build;
     out->builds = e->builds;
-    out->_pad = 0;
+    out->builder = (uint32_t)e->builder;
     return RTS_OK;
 }
 

@@ -16,6 +16,8 @@
 //                    triangles are collapsed into one leaf reference
 #include "engine.h"
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <vector>
 #include <math_constants.h>
 #include <cstring>
 #include <cmath>
@@ -174,6 +176,14 @@ __global__ void k_hierarchy(const unsigned long long *__restrict__ keys, int n, 
     parent[left >= 0 ? left : (n - 1) + ~left] = i;
     parent[right >= 0 ? right : (n - 1) + ~right] = i;
     if (i == 0) parent[0] = -1;
+}
+
+#include "ploc.cuh"
+
+__global__ void k_range_init(int2 *range, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) range[i] = make_int2(0x7fffffff, -1);
 }
 
 __global__ void k_leaf_of_tri(const uint32_t *__restrict__ order, uint32_t *__restrict__ leaf_of_tri, uint32_t n)
@@ -597,29 +607,148 @@ int bvh_read_scene_box(rts_engine *e)
     return RTS_OK;
 }
 
-int bvh_build(rts_engine *e)
+// Topology by PLOC (ploc.cuh) over the Morton-sorted triangles in d_order; leaves d_children / d_parent / d_range /
+// d_order in the layout of k_hierarchy.  Build-time only: temporaries are allocated and freed here, and each round
+// reads two counts back.
+static int build_ploc(rts_engine *e)
+{
+    const int n = (int)e->n_tris;
+    const unsigned bs = 256;
+    cudaStream_t st = e->stream;
+    int *ref[2] = {nullptr, nullptr}, *nn = nullptr, *keep = nullptr, *merged = nullptr, *keep_scan = nullptr, *merged_scan = nullptr;
+    int *count = nullptr, *pos_of0 = nullptr;
+    int32_t *parent_node = nullptr, *parent_leaf0 = nullptr;
+    uint32_t *order_tmp = nullptr;
+    PlocBox *box[2] = {nullptr, nullptr};
+    void *scan_tmp = nullptr;
+    size_t scan_bytes = 0;
+    int rc = RTS_OK;
+    int m = n, next_id = n - 2, cur = 0, rounds = 0;
+#define PLOC_CUDA(call)                                                                                         \
+    do {                                                                                                        \
+        cudaError_t _e = (call);                                                                                \
+        if (_e != cudaSuccess) {                                                                                \
+            rc = rts_fail(RTS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            goto done;                                                                                          \
+        }                                                                                                       \
+    } while (0)
+    for (int k = 0; k < 2; k++) {
+        PLOC_CUDA(cudaMalloc(&ref[k], sizeof(int) * (size_t)n));
+        PLOC_CUDA(cudaMalloc(&box[k], sizeof(PlocBox) * (size_t)n));
+    }
+    PLOC_CUDA(cudaMalloc(&nn, sizeof(int) * (size_t)n));
+    PLOC_CUDA(cudaMalloc(&keep, sizeof(int) * (size_t)n));
+    PLOC_CUDA(cudaMalloc(&merged, sizeof(int) * (size_t)n));
+    PLOC_CUDA(cudaMalloc(&keep_scan, sizeof(int) * (size_t)n));
+    PLOC_CUDA(cudaMalloc(&merged_scan, sizeof(int) * (size_t)n));
+    PLOC_CUDA(cudaMalloc(&count, sizeof(int) * (size_t)n));
+    PLOC_CUDA(cudaMalloc(&pos_of0, sizeof(int) * (size_t)n));
+    PLOC_CUDA(cudaMalloc(&parent_node, sizeof(int32_t) * (size_t)n));
+    PLOC_CUDA(cudaMalloc(&parent_leaf0, sizeof(int32_t) * (size_t)n));
+    PLOC_CUDA(cudaMalloc(&order_tmp, sizeof(uint32_t) * (size_t)n));
+    PLOC_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, keep, keep_scan, n, st));
+    PLOC_CUDA(cudaMalloc(&scan_tmp, std::max<size_t>(16, scan_bytes)));
+    PLOC_CUDA(cudaMemsetAsync(parent_node, 0xff, sizeof(int32_t) * (size_t)n, st));
+    PLOC_CUDA(cudaMemsetAsync(parent_leaf0, 0xff, sizeof(int32_t) * (size_t)n, st));
+    k_ploc_init<<<blocks_for(n, bs), bs, 0, st>>>(e->d_order, e->d_tri_box, n, ref[0], box[0]);
+    e->launches++;
+    while (m > 1) {
+        k_ploc_nn<<<blocks_for(m, bs), bs, 0, st>>>(box[cur], m, nn);
+        k_ploc_flags<<<blocks_for(m, bs), bs, 0, st>>>(nn, m, keep, merged);
+        PLOC_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, keep, keep_scan, m, st));
+        PLOC_CUDA(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, merged, merged_scan, m, st));
+        k_ploc_merge<<<blocks_for(m, bs), bs, 0, st>>>(nn, keep_scan, merged_scan, keep, merged, m, next_id, ref[cur], box[cur],
+                                                       ref[cur ^ 1], box[cur ^ 1], e->d_children, parent_node, parent_leaf0);
+        e->launches += 5;
+        int tail[4];
+        PLOC_CUDA(cudaMemcpyAsync(tail + 0, keep_scan + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        PLOC_CUDA(cudaMemcpyAsync(tail + 1, keep + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        PLOC_CUDA(cudaMemcpyAsync(tail + 2, merged_scan + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        PLOC_CUDA(cudaMemcpyAsync(tail + 3, merged + (m - 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+        PLOC_CUDA(cudaStreamSynchronize(st));
+        const int m2 = tail[0] + tail[1], k = tail[2] + tail[3];
+        if (k <= 0 || m2 != m - k) { rc = rts_fail(RTS_ERR_STATE, "PLOC round %d made no progress (m=%d, merges=%d)", rounds, m, k); goto done; }
+        next_id -= k;
+        m = m2;
+        cur ^= 1;
+        rounds++;
+    }
+    if (next_id != -1) { rc = rts_fail(RTS_ERR_STATE, "PLOC produced %d internal nodes for %d leaves", n - 2 - next_id, n); goto done; }
+    PLOC_CUDA(cudaMemsetAsync(e->d_fit_flags, 0, sizeof(uint32_t) * (size_t)n, st));
+    k_ploc_counts<<<blocks_for(n, bs), bs, 0, st>>>(e->d_children, parent_node, parent_leaf0, n, e->d_fit_flags, count);
+    k_ploc_positions<<<blocks_for(n, bs), bs, 0, st>>>(e->d_children, parent_node, parent_leaf0, count, n, e->d_order, order_tmp, pos_of0);
+    k_range_init<<<blocks_for(n, bs), bs, 0, st>>>(e->d_range, n);
+    k_ploc_finish<<<blocks_for(n, bs), bs, 0, st>>>(e->d_children, parent_node, parent_leaf0, pos_of0, n, e->d_parent, e->d_range);
+    e->launches += 4;
+    PLOC_CUDA(cudaGetLastError());
+    PLOC_CUDA(cudaMemcpyAsync(e->d_order, order_tmp, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    PLOC_CUDA(cudaStreamSynchronize(st));
+done:
+#undef PLOC_CUDA
+    for (int k = 0; k < 2; k++) { cudaFree(ref[k]); cudaFree(box[k]); }
+    cudaFree(nn); cudaFree(keep); cudaFree(merged); cudaFree(keep_scan); cudaFree(merged_scan); cudaFree(count); cudaFree(pos_of0);
+    cudaFree(parent_node); cudaFree(parent_leaf0); cudaFree(order_tmp); cudaFree(scan_tmp);
+    return rc;
+}
+
+// One topology build at the current world geometry + fit + pack; returns the tree's SAH cost (sum of the
+// internal-node box areas).  Synchronises.
+static int build_once(rts_engine *e, bool ploc, double *sah_out)
 {
     const unsigned bs = 256;
     const int n = (int)e->n_tris;
-    e->partial_ready = false;
-    e->sah_pending = false;
-    cudaEventRecord(e->ev[4], e->stream);
-    int rc = bvh_update_world(e);
-    if (rc) return rc;
+    int rc;
     if (n > 0) {
         { k_morton<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_tri_box, (const unsigned *)e->d_scene_box, e->d_morton,
                                                          e->d_order_in, n); e->launches++; }
         size_t bytes = e->cub_temp_bytes;
         RTS_CUDA(cub::DeviceRadixSort::SortPairs(e->d_cub_temp, bytes, e->d_morton, e->d_morton_sorted, e->d_order_in,
                                                  e->d_order, n, 0, 63, e->stream));
+        if (n >= 2) {
+            if (ploc) {
+                if ((rc = build_ploc(e))) return rc;
+            } else {
+                k_hierarchy<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_morton_sorted, n, e->d_children, e->d_range, e->d_parent);
+                e->launches++;
+            }
+        }
         { k_leaf_of_tri<<<blocks_for(n, bs), bs, 0, e->stream>>>(e->d_order, e->d_leaf_of_tri, n); e->launches++; }
-        if (n >= 2)
-            { k_hierarchy<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_morton_sorted, n, e->d_children, e->d_range,
-                                                                    e->d_parent); e->launches++; }
         RTS_CUDA(cudaGetLastError());
     }
-    rc = fit_and_pack(e);
+    if ((rc = fit_and_pack(e))) return rc;
+    double sah = 0;
+    if (n >= 2) RTS_CUDA(cudaMemcpyAsync(&sah, e->d_sah, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    RTS_CUDA(cudaStreamSynchronize(e->stream));
+    *sah_out = sah;
+    return RTS_OK;
+}
+
+// Full build at the current poses.  Two topology builders feed the same arrays: the Morton radix tree (k_hierarchy,
+// < 1 ms per million triangles) and PLOC (ploc.cuh, tens of ms).  Neither wins everywhere — the radix tree is the
+// better one on regular height fields, PLOC by far on irregular meshes with mixed triangle sizes (ship on a sea
+// plane: 7x lower SAH cost) — so the first build of a scene makes both and keeps the one with the lower SAH cost
+// (RTS_BVH=lbvh|ploc forces one); later rebuilds (SAH drift, rts_scene_rebuild) reuse that choice.
+int bvh_build(rts_engine *e)
+{
+    const int n = (int)e->n_tris;
+    e->partial_ready = false;
+    e->sah_pending = false;
+    cudaEventRecord(e->ev[4], e->stream);
+    int rc = bvh_update_world(e);
     if (rc) return rc;
+    double sah = 0;
+    if (e->builder == 0 && n >= 64) {            // undecided: try both
+        double sah_l = 0, sah_p = 0;
+        if ((rc = build_once(e, false, &sah_l))) return rc;
+        if ((rc = build_once(e, true, &sah_p))) return rc;
+        if (sah_p < 0.97 * sah_l) { e->builder = 2; sah = sah_p; }
+        else {
+            e->builder = 1;
+            if ((rc = build_once(e, false, &sah))) return rc;
+        }
+    } else {
+        if ((rc = build_once(e, e->builder == 2, &sah))) return rc;
+    }
     cudaEventRecord(e->ev[5], e->stream);
     RTS_CUDA(cudaStreamSynchronize(e->stream));
     float ms = 0;
@@ -631,9 +760,8 @@ int bvh_build(rts_engine *e)
     bi.root_is_leaf = e->root_ref < 0;
     bi.max_leaf = e->leaf_max;
     bi.ms_build = ms;
-    double sah = 0;
-    if (n >= 2) RTS_CUDA(cudaMemcpy(&sah, e->d_sah, sizeof(double), cudaMemcpyDeviceToHost));
     bi.sah_cost = sah;
+    bi.builder = (uint32_t)e->builder;
     e->sah_at_build = sah;
     e->builds++;
     e->refits_since_build = 0;
@@ -680,7 +808,10 @@ int bvh_refit(rts_engine *e)
         if (e->refits_since_build < 2) {
             e->refits_since_build++;
             collect_sah(e, true);
-            if (e->sah_at_build > 0 && e->bvh_info.sah_cost > RTS_REBUILD_RATIO * e->sah_at_build) return bvh_build(e);
+            if (e->sah_at_build > 0 && e->bvh_info.sah_cost > RTS_REBUILD_RATIO * e->sah_at_build) {
+                e->builder = e->builder_forced;   // the geometry the builder was chosen on was not representative: choose again
+                return bvh_build(e);
+            }
         }
     }
     return RTS_OK;

@@ -195,6 +195,8 @@ struct rts_engine {
     size_t cub_temp_bytes = 0;
     int32_t root_ref = 0;
     int leaf_max = RTS_LEAF_MAX;       // 1..8; RTS_LEAF_MAX env var overrides (tuning)
+    int builder_forced = 0;            // RTS_BVH=lbvh (1) | ploc (2); 0 = choose per scene by SAH cost
+    int builder = 0;                   // the scene's topology builder: 0 undecided, 1 Morton radix tree, 2 PLOC (ploc.cuh)
     rts_bvh_info bvh_info = {};
     float *d_scene_abs = nullptr;      // [3] max |coordinate| of the scene box per axis, refreshed by every update
     // partial refit: only the targets that have moved since the scene was committed

@@ -41,7 +41,7 @@ class RtsSizes(C.Structure):
 class RtsBvhInfo(C.Structure):
     _fields_ = [("n_tris", C.c_uint32), ("n_nodes", C.c_uint32), ("root_is_leaf", C.c_uint32), ("max_leaf", C.c_uint32),
                 ("scene_lo", C.c_float * 3), ("scene_hi", C.c_float * 3), ("ms_build", C.c_float), ("ms_refit", C.c_float),
-                ("sah_cost", C.c_double), ("sah_at_build", C.c_double), ("builds", C.c_uint32), ("_pad", C.c_uint32)]
+                ("sah_cost", C.c_double), ("sah_at_build", C.c_double), ("builds", C.c_uint32), ("builder", C.c_uint32)]
 
 
 #: every symbol include/rts_b200.h declares (tests/test_abi.py checks the library exports them all)

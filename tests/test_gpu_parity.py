@@ -379,3 +379,33 @@ def test_C5_multistatic_eight_shards_and_batched_launch(engine):
     assert st_big["primary_rays"] == 2 << 24 and seg == st_big["segments"]
     assert np.array_equal(hsum[:, 0], whole[0][:, 0]) and np.array_equal(hmin, whole[1])
     assert np.allclose(hsum, whole[0], rtol=1e-11, atol=0)
+
+
+def test_builder_choice_and_ploc_parity(monkeypatch):
+    """Two topology builders (Morton radix tree, PLOC) feed the same refit / traversal code; a scene keeps the one with
+    the lower SAH cost.  Forced PLOC reproduces the oracle bit for bit, including moving targets with partial refit."""
+    with L.Engine(0) as eng:                                     # automatic choice
+        targets, spec = scenes.ship(n=64, hull_res=64)
+        eng.set_targets(targets)
+        assert eng.bvh_info().builder == 2                       # irregular mesh + huge sea triangles: PLOC
+        ms = scenes.terrain_scene(n=64, cells_x=200, cells_y=100, movers=0)
+        eng.set_targets(ms.base)
+        assert eng.bvh_info().builder == 1                       # regular height field: the radix tree
+    monkeypatch.setenv("RTS_BVH", "ploc")
+    with L.Engine(0) as eng:
+        for name in ("slab", "ship_small", "spheres_interp"):
+            targets, spec = SMALL[name]()
+            orc = O.trace(targets, spec, use_bvh=False)
+            recs, gbins, st = parity.run_gpu_records(eng, targets, spec)
+            assert eng.bvh_info().builder == 2 and eng.check_bvh() == 0
+            parity.assert_records_equal(parity.compare_records(recs, orc, spec, name + "/ploc"))
+        ms = scenes.terrain_scene(n=128, cells_x=80, cells_y=40, movers=8, n_rx=2)
+        eng.set_targets(ms.base)
+        for pulse in (0, 3, 9):
+            eng.set_poses(*ms.poses(pulse))
+            spec = ms.spec_for(pulse)
+            eng.trace(spec, L.RTS_OUT_RECORDS | L.RTS_OUT_BINS)
+            recs = eng.records()
+            assert eng.check_bvh() == 0 and eng.bvh_info().builder == 2
+            orc = O.trace(ms.world_targets(pulse), spec, use_bvh=True)
+            parity.assert_records_equal(parity.compare_records(recs, orc, spec, f"ploc/pulse{pulse}"))
