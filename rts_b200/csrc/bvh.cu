@@ -180,12 +180,6 @@ __global__ void k_hierarchy(const unsigned long long *__restrict__ keys, int n, 
 
 #include "ploc.cuh"
 
-__global__ void k_range_init(int2 *range, int n)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) range[i] = make_int2(0x7fffffff, -1);
-}
-
 __global__ void k_leaf_of_tri(const uint32_t *__restrict__ order, uint32_t *__restrict__ leaf_of_tri, uint32_t n)
 {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -677,8 +671,8 @@ static int build_ploc(rts_engine *e)
     PLOC_CUDA(cudaMemsetAsync(e->d_fit_flags, 0, sizeof(uint32_t) * (size_t)n, st));
     k_ploc_counts<<<blocks_for(n, bs), bs, 0, st>>>(e->d_children, parent_node, parent_leaf0, n, e->d_fit_flags, count);
     k_ploc_positions<<<blocks_for(n, bs), bs, 0, st>>>(e->d_children, parent_node, parent_leaf0, count, n, e->d_order, order_tmp, pos_of0);
-    k_range_init<<<blocks_for(n, bs), bs, 0, st>>>(e->d_range, n);
-    k_ploc_finish<<<blocks_for(n, bs), bs, 0, st>>>(e->d_children, parent_node, parent_leaf0, pos_of0, n, e->d_parent, e->d_range);
+    k_ploc_ranges<<<blocks_for(n, bs), bs, 0, st>>>(e->d_children, pos_of0, count, n, e->d_range);
+    k_ploc_finish<<<blocks_for(n, bs), bs, 0, st>>>(e->d_children, parent_node, parent_leaf0, pos_of0, n, e->d_parent);
     e->launches += 4;
     PLOC_CUDA(cudaGetLastError());
     PLOC_CUDA(cudaMemcpyAsync(e->d_order, order_tmp, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToDevice, st));

@@ -132,10 +132,23 @@ __global__ void k_ploc_positions(const int2 *__restrict__ children, const int32_
     order[pos] = order0[p0];
 }
 
-// relabel leaf references to final positions, fill parent[] and range[] in the layout k_hierarchy produces
+// position range of every internal node: its leftmost leaf's position and its leaf count (leaf references are
+// still initial Morton positions here)
+__global__ void k_ploc_ranges(const int2 *__restrict__ children, const int *__restrict__ pos_of0, const int *__restrict__ count,
+                              int n, int2 *__restrict__ range)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    int ref = i;
+    while (ref >= 0) ref = children[ref].x;
+    const int lo = pos_of0[~ref];
+    range[i] = make_int2(lo, lo + count[i] - 1);
+}
+
+// relabel leaf references to final positions and fill parent[] in the layout k_hierarchy produces
 __global__ void k_ploc_finish(int2 *__restrict__ children, const int32_t *__restrict__ parent_node,
                               const int32_t *__restrict__ parent_leaf0, const int *__restrict__ pos_of0, int n,
-                              int32_t *__restrict__ parent, int2 *__restrict__ range)
+                              int32_t *__restrict__ parent)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n - 1) {
@@ -145,15 +158,5 @@ __global__ void k_ploc_finish(int2 *__restrict__ children, const int32_t *__rest
         children[i] = ch;
         parent[i] = parent_node[i];
     }
-    if (i < n) {
-        const int pos = pos_of0[i];
-        parent[(n - 1) + pos] = parent_leaf0[i];
-        // leaves widen the position range of all their ancestors
-        int cur = parent_leaf0[i];
-        while (cur >= 0) {
-            atomicMin(&range[cur].x, pos);
-            atomicMax(&range[cur].y, pos);
-            cur = parent_node[cur];
-        }
-    }
+    if (i < n) parent[(n - 1) + pos_of0[i]] = parent_leaf0[i];
 }
