@@ -409,3 +409,44 @@ def test_builder_choice_and_ploc_parity(monkeypatch):
             assert eng.check_bvh() == 0 and eng.bvh_info().builder == 2
             orc = O.trace(ms.world_targets(pulse), spec, use_bvh=True)
             parity.assert_records_equal(parity.compare_records(recs, orc, spec, f"ploc/pulse{pulse}"))
+
+
+def _shifted(targets, spec, shift):
+    from rts_b200.abi import Target
+    shift = np.asarray(shift, dtype=np.float64)
+    t2 = [Target(t.verts + shift, t.tris, t.normals, t.refl_coeff, t.refr_index) for t in targets]
+    spec.tx_origin = tuple(np.asarray(spec.tx_origin) + shift)
+    for r in spec.rx:
+        for a in range(3):
+            r.centre[a] += float(shift[a])
+    return t2, spec
+
+
+@pytest.mark.parametrize("name", ["earth_scale", "degenerate", "axis_parallel"])
+def test_conservative_traversal_edge_cases(engine, name):
+    """The fp32 slab test must never prune a box the fp64 triangle test could hit: coordinates at Earth-radius scale
+    (the reference hard-codes an Earth sphere, ray_tracer.cu:447, so such scenes are legal; fp32 ulp there is 0.5 m),
+    zero-area triangles (n.d = 0 -> NaN, rejected by the comparisons, triangle_mesh.cu:124-136), and rays with
+    exactly-zero direction components (odd grid: the centre ray runs along the boresight)."""
+    if name == "earth_scale":
+        targets, spec = scenes.trihedral(n=120)
+        targets, spec = _shifted(targets, spec, (6.3e6, 1.0e5, -2.0e5))
+    elif name == "degenerate":
+        from rts_b200.abi import Target
+        targets, spec = scenes.slab(n=64)
+        t = targets[0]
+        v = np.vstack([t.verts, [[49.0, 0.0, 0.0], [49.0, 1.0, 0.0], [49.0, 2.0, 0.0], [49.5, 0.3, 0.2]]])
+        nv = len(t.verts)
+        tris = np.vstack([t.tris, [[nv, nv + 1, nv + 2], [nv + 3, nv + 3, nv + 3]]]).astype(np.uint32)   # collinear, and a point
+        nrm = np.vstack([t.normals, [[1.0, 0, 0], [1.0, 0, 0]]])
+        targets = [Target(v, tris, nrm, t.refl_coeff, t.refr_index)]
+    else:
+        targets, spec = scenes.flat_plate(n=65)
+        spec.max_refl = 2
+    orc = O.trace(targets, spec, use_bvh=False)
+    recs, gbins, st = parity.run_gpu_records(engine, targets, spec)
+    cmp = parity.compare_records(recs, orc, spec, name)
+    parity.assert_records_equal(cmp)
+    for k in ("segments", "hits", "shaded_hits"):
+        assert st[k] == orc["stats"][k], k
+    assert st["hits"] > 0 and engine.check_bvh() == 0
