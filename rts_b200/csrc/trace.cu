@@ -46,31 +46,33 @@ __device__ __forceinline__ uint32_t m_make(uint32_t refl, uint32_t refr, uint32_
 // The state is loaded in two parts: what traversal needs (origin, direction, flags) before it, the
 // rest (length, power, Doppler, first hit, indices, path key) only after it — that keeps ~20 registers
 // free during the traversal loop (occupancy is the lever: see profiles/).
+// Queue columns are streamed once per wave: evict-first loads and stores (ld.global.cs / st.global.cs) keep them from
+// pushing the BVH nodes and triangle records out of L2.
 __device__ __forceinline__ void load_ray_geom(const RayQueue &q, unsigned long long i, Ray &r)
 {
-    r.ox = q.f[F_OX][i]; r.oy = q.f[F_OY][i]; r.oz = q.f[F_OZ][i];
-    r.dx = q.f[F_DX][i]; r.dy = q.f[F_DY][i]; r.dz = q.f[F_DZ][i];
-    r.meta = q.meta[i];
+    r.ox = __ldcs(q.f[F_OX] + i); r.oy = __ldcs(q.f[F_OY] + i); r.oz = __ldcs(q.f[F_OZ] + i);
+    r.dx = __ldcs(q.f[F_DX] + i); r.dy = __ldcs(q.f[F_DY] + i); r.dz = __ldcs(q.f[F_DZ] + i);
+    r.meta = __ldcs(q.meta + i);
 }
 // The first hit point is only ever reported through the records, the refractive indices only matter with a
 // refraction budget: those five columns are skipped otherwise (88 instead of 128 bytes per queued ray).
 __device__ __forceinline__ void load_ray_rest(const RayQueue &q, unsigned long long i, Ray &r, bool records, bool refr)
 {
-    r.len = q.f[F_LEN][i]; r.pw = q.f[F_PW][i]; r.dop = q.f[F_DOP][i];
-    if (records) { r.fx = q.f[F_FX][i]; r.fy = q.f[F_FY][i]; r.fz = q.f[F_FZ][i]; }
+    r.len = __ldcs(q.f[F_LEN] + i); r.pw = __ldcs(q.f[F_PW] + i); r.dop = __ldcs(q.f[F_DOP] + i);
+    if (records) { r.fx = __ldcs(q.f[F_FX] + i); r.fy = __ldcs(q.f[F_FY] + i); r.fz = __ldcs(q.f[F_FZ] + i); }
     else { r.fx = 0; r.fy = 0; r.fz = 0; }
-    if (refr) { r.n0 = q.f[F_N0][i]; r.n1 = q.f[F_N1][i]; }
+    if (refr) { r.n0 = __ldcs(q.f[F_N0] + i); r.n1 = __ldcs(q.f[F_N1] + i); }
     else { r.n0 = 1; r.n1 = 1; }
-    r.key = q.key[i]; r.ray = q.ray[i];
+    r.key = __ldcs(q.key + i); r.ray = __ldcs(q.ray + i);
 }
 __device__ __forceinline__ void store_ray(const RayQueue &q, unsigned long long i, const Ray &r, bool records, bool refr)
 {
-    q.f[F_OX][i] = r.ox; q.f[F_OY][i] = r.oy; q.f[F_OZ][i] = r.oz;
-    q.f[F_DX][i] = r.dx; q.f[F_DY][i] = r.dy; q.f[F_DZ][i] = r.dz;
-    q.f[F_LEN][i] = r.len; q.f[F_PW][i] = r.pw; q.f[F_DOP][i] = r.dop;
-    if (records) { q.f[F_FX][i] = r.fx; q.f[F_FY][i] = r.fy; q.f[F_FZ][i] = r.fz; }
-    if (refr) { q.f[F_N0][i] = r.n0; q.f[F_N1][i] = r.n1; }
-    q.key[i] = r.key; q.ray[i] = r.ray; q.meta[i] = r.meta;
+    __stcs(q.f[F_OX] + i, r.ox); __stcs(q.f[F_OY] + i, r.oy); __stcs(q.f[F_OZ] + i, r.oz);
+    __stcs(q.f[F_DX] + i, r.dx); __stcs(q.f[F_DY] + i, r.dy); __stcs(q.f[F_DZ] + i, r.dz);
+    __stcs(q.f[F_LEN] + i, r.len); __stcs(q.f[F_PW] + i, r.pw); __stcs(q.f[F_DOP] + i, r.dop);
+    if (records) { __stcs(q.f[F_FX] + i, r.fx); __stcs(q.f[F_FY] + i, r.fy); __stcs(q.f[F_FZ] + i, r.fz); }
+    if (refr) { __stcs(q.f[F_N0] + i, r.n0); __stcs(q.f[F_N1] + i, r.n1); }
+    __stcs(q.key + i, r.key); __stcs(q.ray + i, r.ray); __stcs(q.meta + i, r.meta);
 }
 
 // Append one ray per calling thread to the next wave's queue: one atomic per converged group.
