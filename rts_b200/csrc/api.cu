@@ -523,9 +523,9 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
         int rc = trace_alloc_queues(e, cap);
         if (rc) return rc;
     }
-    // primary visibility by projection (opt-in, RTS_RASTER=1: measured equal to the BVH primary wave on the 1M-triangle
-    // workload): launches whose rays form one image (nx == 1) with a forward image plane
-    const bool use_raster = p->nx == 1 && !P.single_ray && e->n_tris > 0 && !(flags & RTS_COUNT_NODES) && getenv("RTS_RASTER") &&
+    // primary visibility by projection (raster.cuh; RTS_NO_RASTER=1 turns it off): launches whose rays form one image
+    // (nx == 1) with a forward image plane; node/triangle counting needs the traversal
+    const bool use_raster = p->nx == 1 && !P.single_ray && e->n_tris > 0 && !(flags & RTS_COUNT_NODES) && !getenv("RTS_NO_RASTER") &&
                             P.beamStart[0] > 1e-6 && (p->ny == 1 || P.slope[1] != 0.0) && (p->nz == 1 || P.slope[2] != 0.0) &&
                             n_primary_total > 0;
     if (use_raster) {

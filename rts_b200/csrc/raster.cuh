@@ -8,12 +8,13 @@
 // evaluates primary_direction once per ray) and the same operations in the same order, so t, beta and gamma are
 // bit-identical.  The closest hit is an atomicMin over (fp32 t bits << 32 | triangle id): smallest fp32 t, ties to the
 // lowest global triangle id — the rule of traverse().  The footprint only has to be conservative: projection is done
-// in fp64 (errors ~1e-10 pixel) and padded by 1.5 pixels.
+// in fp64 (errors ~1e-9 pixel); the pixel bounds are padded by 1e-3 pixel, the fp32 edge functions by 0.05 pixel plus
+// their evaluation error.
 //
-// STATUS: opt-in (environment variable RTS_RASTER=1).  Bit-identical results to the BVH primary wave on every parity
-// test, but on the 1M-triangle benchmark it only ties it (1.70 ms vs 1.66 ms per 16.8M-ray pulse: footprint walk
-// 0.91 ms at 46 % SIMT efficiency, direction pass 0.18 ms, shading pass 0.60 ms bound by the latency of the scattered
-// triangle-record fetch), so the BVH wave stays the default.
+// STATUS: the default primary wave for launches whose rays form one image (nx == 1; RTS_NO_RASTER=1 switches back to
+// BVH traversal, which also serves cubic launches).  Bit-identical results on every parity test.  On the 1M-triangle
+// benchmark the primary wave takes 1.11 ms against 1.60 ms by traversal (direction pass 0.18 ms, footprints 0.03 +
+// 0.37 ms for 30 M candidates = 1.8 per ray, resolve + shading pass 0.5 ms).
 //
 // Work distribution: one thread per triangle walks small footprints (k_raster_small); large ones are cut into row
 // chunks taken by warps (k_raster_big).  A device-side guard turns the whole path off for launches where the summed
@@ -121,8 +122,11 @@ __device__ __forceinline__ bool tri_footprint(const WaveParams &P, unsigned pos,
     }
     if (!(umin <= umax) || !(wmin <= wmax)) return false;   // NaN guard
     const double big = 2.0e9;
-    int y0 = P.ny > 1 ? (int)clampd(floor(umin) - 1.0, -big, big) : 0, y1 = P.ny > 1 ? (int)clampd(ceil(umax) + 1.0, -big, big) : 0;
-    int z0 = P.nz > 1 ? (int)clampd(floor(wmin) - 1.0, -big, big) : 0, z1 = P.nz > 1 ? (int)clampd(ceil(wmax) + 1.0, -big, big) : 0;
+    // a ray passes exactly through its pixel centre (integer u, w); the projection is good to ~1e-9 pixel, so the
+    // integer pixels inside [min - pad, max + pad] are all that can be hit
+    const double pad = 1e-3;
+    int y0 = P.ny > 1 ? (int)clampd(ceil(umin - pad), -big, big) : 0, y1 = P.ny > 1 ? (int)clampd(floor(umax + pad), -big, big) : 0;
+    int z0 = P.nz > 1 ? (int)clampd(ceil(wmin - pad), -big, big) : 0, z1 = P.nz > 1 ? (int)clampd(floor(wmax + pad), -big, big) : 0;
     y0 = max(y0, 0); y1 = min(y1, (int)P.ny - 1); z0 = max(z0, 0); z1 = min(z1, (int)P.nz - 1);
     // rows of this batch only (a batch is a contiguous range of shard-local indices, i.e. of rows up to one partial row)
     {
@@ -151,7 +155,8 @@ __device__ __forceinline__ bool tri_footprint(const WaveParams &P, unsigned pos,
             for (int k = 0; k < 3; k++) {
                 const int a = k, b = (k + 1) % 3;
                 const double A = -(ys[b] - ys[a]) * sg, B = (xs[b] - xs[a]) * sg;
-                const double C = -(A * xs[a] + B * ys[a]) + 1.5 * (fabs(A) + fabs(B)) + 1e-3 * (fabs(A * xs[a]) + fabs(B * ys[a]));
+                // slack: 0.05 pixel along the edge normal plus the fp32 evaluation error of the edge function
+                const double C = -(A * xs[a] + B * ys[a]) + 0.05 * (fabs(A) + fabs(B)) + 1e-5 * (fabs(A * xs[a]) + fabs(B * ys[a]) + (fabs(A) + fabs(B)) * 64.0);
                 F.ea[k] = (float)A; F.eb[k] = (float)B; F.ec[k] = (float)C;
             }
             F.use2d = true;
@@ -263,36 +268,52 @@ __global__ void k_raster_big(const __grid_constant__ WaveParams P)
     }
 }
 
-// Pass 3: the primary wave without traversal — the closest hit comes from the hit buffer.
+// Pass 3a: winner's triangle id -> leaf position, in place, so that the shading pass below has one dependent
+// (scattered) fetch per ray — the triangle record — instead of three.
+__global__ void k_raster_resolve(const __grid_constant__ WaveParams P)
+{
+    if (!raster_on(P)) return;
+    for (unsigned long long rel = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; rel < P.n_primary;
+         rel += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long hit = P.hits[rel];
+        if (hit != ~0ull) P.hits[rel] = (hit & 0xffffffff00000000ull) | (unsigned long long)P.leaf_of_tri[(uint32_t)hit];
+    }
+}
+
+// Pass 3b: the primary wave without traversal — the closest hit comes from the hit buffer.
 template <bool RECORDS>
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_primary_shade(const __grid_constant__ WaveParams P)
 {
     if (!raster_on(P)) return;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned n_in = (unsigned)P.n_primary;
-    unsigned *work = reinterpret_cast<unsigned *>(P.work_counter);
     Local L = {0, 0, 0, 0, 0};
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(P.wave_segs + P.wave_index, (unsigned long long)n_in);
         atomicAdd(&P.counters->segments, (unsigned long long)n_in);
     }
-    for (;;) {
-        unsigned base = 0;
-        if (lane == 0) base = atomicAdd(work, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= n_in) break;
-        const unsigned rel = base + lane;
-        if (rel >= n_in) continue;
+    // Every ray costs about the same here (no traversal), so the rays are dealt out statically; the next ray's
+    // hit word and direction are fetched, and its triangle record prefetched, while the current one is shaded.
+    const unsigned stride = gridDim.x * blockDim.x;
+    unsigned rel = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long hit_n = ~0ull;
+    double dnx = 0, dny = 0, dnz = 0;
+    if (rel < n_in) { hit_n = __ldcs(P.hits + rel); dnx = __ldcs(P.dirs[0] + rel); dny = __ldcs(P.dirs[1] + rel); dnz = __ldcs(P.dirs[2] + rel); }
+    while (rel < n_in) {
+        const unsigned long long hit = hit_n;
         Ray r;
         r.ox = P.origin[0]; r.oy = P.origin[1]; r.oz = P.origin[2];
-        r.dx = P.dirs[0][rel]; r.dy = P.dirs[1][rel]; r.dz = P.dirs[2][rel];
+        r.dx = dnx; r.dy = dny; r.dz = dnz;
+        const unsigned nrel = rel + stride;
+        if (nrel < n_in) {
+            hit_n = __ldcs(P.hits + nrel); dnx = __ldcs(P.dirs[0] + nrel); dny = __ldcs(P.dirs[1] + nrel); dnz = __ldcs(P.dirs[2] + nrel);
+        }
         r.meta = m_make(0, 0, 0, false, true, 0);
         r.len = 0; r.pw = 0; r.dop = 0; r.fx = 0; r.fy = 0; r.fz = 0; r.n0 = 1; r.n1 = 1;
         r.key = 0; r.ray = (uint32_t)(P.ray_begin + (P.batch_base + rel) * P.ray_stride);
-        const unsigned long long hit = P.hits[rel];
         if (hit != ~0ull) {
             HitRec h;
-            h.id = (uint32_t)hit; h.t = __uint_as_float((unsigned)(hit >> 32)); h.pos = (int)P.leaf_of_tri[h.id];
+            h.pos = (int)(uint32_t)hit; h.t = __uint_as_float((unsigned)(hit >> 32)); h.id = 0;   // shade() takes the id from the record
             L.a += C_HIT;
             shade<RECORDS>(P, r, h, L, false);
         } else {
@@ -302,6 +323,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_primar
                 if (P.flags & RTS_OUT_BINS) accumulate_bin(P, r, received);
             }
         }
+        rel = nrel;
     }
     unsigned long long *c = reinterpret_cast<unsigned long long *>(P.counters);
     const unsigned f[7] = {(unsigned)(L.a & 0x1fffff), (unsigned)((L.a >> 21) & 0x1fffff), (unsigned)(L.a >> 42),

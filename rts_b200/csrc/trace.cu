@@ -804,10 +804,11 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records)
     k_raster_setup<<<tri_blocks, bs, 0, st>>>(p);
     k_raster_small<<<tri_blocks, bs, 0, st>>>(p);
     k_raster_big<<<e->num_sms * 8, bs, 0, st>>>(p);
+    k_raster_resolve<<<e->num_sms * 16, 256, 0, st>>>(p);
     if (records) k_primary_shade<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     else k_primary_shade<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     RTS_CUDA(cudaGetLastError());
-    e->launches += 5;
+    e->launches += 6;
     return RTS_OK;
 }
 

@@ -303,8 +303,9 @@ def test_targets_that_start_moving_later_and_drift_rebuild(engine):
 
 @pytest.mark.parametrize("name", ["plate", "trihedral", "slab", "terrain"])
 def test_projected_primary_wave_is_bit_identical(engine, name, monkeypatch):
-    """RTS_RASTER=1 (rts_b200/csrc/raster.cuh): primary visibility by projecting the triangles into the launch grid
-    instead of walking the BVH per ray — same closest hits, hence the same records bit for bit, also for a shard."""
+    """rts_b200/csrc/raster.cuh (default for nx == 1 launches; RTS_NO_RASTER=1 switches it off): primary visibility by
+    projecting the triangles into the launch grid instead of walking the BVH per ray — same closest hits, hence the
+    same records bit for bit, also for a shard."""
     if name == "plate":
         targets, spec = scenes.flat_plate(n=256)
     elif name == "trihedral":
@@ -317,10 +318,10 @@ def test_projected_primary_wave_is_bit_identical(engine, name, monkeypatch):
     engine.set_targets(targets)
     for shard in ((0, 0, 0), (1, 0, 4)):
         spec.ray_begin, spec.ray_count, spec.ray_stride = shard
-        monkeypatch.delenv("RTS_RASTER", raising=False)
+        monkeypatch.setenv("RTS_NO_RASTER", "1")
         st0 = engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_OUT_BINS)
         a, bins_a = engine.records(), engine.bins()
-        monkeypatch.setenv("RTS_RASTER", "1")
+        monkeypatch.delenv("RTS_NO_RASTER", raising=False)
         st1 = engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_OUT_BINS)
         b, bins_b = engine.records(), engine.bins()
         for k in ("segments", "hits", "shaded_hits", "captured", "edge_rays"):

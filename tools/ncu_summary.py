@@ -17,7 +17,7 @@ for r in rows[1:]:
     a[1] += float(r[vi].replace(",", ""))
 tot = sum(a[1] for a in agg.values())
 lines = [f"# ncu launch list ({tag}): python bench.py --steps 2 --warmup 1 --no-cpu-baseline",
-         "# ncu --metrics gpu__time_duration.sum --clock-control none -c 2000  (cold-cache, serialised: compare SHARES)",
+         "# ncu --metrics gpu__time_duration.sum --clock-control none -c 2500  (cold-cache, serialised: compare SHARES)",
          f"# total {tot / 1e6:.3f} ms over {sum(a[0] for a in agg.values())} launches", "ms,launches,share_pct,kernel"]
 for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
     lines.append(f"{t / 1e6:.4f},{n},{100 * t / tot:.2f},\"{k[:120]}\"")
@@ -56,8 +56,11 @@ def gb(s):
     v, u = s.split()
     return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
 prim = [d for d in summ if "k_wave<1, 0" in d["Kernel Name"]]
+later = [d for d in summ if "k_wave<0, 0, 0, 0" in d["Kernel Name"]]
+out = {"source": f"profiles/{tag}_k_wave_ncu_full.json (ncu --set full, one launch each)"}
 if prim:
-    t = gb(prim[0]["dram__bytes_read.sum"]) + gb(prim[0]["dram__bytes_write.sum"])
-    json.dump({"k_wave_primary_dram_bytes_per_launch": t, "source": f"profiles/{tag}_k_wave_ncu_full.json (ncu --set full, one launch)"},
-              open(os.path.join(out_dir, "r01_traffic.json"), "w"))
-    print("primary wave DRAM traffic per launch: %.3f GB" % (t / 1e9))
+    out["k_wave_primary_dram_bytes_per_launch"] = gb(prim[0]["dram__bytes_read.sum"]) + gb(prim[0]["dram__bytes_write.sum"])
+if later:
+    out["k_wave_later_dram_bytes_per_launch"] = gb(later[0]["dram__bytes_read.sum"]) + gb(later[0]["dram__bytes_write.sum"])
+json.dump(out, open(os.path.join(out_dir, "r01_traffic.json"), "w"))
+print(out)

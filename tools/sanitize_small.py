@@ -17,9 +17,9 @@ def main():
         rr = eng.received()
         if len(rr[0]):
             eng.aggregate(rr[0], rr[1], s.cspeed, s.carrier, ray_total=s.ray_total)
-        os.environ["RTS_RASTER"] = "1"
+        os.environ["RTS_NO_RASTER"] = "1"
         eng.trace(s, L.RTS_OUT_BINS)
-        del os.environ["RTS_RASTER"]
+        del os.environ["RTS_NO_RASTER"]
         print(name, st["segments"], st["hits"], len(bins), len(resp), len(rr[0]))
     ms = scenes.terrain_scene(n=96, cells_x=64, cells_y=40, movers=6, n_rx=2)     # 5120 + mover triangles: partial refit path
     eng.set_targets(ms.base)
@@ -30,7 +30,6 @@ def main():
     eng.rebuild()
     sp = ms.spec_for(3)
     sp.ray_begin, sp.ray_stride = 1, 3
-    os.environ["RTS_RASTER"] = "1"
     print("shard", eng.trace(sp, L.RTS_OUT_BINS)["segments"])
     eng.close()
 
