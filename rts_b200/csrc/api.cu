@@ -528,9 +528,15 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     const bool use_raster = p->nx == 1 && !P.single_ray && e->n_tris > 0 && !(flags & RTS_COUNT_NODES) && !getenv("RTS_NO_RASTER") &&
                             P.beamStart[0] > 1e-6 && (p->ny == 1 || P.slope[1] != 0.0) && (p->nz == 1 || P.slope[2] != 0.0) &&
                             n_primary_total > 0;
+    P.lat_w = 0; P.lat_c0 = 0; P.lat_g0 = 0;
     if (use_raster) {
         int rc = trace_raster_alloc(e, batch);
         if (rc) return rc;
+        if (p->ny % stride == 0) {
+            P.lat_w = (uint32_t)(p->ny / stride);
+            P.lat_c0 = (uint32_t)(begin % stride);
+            P.lat_g0 = (begin - P.lat_c0) / stride;
+        }
     }
     P.out_capacity = e->q_capacity;
     P.counters = e->d_counters;

@@ -30,9 +30,17 @@
 
 __device__ __forceinline__ bool raster_on(const WaveParams &P) { return P.raster_ctl->area <= RTS_RASTER_LIMIT * P.n_primary; }
 
-// shard-local index (relative to the batch) of launch-grid pixel (iy, iz), nx == 1
-__device__ __forceinline__ bool pixel_local(const WaveParams &P, unsigned iy, unsigned iz, unsigned &rel)
+// shard-local index (relative to the batch) of launch-grid pixel (iy, iz), nx == 1.  When the shard's columns form a
+// lattice (stride divides the row length: always for stride 1) the caller walks that lattice and passes the column
+// counter k = (iy - c0) / stride, and the index is z * (ny / stride) + k - g0 without any division.
+__device__ __forceinline__ bool pixel_local(const WaveParams &P, unsigned iy, unsigned iz, int k, unsigned &rel)
 {
+    if (P.lat_w) {
+        const long long g = (long long)iz * P.lat_w + k - (long long)P.lat_g0 - (long long)P.batch_base;
+        if (g < 0 || g >= (long long)P.n_primary) return false;
+        rel = (unsigned)g;
+        return true;
+    }
     const unsigned long long rayIndex = (unsigned long long)iz * P.ny + iy;
     if (rayIndex < P.ray_begin) return false;
     unsigned long long off = rayIndex - P.ray_begin;
@@ -63,6 +71,7 @@ struct TriFoot {
     uint32_t id;
     int y0, y1, z0, z1;         // inclusive pixel bounds, already clamped to the grid; y0 > y1: no coverage
     int ystep;                  // this shard's columns: y0 is on the shard's lattice, step = stride (or 1)
+    int k0;                     // lattice column counter of y0: y = c0 + k * stride
     float ea[3], eb[3], ec[3];  // padded 2D edge functions relative to (y0, z0): inside iff all >= 0
     bool use2d;
 };
@@ -136,10 +145,12 @@ __device__ __forceinline__ bool tri_footprint(const WaveParams &P, unsigned pos,
     }
     // columns of this shard only, when they form a lattice (stride divides the row length)
     F.ystep = 1;
-    if (P.ray_stride > 1 && P.ny % P.ray_stride == 0) {
-        const int s = (int)P.ray_stride, c0 = (int)(P.ray_begin % P.ray_stride);
+    F.k0 = y0;
+    if (P.lat_w && P.ray_stride > 1) {
+        const int s = (int)P.ray_stride, c0 = (int)P.lat_c0;
         y0 += ((c0 - y0 % s) + s) % s;
         F.ystep = s;
+        F.k0 = (y0 - c0) / s;
     }
     F.y0 = y0; F.y1 = y1; F.z0 = z0; F.z1 = z1;
     if (y0 > y1 || z0 > z1) return false;
@@ -234,15 +245,15 @@ __global__ void k_raster_small(const __grid_constant__ WaveParams P)
     const unsigned pos = blockIdx.x * blockDim.x + threadIdx.x;
     TriFoot F;
     bool have = pos < P.n_tris && tri_footprint(P, pos, F) && foot_area(F) <= RTS_RASTER_SMALL;
-    int y = have ? F.y0 : 0, z = have ? F.z0 : 1;
+    int y = have ? F.y0 : 0, z = have ? F.z0 : 1, k = have ? F.k0 : 0;
     const int z1 = have ? F.z1 : 0;
     while (__any_sync(0xffffffffu, z <= z1)) {
         unsigned rel = 0;
         bool found = false;
         while (z <= z1) {
-            const bool ok = foot_inside2d(F, y, z) && pixel_local(P, (unsigned)y, (unsigned)z, rel);
-            y += F.ystep;
-            if (y > F.y1) { y = F.y0; z++; }
+            const bool ok = foot_inside2d(F, y, z) && pixel_local(P, (unsigned)y, (unsigned)z, k, rel);
+            y += F.ystep; k++;
+            if (y > F.y1) { y = F.y0; k = F.k0; z++; }
             if (ok) { found = true; break; }
         }
         if (found) foot_test(P, F, rel);
@@ -261,9 +272,9 @@ __global__ void k_raster_big(const __grid_constant__ WaveParams P)
         TriFoot F;
         if (!tri_footprint(P, I.pos, F)) continue;
         for (int z = (int)I.z0; z <= (int)I.z1; z++)
-            for (int y = F.y0 + (int)lane * F.ystep; y <= F.y1; y += 32 * F.ystep) {
+            for (int y = F.y0 + (int)lane * F.ystep, k = F.k0 + (int)lane; y <= F.y1; y += 32 * F.ystep, k += 32) {
                 unsigned rel;
-                if (foot_inside2d(F, y, z) && pixel_local(P, (unsigned)y, (unsigned)z, rel)) foot_test(P, F, rel);
+                if (foot_inside2d(F, y, z) && pixel_local(P, (unsigned)y, (unsigned)z, k, rel)) foot_test(P, F, rel);
             }
     }
 }
