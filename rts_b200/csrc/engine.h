@@ -162,6 +162,14 @@ struct StageSlot {
     bool in_flight = false;
 };
 
+// What the primary ray directions of a batch depend on (raster.cuh: k_primary_dirs); equal key = reusable buffer.
+struct DirsKey {
+    uint32_t nx, ny, nz;
+    int single;
+    uint64_t begin, stride, base, n;
+    double c[30];   // origin, beamStart, slope, Rot, Rot1, boresight
+};
+
 struct rts_engine {
     int device = 0;
     int num_sms = 0;
@@ -234,6 +242,8 @@ struct rts_engine {
     unsigned long long *d_hits = nullptr;
     void *d_raster_ctl = nullptr, *d_raster_items = nullptr;
     uint64_t raster_alloc = 0;
+    DirsKey dirs_key = {};
+    bool dirs_valid = false;
 
     // outputs
     double *d_bin_sums = nullptr;

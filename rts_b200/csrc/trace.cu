@@ -17,6 +17,7 @@
 #include "dev_math.cuh"
 #include <cooperative_groups.h>
 #include <cooperative_groups/reduce.h>
+#include <cstring>
 
 namespace cg = cooperative_groups;
 
@@ -785,6 +786,7 @@ int trace_raster_alloc(rts_engine *e, uint64_t batch)
     RTS_CUDA(cudaMalloc(&e->d_raster_ctl, sizeof(RasterCtl)));
     RTS_CUDA(cudaMalloc(&e->d_raster_items, sizeof(RasterItem) * (size_t)RTS_RASTER_ITEM_CAP));
     e->raster_alloc = batch;
+    e->dirs_valid = false;
     return RTS_OK;
 }
 
@@ -800,7 +802,24 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records)
     RTS_CUDA(cudaMemsetAsync(e->d_raster_ctl, 0, sizeof(RasterCtl), st));
     const unsigned bs = 128;
     const unsigned tri_blocks = (p.n_tris + bs - 1) / bs;
-    k_primary_dirs<<<e->num_sms * 16, 256, 0, st>>>(p);
+    // The directions depend on the launch geometry only (Tx boresight and span, grid, shard, batch) — not on the scene:
+    // when a pulse repeats the previous pulse's launch (a staring transmitter), the buffer is still valid and only
+    // the hit words are reset.
+    DirsKey key;
+    memset(&key, 0, sizeof(key));
+    key.nx = p.nx; key.ny = p.ny; key.nz = p.nz; key.single = p.single_ray;
+    key.begin = p.ray_begin; key.stride = p.ray_stride; key.base = p.batch_base; key.n = p.n_primary;
+    memcpy(key.c, p.origin, sizeof(double) * 3); memcpy(key.c + 3, p.beamStart, sizeof(double) * 3);
+    memcpy(key.c + 6, p.slope, sizeof(double) * 3); memcpy(key.c + 9, p.Rot, sizeof(double) * 9);
+    memcpy(key.c + 18, p.Rot1, sizeof(double) * 9); memcpy(key.c + 27, p.boresight, sizeof(double) * 3);
+    if (e->dirs_valid && memcmp(&key, &e->dirs_key, sizeof(key)) == 0) {
+        RTS_CUDA(cudaMemsetAsync(e->d_hits, 0xff, sizeof(unsigned long long) * p.n_primary, st));
+    } else {
+        k_primary_dirs<<<e->num_sms * 16, 256, 0, st>>>(p);
+        e->dirs_key = key;
+        e->dirs_valid = true;
+        e->launches++;
+    }
     k_raster_setup<<<tri_blocks, bs, 0, st>>>(p);
     k_raster_small<<<tri_blocks, bs, 0, st>>>(p);
     k_raster_big<<<e->num_sms * 8, bs, 0, st>>>(p);
@@ -808,7 +827,7 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records)
     if (records) k_primary_shade<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     else k_primary_shade<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     RTS_CUDA(cudaGetLastError());
-    e->launches += 6;
+    e->launches += 5;
     return RTS_OK;
 }
 

@@ -451,3 +451,28 @@ def test_conservative_traversal_edge_cases(engine, name):
     for k in ("segments", "hits", "shaded_hits"):
         assert st[k] == orc["stats"][k], k
     assert st["hits"] > 0 and engine.check_bvh() == 0
+
+
+def test_primary_direction_buffer_reuse(engine):
+    """The projected primary wave keeps the ray directions of the previous pulse when the launch geometry is the same
+    and regenerates them when the boresight, span, grid or shard changes: records equal the oracle every time."""
+    targets, spec = scenes.trihedral(n=160)
+    engine.set_targets(targets)
+    import copy
+    variants = []
+    for k, (daz, n, stride) in enumerate([(0.0, 160, 0), (0.0, 160, 0), (0.01, 160, 0), (0.0, 160, 0), (0.0, 128, 0), (0.0, 128, 3), (0.0, 128, 3)]):
+        s = copy.copy(spec)
+        s.tx_dir = (spec.tx_dir[0] + daz, spec.tx_dir[1])
+        s.grid = (1, n, n)
+        s.ray_begin, s.ray_count, s.ray_stride = (1 if stride else 0), 0, stride
+        variants.append(s)
+    for k, s in enumerate(variants):
+        st = engine.trace(s, L.RTS_OUT_RECORDS | L.RTS_OUT_BINS)
+        assert st["primary_projected"] == 1
+        if s.ray_stride:      # the oracle leaves the slots of other shards untouched: compare what the shard produced
+            obins, ost = O.trace_bins(targets, s, use_bvh=False)
+            assert st["segments"] == ost["segments"] and st["hits"] == ost["hits"]
+            parity.assert_bins_close(parity.compare_bins(engine.bins(), obins))
+        else:
+            orc = O.trace(targets, s, use_bvh=False)
+            parity.assert_records_equal(parity.compare_records(engine.records(), orc, s, f"variant{k}"))
