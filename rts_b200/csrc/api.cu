@@ -122,7 +122,7 @@ extern "C" void rts_destroy(rts_engine *e)
     cudaStreamSynchronize(e->stream);
     free_scene(e);
     for (int k = 0; k < 2; k++) if (e->q_slab[k]) cudaFree(e->q_slab[k]);
-    void *ptrs[] = {e->d_dirs, e->d_hits, e->d_raster_ctl, e->d_raster_items, e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count, e->d_rx_sums, e->d_rx_mins,
+    void *ptrs[] = {e->d_dirs, e->d_hits, e->d_hits_static, e->d_raster_ctl, e->d_raster_ctl_static, e->d_raster_items, e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count, e->d_rx_sums, e->d_rx_mins,
                     e->d_results, e->d_targ_intersect, e->d_tri_path, e->d_rcs_angle};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -238,6 +238,8 @@ extern "C" int rts_scene_set_targets(rts_engine *e, const rts_target_mesh *targe
     if ((rc = upload(&e->d_poses, poses))) return rc;
     e->h_poses = poses;
     e->moving.assign(n_targets, 0);
+    e->scene_version++;
+    e->moving_version++;
     e->builder = e->builder_forced;
     if ((rc = bvh_alloc(e))) return rc;
     if ((rc = bvh_build(e))) return rc;
@@ -267,7 +269,7 @@ extern "C" int rts_scene_set_poses(rts_engine *e, const rts_pose *poses, uint32_
         }
         e->h_poses[k] = poses[k];
     }
-    if (grew) e->partial_ready = false;
+    if (grew) { e->partial_ready = false; e->moving_version++; }
     if (!changed) { e->refit_timed = false; e->bvh_info.ms_refit = 0.f; return RTS_OK; }
     cudaEventRecord(e->ev[4], e->stream);
     char *st = stage_acquire(e, sizeof(rts_pose) * n_targets);
@@ -575,7 +577,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
             Q.wave_index = w;
             if (single_batch) cudaEventRecord(e->wave_ev[w], st);
             if (w == 0 && use_raster) {   // projected primary wave; the BVH one behind it runs only if the guard trips
-                int rr = trace_launch_raster(e, Q, records);
+                int rr = trace_launch_raster(e, Q, records, single_batch);
                 if (rr) return rr;
             }
             int rc = trace_launch_wave(e, Q, w == 0, records);
@@ -589,7 +591,12 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     RTS_CUDA(cudaMemcpyAsync(&e->h_rb->counters, e->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
     RTS_CUDA(cudaMemcpyAsync(e->h_rb->wave_segs, e->d_wave_segs, sizeof(unsigned long long) * 32, cudaMemcpyDeviceToHost, st));
     e->pulse_raster = use_raster;
-    if (use_raster) RTS_CUDA(cudaMemcpyAsync(&e->h_rb->raster, e->d_raster_ctl, sizeof(RasterCtl), cudaMemcpyDeviceToHost, st));
+    if (use_raster) {
+        RTS_CUDA(cudaMemcpyAsync(&e->h_rb->raster, e->d_raster_ctl, sizeof(RasterCtl), cudaMemcpyDeviceToHost, st));
+        e->h_rb->raster_static.area = 0;
+        if (e->static_valid)
+            RTS_CUDA(cudaMemcpyAsync(&e->h_rb->raster_static, e->d_raster_ctl_static, sizeof(RasterCtl), cudaMemcpyDeviceToHost, st));
+    }
     e->pulse_pending = true;
     e->pulse_single_batch = single_batch && n_primary_total;
     e->pulse_primary = n_primary_total; e->pulse_waves = waves;
@@ -626,9 +633,9 @@ int pulse_collect(rts_engine *e)
     s.nodes_visited = c.nodes; s.tris_tested = c.tris; s.waves = e->pulse_waves;
     s.ms_trace = ms; s.ms_update = e->bvh_info.ms_refit; s.ms_total = ms;
     // the guard of raster.cuh, evaluated on the last batch's control block (16 candidates per ray)
-    s.primary_projected = (e->pulse_raster && e->h_rb->raster.area <= 16ull * std::min<uint64_t>(e->pulse_primary, 1ull << 24)) ? 1u : 0u;
+    s.primary_projected = (e->pulse_raster && e->h_rb->raster.area + e->h_rb->raster_static.area <= 16ull * std::min<uint64_t>(e->pulse_primary, 1ull << 24)) ? 1u : 0u;
     if (getenv("RTS_DEBUG_RASTER") && e->pulse_raster)
-        fprintf(stderr, "[raster] candidates %llu, %u row chunks, projected %u\n", e->h_rb->raster.area, e->h_rb->raster.n_items, s.primary_projected);
+        fprintf(stderr, "[raster] candidates %llu (+ %llu kept from the static pass), %u row chunks, projected %u\n", e->h_rb->raster.area, e->h_rb->raster_static.area, e->h_rb->raster.n_items, s.primary_projected);
     if (c.overflow) return rts_fail(RTS_ERR_CAPACITY, "%llu ray states dropped (queue/stack overflow)", (unsigned long long)c.overflow);
     return RTS_OK;
 }

@@ -142,6 +142,12 @@ struct WaveParams {
     // shard-local index = z * lat_w + k - lat_g0; lat_w == 0: no lattice (general begin / stride)
     uint32_t lat_w, lat_c0;
     uint64_t lat_g0;
+    // footprint pass over a subset: triangle ids of the moving targets (raster_list), or everything but them (raster_skip:
+    // per-target flags); raster_static: control block of the cached static pass, counted by the guard
+    const uint32_t *raster_list;
+    uint32_t raster_list_count;
+    const uint32_t *raster_skip;
+    const RasterCtl *raster_static;
 };
 
 // ---- engine ---------------------------------------------------------------------------------
@@ -150,7 +156,7 @@ struct Readback {
     Counters counters;
     unsigned long long wave_segs[32];
     double sah;
-    RasterCtl raster;
+    RasterCtl raster, raster_static;
     uint32_t bins_count;
 };
 
@@ -244,6 +250,11 @@ struct rts_engine {
     uint64_t raster_alloc = 0;
     DirsKey dirs_key = {};
     bool dirs_valid = false;
+    // closest hits of the triangles that never move, kept while launch geometry, scene and moving set stay the same
+    unsigned long long *d_hits_static = nullptr;
+    void *d_raster_ctl_static = nullptr;
+    bool static_valid = false;
+    uint64_t scene_version = 0, moving_version = 0, static_scene_version = 0, static_moving_version = 0;
 
     // outputs
     double *d_bin_sums = nullptr;
@@ -304,7 +315,7 @@ int pulse_collect(rts_engine *e);                   // fold the read-back of an 
 int trace_alloc_queues(rts_engine *e, uint64_t capacity);
 int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool records);
 int trace_raster_alloc(rts_engine *e, uint64_t batch);     // buffers of the projected primary wave
-int trace_launch_raster(rts_engine *e, WaveParams &p, bool records);   // enqueue it (before the BVH primary wave)
+int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_batch);   // enqueue it (before the BVH primary wave)
 int trace_wave_grid(rts_engine *e);
 
 // aggregate.cu

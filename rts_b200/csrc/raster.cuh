@@ -28,7 +28,14 @@
 #define RTS_RASTER_CHUNK 2048u         // candidates per row chunk of a large footprint
 #define RTS_RASTER_LIMIT 16ull         // candidates per primary ray beyond which the BVH primary wave is used
 
-__device__ __forceinline__ bool raster_on(const WaveParams &P) { return P.raster_ctl->area <= RTS_RASTER_LIMIT * P.n_primary; }
+__device__ __forceinline__ bool raster_on(const WaveParams &P)
+{
+    const unsigned long long area = P.raster_ctl->area + (P.raster_static ? P.raster_static->area : 0ull);
+    return area <= RTS_RASTER_LIMIT * P.n_primary;
+}
+// The triangles a footprint pass covers: all leaf positions, or the triangles of the moving targets (by id).
+__device__ __forceinline__ unsigned raster_count(const WaveParams &P) { return P.raster_list ? P.raster_list_count : P.n_tris; }
+__device__ __forceinline__ unsigned raster_pos(const WaveParams &P, unsigned i) { return P.raster_list ? P.leaf_of_tri[P.raster_list[i]] : i; }
 
 // shard-local index (relative to the batch) of launch-grid pixel (iy, iz), nx == 1.  When the shard's columns form a
 // lattice (stride divides the row length: always for stride 1) the caller walks that lattice and passes the column
@@ -82,6 +89,7 @@ __device__ __forceinline__ double clampd(double v, double lo, double hi) { retur
 __device__ __forceinline__ bool tri_footprint(const WaveParams &P, unsigned pos, TriFoot &F)
 {
     const Tri T = load_tri(P.trirec, pos);
+    if (P.raster_skip && P.raster_skip[T.target]) return false;   // static pass: the moving targets come separately
     const d3 o = mk3(P.origin[0], P.origin[1], P.origin[2]);
     F.e0 = T.p1 - T.p0;
     F.e1 = T.p0 - T.p2;
@@ -210,9 +218,10 @@ __device__ __forceinline__ void foot_test(const WaveParams &P, const TriFoot &F,
 // Pass 1: summed footprint (the guard) and the row chunks of the large footprints.
 __global__ void k_raster_setup(const __grid_constant__ WaveParams P)
 {
-    const unsigned pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long area = 0;
-    if (pos < P.n_tris) {
+    if (idx < raster_count(P)) {
+        const unsigned pos = raster_pos(P, idx);
         TriFoot F;
         if (tri_footprint(P, pos, F)) {
             area = foot_area(F);
@@ -242,9 +251,9 @@ __global__ void k_raster_setup(const __grid_constant__ WaveParams P)
 __global__ void k_raster_small(const __grid_constant__ WaveParams P)
 {
     if (!raster_on(P)) return;
-    const unsigned pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     TriFoot F;
-    bool have = pos < P.n_tris && tri_footprint(P, pos, F) && foot_area(F) <= RTS_RASTER_SMALL;
+    bool have = idx < raster_count(P) && tri_footprint(P, raster_pos(P, idx), F) && foot_area(F) <= RTS_RASTER_SMALL;
     int y = have ? F.y0 : 0, z = have ? F.z0 : 1, k = have ? F.k0 : 0;
     const int z1 = have ? F.z1 : 0;
     while (__any_sync(0xffffffffu, z <= z1)) {

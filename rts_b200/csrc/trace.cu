@@ -778,19 +778,35 @@ int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool rec
 int trace_raster_alloc(rts_engine *e, uint64_t batch)
 {
     if (e->raster_alloc >= batch) return RTS_OK;
-    void **ptrs[] = {(void **)&e->d_dirs, (void **)&e->d_hits, &e->d_raster_ctl, &e->d_raster_items};
+    void **ptrs[] = {(void **)&e->d_dirs, (void **)&e->d_hits, (void **)&e->d_hits_static, &e->d_raster_ctl, &e->d_raster_ctl_static,
+                     &e->d_raster_items};
     for (void **p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
     e->raster_alloc = 0;
     RTS_CUDA(cudaMalloc(&e->d_dirs, sizeof(double) * 3 * batch));
     RTS_CUDA(cudaMalloc(&e->d_hits, sizeof(unsigned long long) * batch));
+    RTS_CUDA(cudaMalloc(&e->d_hits_static, sizeof(unsigned long long) * batch));
     RTS_CUDA(cudaMalloc(&e->d_raster_ctl, sizeof(RasterCtl)));
+    RTS_CUDA(cudaMalloc(&e->d_raster_ctl_static, sizeof(RasterCtl)));
     RTS_CUDA(cudaMalloc(&e->d_raster_items, sizeof(RasterItem) * (size_t)RTS_RASTER_ITEM_CAP));
     e->raster_alloc = batch;
     e->dirs_valid = false;
+    e->static_valid = false;
     return RTS_OK;
 }
 
-int trace_launch_raster(rts_engine *e, WaveParams &p, bool records)
+// One footprint pass (setup + small + large footprints) over the triangles p selects.
+static void launch_footprints(rts_engine *e, const WaveParams &p, unsigned count)
+{
+    const unsigned bs = 128;
+    const unsigned blocks = (count + bs - 1) / bs;
+    if (!blocks) return;
+    k_raster_setup<<<blocks, bs, 0, e->stream>>>(p);
+    k_raster_small<<<blocks, bs, 0, e->stream>>>(p);
+    k_raster_big<<<e->num_sms * 8, bs, 0, e->stream>>>(p);
+    e->launches += 3;
+}
+
+int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_batch)
 {
     cudaStream_t st = e->stream;
     for (int a = 0; a < 3; a++) p.dirs[a] = e->d_dirs + (size_t)a * e->raster_alloc;
@@ -799,12 +815,10 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records)
     p.raster_items = (RasterItem *)e->d_raster_items;
     p.raster_item_cap = RTS_RASTER_ITEM_CAP;
     p.leaf_of_tri = e->d_leaf_of_tri;
+    p.raster_list = nullptr; p.raster_list_count = 0; p.raster_skip = nullptr; p.raster_static = nullptr;
     RTS_CUDA(cudaMemsetAsync(e->d_raster_ctl, 0, sizeof(RasterCtl), st));
-    const unsigned bs = 128;
-    const unsigned tri_blocks = (p.n_tris + bs - 1) / bs;
     // The directions depend on the launch geometry only (Tx boresight and span, grid, shard, batch) — not on the scene:
-    // when a pulse repeats the previous pulse's launch (a staring transmitter), the buffer is still valid and only
-    // the hit words are reset.
+    // when a pulse repeats the previous pulse's launch (a staring transmitter), the buffer is still valid.
     DirsKey key;
     memset(&key, 0, sizeof(key));
     key.nx = p.nx; key.ny = p.ny; key.nz = p.nz; key.single = p.single_ray;
@@ -812,22 +826,52 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records)
     memcpy(key.c, p.origin, sizeof(double) * 3); memcpy(key.c + 3, p.beamStart, sizeof(double) * 3);
     memcpy(key.c + 6, p.slope, sizeof(double) * 3); memcpy(key.c + 9, p.Rot, sizeof(double) * 9);
     memcpy(key.c + 18, p.Rot1, sizeof(double) * 9); memcpy(key.c + 27, p.boresight, sizeof(double) * 3);
-    if (e->dirs_valid && memcmp(&key, &e->dirs_key, sizeof(key)) == 0) {
-        RTS_CUDA(cudaMemsetAsync(e->d_hits, 0xff, sizeof(unsigned long long) * p.n_primary, st));
-    } else {
-        k_primary_dirs<<<e->num_sms * 16, 256, 0, st>>>(p);
+    const bool same_launch = e->dirs_valid && memcmp(&key, &e->dirs_key, sizeof(key)) == 0;
+    if (!same_launch) {
+        k_primary_dirs<<<e->num_sms * 16, 256, 0, st>>>(p);   // also resets the hit words
         e->dirs_key = key;
         e->dirs_valid = true;
+        e->static_valid = false;
         e->launches++;
     }
-    k_raster_setup<<<tri_blocks, bs, 0, st>>>(p);
-    k_raster_small<<<tri_blocks, bs, 0, st>>>(p);
-    k_raster_big<<<e->num_sms * 8, bs, 0, st>>>(p);
+    // The closest hits among the triangles that never move are the same from pulse to pulse as long as the launch, the
+    // scene and the set of moving targets are: they are kept (static pass once), and a pulse only projects the
+    // triangles of the moving targets on top of a copy.  Needs the moving-target lists of the partial refit (bvh.cu).
+    uint32_t n_moving = 0;
+    for (uint32_t k = 0; k < e->n_targets; k++) n_moving += e->moving[k] ? 1u : 0u;
+    const bool cacheable = single_batch && !getenv("RTS_NO_STATIC_HITS") && (n_moving == 0 || e->partial_ready);
+    if (cacheable) {
+        const bool valid = e->static_valid && same_launch && e->static_scene_version == e->scene_version &&
+                           e->static_moving_version == e->moving_version;
+        if (!valid) {
+            if (same_launch) RTS_CUDA(cudaMemsetAsync(e->d_hits, 0xff, sizeof(unsigned long long) * p.n_primary, st));
+            RTS_CUDA(cudaMemsetAsync(e->d_raster_ctl_static, 0, sizeof(RasterCtl), st));
+            WaveParams q = p;
+            q.raster_ctl = (RasterCtl *)e->d_raster_ctl_static;
+            q.raster_skip = n_moving ? e->d_moving : nullptr;
+            launch_footprints(e, q, p.n_tris);
+            RTS_CUDA(cudaMemcpyAsync(e->d_hits_static, e->d_hits, sizeof(unsigned long long) * p.n_primary, cudaMemcpyDeviceToDevice, st));
+            e->static_valid = true;
+            e->static_scene_version = e->scene_version;
+            e->static_moving_version = e->moving_version;
+        } else {
+            RTS_CUDA(cudaMemcpyAsync(e->d_hits, e->d_hits_static, sizeof(unsigned long long) * p.n_primary, cudaMemcpyDeviceToDevice, st));
+        }
+        p.raster_static = (const RasterCtl *)e->d_raster_ctl_static;
+        if (n_moving && e->n_dt) {
+            p.raster_list = e->d_tlist; p.raster_list_count = e->n_dt;
+            launch_footprints(e, p, e->n_dt);
+        }
+    } else {
+        if (same_launch) RTS_CUDA(cudaMemsetAsync(e->d_hits, 0xff, sizeof(unsigned long long) * p.n_primary, st));
+        e->static_valid = false;
+        launch_footprints(e, p, p.n_tris);
+    }
     k_raster_resolve<<<e->num_sms * 16, 256, 0, st>>>(p);
     if (records) k_primary_shade<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     else k_primary_shade<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     RTS_CUDA(cudaGetLastError());
-    e->launches += 5;
+    e->launches += 2;
     return RTS_OK;
 }
 
