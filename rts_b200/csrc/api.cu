@@ -122,7 +122,7 @@ extern "C" void rts_destroy(rts_engine *e)
     cudaStreamSynchronize(e->stream);
     free_scene(e);
     for (int k = 0; k < 2; k++) if (e->q_slab[k]) cudaFree(e->q_slab[k]);
-    void *ptrs[] = {e->d_dirs, e->d_hits, e->d_hits_static, e->d_raster_ctl, e->d_raster_ctl_static, e->d_raster_items, e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count, e->d_rx_sums, e->d_rx_mins,
+    void *ptrs[] = {e->d_w1_static, e->d_target_box, e->d_mover_nodes, e->d_dirs, e->d_hits, e->d_hits_static, e->d_raster_ctl, e->d_raster_ctl_static, e->d_raster_items, e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count, e->d_rx_sums, e->d_rx_mins,
                     e->d_results, e->d_targ_intersect, e->d_tri_path, e->d_rcs_angle};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -563,6 +563,9 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
         P.swz_w = (uint32_t)(p->ny / stride);
         P.swz_limit = n_primary_total / (4ull * P.swz_w) * (4ull * P.swz_w);
     }
+    bool kept = false;
+    WaveParams kept_params;
+    memset(&kept_params, 0, sizeof(kept_params));
     for (uint64_t done = 0; done < n_primary_total; done += batch) {
         const uint64_t nb = std::min<uint64_t>(batch, n_primary_total - done);
         // d_counts: [0..31] queue counts per wave, [32..63] work counters per wave
@@ -578,6 +581,14 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
             if (single_batch) cudaEventRecord(e->wave_ev[w], st);
             if (w == 0 && use_raster) {   // projected primary wave; the BVH one behind it runs only if the guard trips
                 int rr = trace_launch_raster(e, Q, records, single_batch);
+                if (rr) return rr;
+                kept = e->coh_on;
+                kept_params = Q;
+            }
+            if (w == 1 && kept) {         // first reflections served from the kept hits (coherent.cuh)
+                Q.w1_static = kept_params.w1_static; Q.hits_static = kept_params.hits_static; Q.moving_flags = kept_params.moving_flags;
+                trace_wave_grid(e);
+                int rr = trace_launch_kept(e, Q, records);
                 if (rr) return rr;
             }
             int rc = trace_launch_wave(e, Q, w == 0, records);

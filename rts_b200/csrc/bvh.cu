@@ -470,6 +470,7 @@ int bvh_alloc(rts_engine *e)
     if ((rc = dalloc(&e->d_sah, (size_t)1))) return rc;
     // partial refit (only the targets that move)
     if ((rc = dalloc(&e->d_moving, (size_t)e->n_targets))) return rc;
+    RTS_CUDA(cudaMemsetAsync(e->d_moving, 0, sizeof(uint32_t) * std::max<size_t>(1, e->n_targets), e->stream));
     if ((rc = dalloc(&e->d_vlist, (size_t)e->n_verts))) return rc;
     if ((rc = dalloc(&e->d_nlist, (size_t)e->n_normals))) return rc;
     if ((rc = dalloc(&e->d_tlist, T))) return rc;

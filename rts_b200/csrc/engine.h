@@ -148,6 +148,13 @@ struct WaveParams {
     uint32_t raster_list_count;
     const uint32_t *raster_skip;
     const RasterCtl *raster_static;
+    // kept first-reflection hits (coherent.cuh); w1_static == nullptr: off
+    unsigned long long *w1_static;          // [batch] closest static hit of each pixel's first reflection (t bits << 32 | leaf pos), ~0 = none
+    const unsigned long long *hits_static;  // [batch] kept primary hits (t bits << 32 | triangle id)
+    const uint32_t *moving_flags;           // per target
+    const BvhNode *mover_nodes;             // bounding boxes of the moving targets, two per node
+    uint32_t n_mover_nodes;
+    unsigned long long *fill_counter;       // work counter of k_wave1_fill
 };
 
 // ---- engine ---------------------------------------------------------------------------------
@@ -255,6 +262,12 @@ struct rts_engine {
     void *d_raster_ctl_static = nullptr;
     bool static_valid = false;
     uint64_t scene_version = 0, moving_version = 0, static_scene_version = 0, static_moving_version = 0;
+    // kept first-reflection hits (coherent.cuh)
+    unsigned long long *d_w1_static = nullptr;
+    unsigned *d_target_box = nullptr;
+    BvhNode *d_mover_nodes = nullptr;
+    bool coh_on = false, coh_fill = false, w1_valid = false;
+    uint32_t w1_builds = 0, w1_interp = 0, w1_dmax = 0, w1_rmax = 0;
 
     // outputs
     double *d_bin_sums = nullptr;
@@ -316,6 +329,7 @@ int trace_alloc_queues(rts_engine *e, uint64_t capacity);
 int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool records);
 int trace_raster_alloc(rts_engine *e, uint64_t batch);     // buffers of the projected primary wave
 int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_batch);   // enqueue it (before the BVH primary wave)
+int trace_launch_kept(rts_engine *e, WaveParams &p, bool records);   // second wave: rays served from the kept first-reflection hits
 int trace_wave_grid(rts_engine *e);
 
 // aggregate.cu

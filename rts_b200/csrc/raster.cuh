@@ -296,7 +296,12 @@ __global__ void k_raster_resolve(const __grid_constant__ WaveParams P)
     for (unsigned long long rel = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; rel < P.n_primary;
          rel += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long hit = P.hits[rel];
-        if (hit != ~0ull) P.hits[rel] = (hit & 0xffffffff00000000ull) | (unsigned long long)P.leaf_of_tri[(uint32_t)hit];
+        if (hit != ~0ull) {
+            // bit 31 of the position word: the winner is the kept static one, so this ray's first reflection is the
+            // same ray as in the pulse the first-reflection hits were kept from (coherent.cuh)
+            const unsigned long long same = (P.w1_static && P.hits_static[rel] == hit) ? 0x80000000ull : 0ull;
+            P.hits[rel] = (hit & 0xffffffff00000000ull) | (unsigned long long)P.leaf_of_tri[(uint32_t)hit] | same;
+        }
     }
 }
 
@@ -333,9 +338,9 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_primar
         r.key = 0; r.ray = (uint32_t)(P.ray_begin + (P.batch_base + rel) * P.ray_stride);
         if (hit != ~0ull) {
             HitRec h;
-            h.pos = (int)(uint32_t)hit; h.t = __uint_as_float((unsigned)(hit >> 32)); h.id = 0;   // shade() takes the id from the record
+            h.pos = (int)((uint32_t)hit & 0x7fffffffu); h.t = __uint_as_float((unsigned)(hit >> 32)); h.id = 0;   // shade() takes the id from the record
             L.a += C_HIT;
-            shade<RECORDS>(P, r, h, L, false);
+            shade<RECORDS>(P, r, h, L, false, ((uint32_t)hit & 0x80000000u) ? M_COH : 0u);
         } else {
             const int received = miss<RECORDS>(P, r, L);
             if (received >= 0) {

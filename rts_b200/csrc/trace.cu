@@ -18,6 +18,7 @@
 #include <cooperative_groups.h>
 #include <cooperative_groups/reduce.h>
 #include <cstring>
+#include <algorithm>
 
 namespace cg = cooperative_groups;
 
@@ -38,6 +39,8 @@ __device__ __forceinline__ uint32_t m_slot(uint32_t m) { return (m >> 10) & 15u;
 __device__ __forceinline__ bool m_end(uint32_t m) { return (m >> 14) & 1u; }
 __device__ __forceinline__ bool m_primary(uint32_t m) { return (m >> 15) & 1u; }
 __device__ __forceinline__ uint32_t m_col(uint32_t m) { return (m >> 16) & 15u; }
+// bit 20: first reflection of a primary ray whose primary hit is the kept static one (coherent.cuh)
+constexpr uint32_t M_COH = 1u << 20;
 __device__ __forceinline__ uint32_t m_make(uint32_t refl, uint32_t refr, uint32_t slot, bool end, bool prim, uint32_t col)
 {
     return (refl & 0xffu) | ((refr & 3u) << 8) | ((slot & 15u) << 10) | ((end ? 1u : 0u) << 14) | ((prim ? 1u : 0u) << 15) |
@@ -181,7 +184,7 @@ __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0,
 // fp32 pairs, matching the BvhNode word order: 12 packed instructions test both child boxes.
 // Closest hit = smallest fp32 t in (tmin, inf), ties to the lowest global triangle id
 // (rtPotentialIntersection semantics with a defined tie rule).
-template <bool COUNT>
+template <bool COUNT, bool STATIC_ONLY = false>
 __device__ __forceinline__ void traverse(const WaveParams &P, const d3 &o, const d3 &dir, float tmin_f, HitRec &best,
                                          unsigned &n_nodes, unsigned &n_tris, unsigned &stack_ovf)
 {
@@ -253,6 +256,7 @@ __device__ __forceinline__ void traverse(const WaveParams &P, const d3 &o, const
             for (int k = 0; k < cnt; k++) {
                 if (COUNT) n_tris++;
                 const Tri T = load_tri(P.trirec, first + k);
+                if (STATIC_ONLY && P.moving_flags[T.target]) continue;   // closest hit among the triangles that never move
                 double t;
                 if (tri_accept(T, o, dir, tmin_d, tmax_d, t)) {
                     const float tf = (float)t;
@@ -307,7 +311,7 @@ constexpr unsigned long long C_MULTI = 1ull, C_EDGE = 1ull << 21, C_REFRACTED = 
 // Returns true when `chain` is set and the reflected ray is to be followed at once by the caller (r holds it)
 // instead of being queued for the next wave.
 template <bool RECORDS>
-__device__ __forceinline__ bool shade(const WaveParams &P, Ray &r, const HitRec &h, Local &L, bool chain)
+__device__ __forceinline__ bool shade(const WaveParams &P, Ray &r, const HitRec &h, Local &L, bool chain, uint32_t coh = 0)
 {
     const uint32_t dMax = P.dMax, rMax = P.rMax;
     uint32_t reflDepth = m_refl(r.meta), refrDepth = m_refr(r.meta);
@@ -474,7 +478,7 @@ __device__ __forceinline__ bool shade(const WaveParams &P, Ray &r, const HitRec 
             }
         }
         }
-        r.meta = m_make(reflDepth, refrDepth, slot, end, false, col + 1);
+        r.meta = m_make(reflDepth, refrDepth, slot, end, false, col + 1) | coh;
         if (chain) return true;
         push_ray(P, r, L.overflow); // :332
     } else {
@@ -631,6 +635,7 @@ __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r
 }
 
 #include "raster.cuh"
+#include "coherent.cuh"
 
 template <bool PRIMARY, bool RECORDS, bool COUNT, bool CHAIN>
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_PRIMARY : RTS_WAVE_MIN_BLOCKS) k_wave(const __grid_constant__ WaveParams P)
@@ -678,6 +683,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
             r.meta = m_make(0, 0, 0, false, true, 0);
         } else {
             load_ray_geom(P.in, idx, r);
+            if (P.w1_static && (r.meta & M_COH)) continue;   // served from the kept first-reflection hits (coherent.cuh)
         }
         for (bool first = true;; first = false) {
             HitRec h;
@@ -785,6 +791,9 @@ int trace_raster_alloc(rts_engine *e, uint64_t batch)
     RTS_CUDA(cudaMalloc(&e->d_dirs, sizeof(double) * 3 * batch));
     RTS_CUDA(cudaMalloc(&e->d_hits, sizeof(unsigned long long) * batch));
     RTS_CUDA(cudaMalloc(&e->d_hits_static, sizeof(unsigned long long) * batch));
+    if (e->d_w1_static) { cudaFree(e->d_w1_static); e->d_w1_static = nullptr; }
+    RTS_CUDA(cudaMalloc(&e->d_w1_static, sizeof(unsigned long long) * batch));
+    e->w1_valid = false;
     RTS_CUDA(cudaMalloc(&e->d_raster_ctl, sizeof(RasterCtl)));
     RTS_CUDA(cudaMalloc(&e->d_raster_ctl_static, sizeof(RasterCtl)));
     RTS_CUDA(cudaMalloc(&e->d_raster_items, sizeof(RasterItem) * (size_t)RTS_RASTER_ITEM_CAP));
@@ -840,6 +849,7 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     uint32_t n_moving = 0;
     for (uint32_t k = 0; k < e->n_targets; k++) n_moving += e->moving[k] ? 1u : 0u;
     const bool cacheable = single_batch && !getenv("RTS_NO_STATIC_HITS") && (n_moving == 0 || e->partial_ready);
+    e->coh_on = false;
     if (cacheable) {
         const bool valid = e->static_valid && same_launch && e->static_scene_version == e->scene_version &&
                            e->static_moving_version == e->moving_version;
@@ -858,6 +868,17 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
             RTS_CUDA(cudaMemcpyAsync(e->d_hits, e->d_hits_static, sizeof(unsigned long long) * p.n_primary, cudaMemcpyDeviceToDevice, st));
         }
         p.raster_static = (const RasterCtl *)e->d_raster_ctl_static;
+        // kept first-reflection hits (coherent.cuh): same conditions, plus few enough movers to test their boxes one by one
+        e->coh_on = n_moving <= 32 && p.dMax >= 2 && !getenv("RTS_NO_KEPT_REFLECTIONS");
+        if (e->coh_on) {
+            const bool w1_ok = valid && e->w1_valid && e->w1_builds == e->builds && e->w1_interp == p.interpolate &&
+                               e->w1_dmax == p.dMax && e->w1_rmax == p.rMax;
+            e->coh_fill = !w1_ok;
+            e->w1_valid = true; e->w1_builds = e->builds; e->w1_interp = p.interpolate; e->w1_dmax = p.dMax; e->w1_rmax = p.rMax;
+            p.w1_static = e->d_w1_static;
+            p.hits_static = e->d_hits_static;
+            p.moving_flags = e->d_moving;
+        }
         if (n_moving && e->n_dt) {
             p.raster_list = e->d_tlist; p.raster_list_count = e->n_dt;
             launch_footprints(e, p, e->n_dt);
@@ -872,6 +893,38 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     else k_primary_shade<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     RTS_CUDA(cudaGetLastError());
     e->launches += 2;
+    return RTS_OK;
+}
+
+// Second wave with kept first-reflection hits: this pulse's boxes of the moving targets, the one-off fill, then the
+// kernel that serves the flagged rays; the ordinary wave kernel behind it takes every ray that is not (or no longer) flagged.
+int trace_launch_kept(rts_engine *e, WaveParams &p, bool records)
+{
+    cudaStream_t st = e->stream;
+    MoverIds M;
+    memset(&M, 0, sizeof(M));
+    for (uint32_t k = 0; k < e->n_targets && M.n < 32; k++)
+        if (e->moving[k]) M.id[M.n++] = k;
+    if (!e->d_target_box) RTS_CUDA(cudaMalloc(&e->d_target_box, sizeof(unsigned) * 6 * std::max<uint32_t>(1, e->n_targets)));
+    if (!e->d_mover_nodes) RTS_CUDA(cudaMalloc(&e->d_mover_nodes, sizeof(BvhNode) * 16));
+    p.n_mover_nodes = (M.n + 1) / 2;
+    p.mover_nodes = e->d_mover_nodes;
+    if (M.n) {
+        k_target_box_init<<<1, 192, 0, st>>>(e->d_target_box, M);
+        if (e->n_dt) k_target_boxes<<<(e->n_dt + 255) / 256, 256, 0, st>>>(e->d_tlist, e->n_dt, e->d_tri_box, e->d_tri_target, e->d_target_box);
+        k_mover_nodes<<<1, 32, 0, st>>>(e->d_target_box, M, e->d_mover_nodes);
+        e->launches += 3;
+    }
+    if (e->coh_fill) {
+        RTS_CUDA(cudaMemsetAsync(e->d_w1_static, 0xfe, sizeof(unsigned long long) * p.n_primary, st));
+        p.fill_counter = e->d_counts + 63;
+        k_wave1_fill<<<e->wave_grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        e->launches++;
+    }
+    if (records) k_wave1_kept<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
+    else k_wave1_kept<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
+    e->launches++;
+    RTS_CUDA(cudaGetLastError());
     return RTS_OK;
 }
 
