@@ -10,8 +10,9 @@
 //   k_wave1_fill (first pulse only)  closest STATIC hit of every flagged first reflection -> w1_static[pixel]
 //   k_wave1_kept                     flagged rays: conservative slab test against the moving targets' boxes (same packed
 //                                    arithmetic and error bound as the node test of traverse()); none touched -> the kept
-//                                    hit is the answer, shade / miss as usual; any touched -> the flag is cleared in
-//                                    the queue and the ordinary k_wave launched right behind traces the ray in full
+//                                    hit is the answer, shade / miss as usual; any touched -> the queue index goes
+//                                    on a to-do list with all the unflagged rays, and the ordinary k_wave launched
+//                                    right behind traces just that list in full
 // A ray carries the flag (M_COH in its queue word) only when its primary hit equals the kept static primary hit
 // (raster.cuh: k_raster_resolve), i.e. when it provably is the same ray.  The kept data is tied to the launch geometry,
 // the scene, the moving set, the tree (leaf positions) and the shading switches that steer the ray (interpolation,
@@ -167,15 +168,23 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_wave1_
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_in; idx += stride) {
         Ray r;
-        load_ray_geom(P.in, idx, r);
-        if (!(r.meta & M_COH)) continue;
-        if (near_movers(P, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz))) {
-            P.in.meta[idx] = r.meta & ~M_COH;      // the ordinary wave kernel behind this one traces it in full
-            continue;
+        r.meta = __ldcs(P.in.meta + idx);
+        bool mine = (r.meta & M_COH) != 0;
+        unsigned long long kept = ~0ull;
+        if (mine) {
+            load_ray_geom(P.in, idx, r);
+            mine = !near_movers(P, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz));
+            if (mine) {
+                kept = P.w1_static[w1_pixel(P, __ldcs(P.in.ray + idx))];
+                mine = kept != W1_UNKNOWN;         // the pixel was behind a moving target when the hits were kept
+            }
         }
-        const unsigned long long kept = P.w1_static[w1_pixel(P, __ldcs(P.in.ray + idx))];
-        if (kept == W1_UNKNOWN) {                  // pixel was behind a moving target when the hits were kept
-            P.in.meta[idx] = r.meta & ~M_COH;
+        if (!mine) {                               // for the ordinary wave kernel launched behind this one
+            cg::coalesced_group g = cg::coalesced_threads();
+            unsigned long long at = 0;
+            if (g.thread_rank() == 0) at = atomicAdd(P.todo_count, (unsigned long long)g.size());
+            at = g.shfl(at, 0);
+            P.todo_list[at + g.thread_rank()] = idx;
             continue;
         }
         load_ray_rest(P.in, idx, r, RECORDS, P.rMax != 0);

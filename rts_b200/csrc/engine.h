@@ -155,6 +155,8 @@ struct WaveParams {
     const BvhNode *mover_nodes;             // bounding boxes of the moving targets, two per node
     uint32_t n_mover_nodes;
     unsigned long long *fill_counter;       // work counter of k_wave1_fill
+    uint32_t *todo_list;                    // queue indices k_wave1_kept leaves to the ordinary wave kernel (nullptr: all)
+    unsigned long long *todo_count;
 };
 
 // ---- engine ---------------------------------------------------------------------------------
@@ -266,6 +268,8 @@ struct rts_engine {
     unsigned long long *d_w1_static = nullptr;
     unsigned *d_target_box = nullptr;
     BvhNode *d_mover_nodes = nullptr;
+    uint32_t *d_todo = nullptr;
+    uint64_t todo_alloc = 0;
     bool coh_on = false, coh_fill = false, w1_valid = false;
     uint32_t w1_builds = 0, w1_interp = 0, w1_dmax = 0, w1_rmax = 0;
 

@@ -643,7 +643,8 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
     if (PRIMARY && P.raster_ctl && raster_on(P)) return;   // the projected primary wave (raster.cuh) did this batch
     const unsigned lane = threadIdx.x & 31u;
     // queue capacity and batch size are < 2^26, so 32-bit indices and a 32-bit work counter suffice
-    const unsigned n_in = PRIMARY ? (unsigned)P.n_primary : (unsigned)*P.in_count;
+    const unsigned n_all = PRIMARY ? (unsigned)P.n_primary : (unsigned)*P.in_count;
+    const unsigned n_in = (!PRIMARY && P.todo_list) ? (unsigned)*P.todo_count : n_all;
     unsigned *work = reinterpret_cast<unsigned *>(P.work_counter);
     Local L = {0, 0, 0, 0, 0};
     // Thin late waves (a few thousand rays whose latency, not throughput, sets the launch time) follow their
@@ -652,15 +653,15 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
     const bool chain = CHAIN && !PRIMARY && n_in < P.chain_below;
     unsigned chained = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        atomicAdd(P.wave_segs + P.wave_index, (unsigned long long)n_in);
-        atomicAdd(&P.counters->segments, (unsigned long long)n_in);   // one closest-hit query per queue entry
+        atomicAdd(P.wave_segs + P.wave_index, (unsigned long long)n_all);
+        atomicAdd(&P.counters->segments, (unsigned long long)n_all);   // one closest-hit query per queue entry
     }
     for (;;) {
         unsigned base = 0;
         if (lane == 0) base = atomicAdd(work, 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_in) break;
-        const unsigned idx = base + lane;
+        unsigned idx = base + lane;
         if (idx >= n_in) continue;
         Ray r;
         unsigned long long rayIndex = 0;
@@ -682,8 +683,9 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
             r.dx = d.x; r.dy = d.y; r.dz = d.z;
             r.meta = m_make(0, 0, 0, false, true, 0);
         } else {
+            if (P.todo_list) idx = P.todo_list[idx];         // the rays k_wave1_kept left for a full trace (coherent.cuh)
             load_ray_geom(P.in, idx, r);
-            if (P.w1_static && (r.meta & M_COH)) continue;   // served from the kept first-reflection hits (coherent.cuh)
+            r.meta &= ~M_COH;
         }
         for (bool first = true;; first = false) {
             HitRec h;
@@ -915,6 +917,15 @@ int trace_launch_kept(rts_engine *e, WaveParams &p, bool records)
         k_mover_nodes<<<1, 32, 0, st>>>(e->d_target_box, M, e->d_mover_nodes);
         e->launches += 3;
     }
+    // to-do list of the ordinary wave kernel: everything the kept kernel does not serve
+    if (e->todo_alloc < e->q_capacity) {
+        if (e->d_todo) cudaFree(e->d_todo);
+        e->d_todo = nullptr; e->todo_alloc = 0;
+        RTS_CUDA(cudaMalloc(&e->d_todo, sizeof(uint32_t) * e->q_capacity));
+        e->todo_alloc = e->q_capacity;
+    }
+    p.todo_list = e->d_todo;
+    p.todo_count = e->d_counts + 62;
     if (e->coh_fill) {
         RTS_CUDA(cudaMemsetAsync(e->d_w1_static, 0xfe, sizeof(unsigned long long) * p.n_primary, st));
         p.fill_counter = e->d_counts + 63;
