@@ -146,6 +146,7 @@ typedef struct rts_stats {
     uint64_t nodes_visited;     /* BVH nodes fetched (0 unless RTS_FLAG_COUNT_NODES) */
     uint64_t tris_tested;       /* triangle tests executed (same flag) */
     uint64_t waves;             /* wavefront launches */
+    uint64_t kept_reflections;  /* first reflections answered from the hits kept from an earlier pulse (no traversal) */
     uint32_t n_bins;            /* non-empty bins */
     uint32_t primary_projected; /* 1 when the primary wave of the last batch ran by projection (RTS_RASTER=1) rather than BVH traversal */
     float    ms_update;         /* scene update + refit */

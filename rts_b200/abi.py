@@ -89,7 +89,7 @@ class RtsStats(C.Structure):
     _fields_ = [
         ("primary_rays", C.c_uint64), ("segments", C.c_uint64), ("hits", C.c_uint64), ("shaded_hits", C.c_uint64),
         ("captured", C.c_uint64), ("multi_captured", C.c_uint64), ("edge_rays", C.c_uint64), ("refracted", C.c_uint64),
-        ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("waves", C.c_uint64),
+        ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("waves", C.c_uint64), ("kept_reflections", C.c_uint64),
         ("n_bins", C.c_uint32), ("primary_projected", C.c_uint32),
         ("ms_update", C.c_float), ("ms_trace", C.c_float), ("ms_finalise", C.c_float), ("ms_total", C.c_float),
     ]

@@ -641,7 +641,7 @@ int pulse_collect(rts_engine *e)
     memset(&s, 0, sizeof(s));
     s.primary_rays = e->pulse_primary; s.segments = c.segments; s.hits = c.hits; s.shaded_hits = c.shaded;
     s.captured = c.captured; s.multi_captured = c.multi; s.edge_rays = c.edge; s.refracted = c.refracted;
-    s.nodes_visited = c.nodes; s.tris_tested = c.tris; s.waves = e->pulse_waves;
+    s.nodes_visited = c.nodes; s.tris_tested = c.tris; s.waves = e->pulse_waves; s.kept_reflections = c.kept;
     s.ms_trace = ms; s.ms_update = e->bvh_info.ms_refit; s.ms_total = ms;
     // the guard of raster.cuh, evaluated on the last batch's control block (16 candidates per ray)
     s.primary_projected = (e->pulse_raster && e->h_rb->raster.area + e->h_rb->raster_static.area <= 16ull * std::min<uint64_t>(e->pulse_primary, 1ull << 24)) ? 1u : 0u;

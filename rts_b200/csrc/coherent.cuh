@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_wave1_
     const unsigned lane = threadIdx.x & 31u;
     const unsigned n_in = (unsigned)*P.in_count;
     Local L = {0, 0, 0, 0, 0};
+    unsigned served = 0;
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_in; idx += stride) {
         Ray r;
@@ -189,6 +190,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_wave1_
         }
         load_ray_rest(P.in, idx, r, RECORDS, P.rMax != 0);
         r.meta &= ~M_COH;
+        served++;
         if (kept != ~0ull) {
             HitRec h;
             h.pos = (int)(uint32_t)kept; h.t = __uint_as_float((unsigned)(kept >> 32)); h.id = 0;
@@ -210,5 +212,9 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_wave1_
     for (int k = 0; k < 7; k++) {
         const unsigned x = __reduce_add_sync(0xffffffffu, f[k]);
         if (lane == 0 && x) atomicAdd(c + slot[k], (unsigned long long)x);
+    }
+    {
+        const unsigned x = __reduce_add_sync(0xffffffffu, served);
+        if (lane == 0 && x) atomicAdd(&P.counters->kept, (unsigned long long)x);
     }
 }

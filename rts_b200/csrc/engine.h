@@ -63,7 +63,7 @@ struct RasterCtl {
 struct RasterItem { unsigned pos, z0, z1, pad; };
 
 struct Counters {              // device-side, accumulated with atomics
-    unsigned long long segments, hits, shaded, captured, multi, edge, refracted, nodes, tris, overflow;
+    unsigned long long segments, hits, shaded, captured, multi, edge, refracted, nodes, tris, overflow, kept;
 };
 
 struct RxDev { double cx, cy, cz, radius, min_theta, max_theta, min_phi, max_phi; };

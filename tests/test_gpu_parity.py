@@ -476,3 +476,37 @@ def test_primary_direction_buffer_reuse(engine):
         else:
             orc = O.trace(targets, s, use_bvh=False)
             parity.assert_records_equal(parity.compare_records(engine.records(), orc, s, f"variant{k}"))
+
+
+def test_kept_hits_over_consecutive_pulses_match_the_oracle(engine):
+    """coherent.cuh / raster.cuh keep the static part of the primary hits and of the first reflections across pulses with
+    the same launch.  Consecutive pulses (no rebuild in between) against the oracle: movers low over the terrain so that
+    first reflections do run into them, a shading switch changing mid-way (refill), and a receiver change (no refill)."""
+    import copy
+    ms = scenes.terrain_scene(n=192, cells_x=80, cells_y=40, movers=8, n_rx=2)
+    ms.positions0[1:, 2] = 18.0 + 4.0 * np.arange(len(ms.positions0) - 1)     # just above the hills
+    ms.velocities[1:] *= 40.0                                                   # metres per pulse, so pixels change hands
+    engine.set_targets(ms.base)
+    seen_kept = 0
+    for k, pulse in enumerate([0, 1, 2, 3, 4, 5, 6, 7]):
+        engine.set_poses(*ms.poses(pulse))
+        spec = ms.spec_for(pulse)
+        if k >= 4:
+            spec.max_refl = 2                       # different depth budget: the kept reflections are refilled
+        if k >= 6:
+            spec.rx = list(reversed(spec.rx))       # receivers do not enter the kept data
+        st = engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_OUT_BINS)
+        assert st["primary_projected"] == 1
+        world = ms.world_targets(pulse)
+        orc = O.trace(world, spec, use_bvh=True)
+        cmp = parity.compare_records(engine.records(), orc, spec, f"pulse{pulse}")
+        parity.assert_records_equal(cmp)
+        for key in ("segments", "hits", "shaded_hits"):
+            assert st[key] == orc["stats"][key], (pulse, key)
+        if cmp["window_edge_rays"] == 0:
+            obins, _ = O.trace_bins(world, spec, use_bvh=True)
+            parity.assert_bins_close(parity.compare_bins(engine.bins(), obins))
+        seen_kept += 1 if st["kept_reflections"] > 0 else 0
+        if k in (1, 2, 3, 5, 6, 7):
+            assert 0 < st["kept_reflections"] < st["segments"] - st["primary_rays"]   # most, but not all: movers in the way
+    assert seen_kept >= 7 and engine.bvh_info().builds >= 2
