@@ -11,7 +11,8 @@ of a (1, 4096, 4096) ray grid per GPU with fused receiver-bin aggregation, and f
 all-reduce of the bins (rays of a (1, 4096*N, 4096) launch are dealt round-robin to the ranks, scene and
 BVH replicated: weak scaling).  Pulses advance every step, so the movers really move.
 
-value  : steps timed without reading the bins back (inputs resident, CUDA events on the engine's stream)
+value  : steps timed without reading the bins back (inputs resident, CUDA events on the engine's stream); every pulse
+         traced from scratch (RTS_NO_REUSE); the figure with the library's between-pulse reuse on is in `temporal_reuse`
 e2e    : the same steps through the C-ABI with host buffers, plus the device->host read of the bins
 roofline: the longest single kernel of a step (k_wave, second wave), algorithmic bytes per SURVEY.md §8(d)
 cpu_baseline: the oracle (BVH mode, OpenMP) on a strided sample of the same pulse
@@ -119,12 +120,14 @@ def run_ours(args):
     begin, count, stride = rank, 0, world
     n_mine = (ms.spec.rays - begin + stride - 1) // stride
 
-    def step(pulse, read_back):
-        # everything below is enqueued on one stream; nothing waits on the host unless the bins are read back
+    def step(pulse, read_back, reuse=False):
+        # everything below is enqueued on one stream; nothing waits on the host unless the bins are read back.
+        # reuse=False (the headline): RTS_NO_REUSE, every pulse is traced from scratch — ray generation, primary
+        # visibility and every bounce wave; nothing computed for an earlier pulse is used.
         eng.set_poses(*ms.poses(pulse))                      # H2D poses + device transform + refit of the movers
         spec = ms.spec_for(pulse)
         spec.ray_begin, spec.ray_count, spec.ray_stride = begin, count, stride
-        eng.trace(spec, L.RTS_OUT_BINS | L.RTS_ASYNC | (L.RTS_NO_FINALISE if world > 1 else 0))
+        eng.trace(spec, L.RTS_OUT_BINS | L.RTS_ASYNC | (0 if reuse else L.RTS_NO_REUSE) | (L.RTS_NO_FINALISE if world > 1 else 0))
         if world > 1:
             rdist.allreduce_bins(eng, dev)
         if read_back:
@@ -137,7 +140,7 @@ def run_ours(args):
             torch.distributed.barrier()
         torch.cuda.synchronize(dev)
 
-    def timed(k0, k, read_back):
+    def timed(k0, k, read_back, reuse=False):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         launches0 = eng.kernel_launches()
@@ -145,7 +148,7 @@ def run_ours(args):
         e0.record(stream)
         waves, segs, caps, d2h = [], 0, 0, 0
         for i in range(k):
-            st, bins = step(k0 + i, read_back)
+            st, bins = step(k0 + i, read_back, reuse)
             if st is not None:
                 waves.append(eng.wave_profile())
                 segs += st["segments"]
@@ -171,6 +174,12 @@ def run_ours(args):
     k0 = args.warmup
     r_dev = timed(k0, args.steps, read_back=False)
     r_e2e = timed(k0, args.steps, read_back=True)
+    # the same steps with what the library keeps between pulses of one launch geometry switched on (static primary hits,
+    # static first-reflection hits, ray directions: raster.cuh / coherent.cuh) — reported beside the headline, not as it
+    for w in range(2):
+        step(k0 + w, True, reuse=True)
+    r_dev_reuse = timed(k0, args.steps, read_back=False, reuse=True)
+    r_e2e_reuse = timed(k0, args.steps, read_back=True, reuse=True)
     clk = clocks.stop() if rank == 0 else None
 
     rays_per_step_total = ms.spec.rays                       # all ranks together
@@ -233,6 +242,13 @@ def run_ours(args):
             "roofline": roof,
             "clocks": clk,
             "msegments_per_s": round(r_e2e["segments"] * world / (r_dev["ms"] * 1e-3) / 1e6, 2),
+            "temporal_reuse": {"value": round(rays_per_step_total * args.steps / (r_dev_reuse["ms"] * 1e-3) / 1e6, 2),
+                               "e2e": round(rays_per_step_total * args.steps / (r_e2e_reuse["ms"] * 1e-3) / 1e6, 2), "unit": "Mrays/s",
+                               "ms_per_step": round(r_dev_reuse["ms"] / args.steps, 4),
+                               "waves_ms_per_step": [round(sum(w[i][0] for w in r_e2e_reuse["waves"] if len(w) > i) / max(1, len(r_e2e_reuse["waves"])), 4)
+                                                     for i in range(max((len(w) for w in r_e2e_reuse["waves"]), default=0))],
+                               "note": "same steps with hits of the static geometry kept between pulses of one launch geometry (bit-identical results); "
+                                       "value / e2e above trace every pulse from scratch (RTS_NO_REUSE)"},
         }
         if cpu is not None:
             out["cpu_baseline"] = cpu

@@ -33,6 +33,8 @@ extern "C" {
 #define RTS_NO_FINALISE   8u  /* leave bins un-finalised (caller reduces across GPUs, then rts_finalise_bins) */
 #define RTS_NO_RCS_ANGLES 16u /* records mode: skip the four atan2 per bounce, leave rcs_angle at -1e6 */
 #define RTS_ASYNC         32u /* return once the pulse is enqueued on the engine's stream; rts_sync / any getter waits */
+#define RTS_NO_REUSE      64u /* trace this pulse from scratch: use nothing kept from earlier pulses (ray directions, static
+                                 primary hits, static first-reflection hits — raster.cuh, coherent.cuh)                 */
 
 typedef struct rts_engine rts_engine;
 

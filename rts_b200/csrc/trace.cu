@@ -837,7 +837,8 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     memcpy(key.c, p.origin, sizeof(double) * 3); memcpy(key.c + 3, p.beamStart, sizeof(double) * 3);
     memcpy(key.c + 6, p.slope, sizeof(double) * 3); memcpy(key.c + 9, p.Rot, sizeof(double) * 9);
     memcpy(key.c + 18, p.Rot1, sizeof(double) * 9); memcpy(key.c + 27, p.boresight, sizeof(double) * 3);
-    const bool same_launch = e->dirs_valid && memcmp(&key, &e->dirs_key, sizeof(key)) == 0;
+    const bool reuse = !(p.flags & RTS_NO_REUSE);
+    const bool same_launch = reuse && e->dirs_valid && memcmp(&key, &e->dirs_key, sizeof(key)) == 0;
     if (!same_launch) {
         k_primary_dirs<<<e->num_sms * 16, 256, 0, st>>>(p);   // also resets the hit words
         e->dirs_key = key;
@@ -850,7 +851,7 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     // triangles of the moving targets on top of a copy.  Needs the moving-target lists of the partial refit (bvh.cu).
     uint32_t n_moving = 0;
     for (uint32_t k = 0; k < e->n_targets; k++) n_moving += e->moving[k] ? 1u : 0u;
-    const bool cacheable = single_batch && !getenv("RTS_NO_STATIC_HITS") && (n_moving == 0 || e->partial_ready);
+    const bool cacheable = reuse && single_batch && !getenv("RTS_NO_STATIC_HITS") && (n_moving == 0 || e->partial_ready);
     e->coh_on = false;
     if (cacheable) {
         const bool valid = e->static_valid && same_launch && e->static_scene_version == e->scene_version &&

@@ -20,6 +20,7 @@ RTS_COUNT_NODES = 4
 RTS_NO_FINALISE = 8
 RTS_NO_RCS_ANGLES = 16
 RTS_ASYNC = 32
+RTS_NO_REUSE = 64
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RTS_B200_LIB", os.path.join(_HERE, "librts_b200.so"))   # override: tuning builds only

@@ -510,3 +510,20 @@ def test_kept_hits_over_consecutive_pulses_match_the_oracle(engine):
         if k in (1, 2, 3, 5, 6, 7):
             assert 0 < st["kept_reflections"] < st["segments"] - st["primary_rays"]   # most, but not all: movers in the way
     assert seen_kept >= 7 and engine.bvh_info().builds >= 2
+
+
+def test_no_reuse_flag_traces_from_scratch(engine):
+    """RTS_NO_REUSE: nothing kept from earlier pulses is used (bench.py's headline legs); identical bins either way."""
+    ms = scenes.terrain_scene(n=160, cells_x=80, cells_y=40, movers=6, n_rx=2)
+    engine.set_targets(ms.base)
+    for pulse in range(4):
+        engine.set_poses(*ms.poses(pulse))
+        spec = ms.spec_for(pulse)
+        a = engine.trace(spec, L.RTS_OUT_BINS)
+        bins_a = engine.bins().copy()
+        b = engine.trace(spec, L.RTS_OUT_BINS | L.RTS_NO_REUSE)
+        bins_b = engine.bins().copy()
+        assert b["kept_reflections"] == 0 and (pulse == 0 or a["kept_reflections"] > 0)
+        for k in ("segments", "hits", "shaded_hits", "captured"):
+            assert a[k] == b[k], (pulse, k)
+        parity.assert_bins_close(parity.compare_bins(bins_a, bins_b), rtol=1e-12)
