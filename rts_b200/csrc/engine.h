@@ -138,6 +138,7 @@ struct WaveParams {
     RasterItem *raster_items;
     uint32_t raster_item_cap;
     const uint32_t *leaf_of_tri;
+    uint32_t hits_resolved;         // k_raster_resolve ran: hit words carry leaf positions (and the kept flag), not triangle ids
     // the shard's columns as a lattice of the image (nx == 1, stride divides ny): y = lat_c0 + k * stride,
     // shard-local index = z * lat_w + k - lat_g0; lat_w == 0: no lattice (general begin / stride)
     uint32_t lat_w, lat_c0;

@@ -65,8 +65,9 @@ __global__ void k_primary_dirs(const __grid_constant__ WaveParams P)
 {
     for (unsigned long long rel = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; rel < P.n_primary;
          rel += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long rayIndex = P.ray_begin + (P.batch_base + rel) * P.ray_stride;
-        const uint32_t iz = (uint32_t)(rayIndex / P.ny), iy = (uint32_t)(rayIndex % P.ny);
+        // launch indices are < 2^32 (api.cu checks the grid): 32-bit division
+        const uint32_t rayIndex = (uint32_t)(P.ray_begin + (P.batch_base + rel) * P.ray_stride);
+        const uint32_t iz = rayIndex / P.ny, iy = rayIndex - iz * P.ny;
         const d3 d = primary_direction(P, 0, iy, iz);
         P.dirs[0][rel] = d.x; P.dirs[1][rel] = d.y; P.dirs[2][rel] = d.z;
         P.hits[rel] = ~0ull;
@@ -338,9 +339,11 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_primar
         r.key = 0; r.ray = (uint32_t)(P.ray_begin + (P.batch_base + rel) * P.ray_stride);
         if (hit != ~0ull) {
             HitRec h;
-            h.pos = (int)((uint32_t)hit & 0x7fffffffu); h.t = __uint_as_float((unsigned)(hit >> 32)); h.id = 0;   // shade() takes the id from the record
+            // low word: leaf position (+ kept flag) after k_raster_resolve, or still the triangle id when that pass was skipped
+            h.pos = P.hits_resolved ? (int)((uint32_t)hit & 0x7fffffffu) : (int)P.leaf_of_tri[(uint32_t)hit];
+            h.t = __uint_as_float((unsigned)(hit >> 32)); h.id = 0;   // shade() takes the id from the record
             L.a += C_HIT;
-            shade<RECORDS>(P, r, h, L, false, ((uint32_t)hit & 0x80000000u) ? M_COH : 0u);
+            shade<RECORDS>(P, r, h, L, false, (P.hits_resolved && ((uint32_t)hit & 0x80000000u)) ? M_COH : 0u);
         } else {
             const int received = miss<RECORDS>(P, r, L);
             if (received >= 0) {

@@ -891,11 +891,14 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
         e->static_valid = false;
         launch_footprints(e, p, p.n_tris);
     }
-    k_raster_resolve<<<e->num_sms * 16, 256, 0, st>>>(p);
+    // the resolve pass exists to flag the rays whose first reflection can be answered from kept hits; without that the
+    // shading pass looks the leaf position up itself
+    p.hits_resolved = e->coh_on ? 1u : 0u;
+    if (e->coh_on) { k_raster_resolve<<<e->num_sms * 16, 256, 0, st>>>(p); e->launches++; }
     if (records) k_primary_shade<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     else k_primary_shade<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     RTS_CUDA(cudaGetLastError());
-    e->launches += 2;
+    e->launches += 1;
     return RTS_OK;
 }
 
