@@ -17,7 +17,7 @@ for r in rows[1:]:
     a[1] += float(r[vi].replace(",", ""))
 tot = sum(a[1] for a in agg.values())
 lines = [f"# ncu launch list ({tag}): python bench.py --steps 2 --warmup 1 --no-cpu-baseline",
-         "# ncu --metrics gpu__time_duration.sum --clock-control none -c 2500  (cold-cache, serialised: compare SHARES)",
+         "# ncu --metrics gpu__time_duration.sum --clock-control none -c 3000  (cold-cache, serialised: compare SHARES)",
          f"# total {tot / 1e6:.3f} ms over {sum(a[0] for a in agg.values())} launches", "ms,launches,share_pct,kernel"]
 for k, (n, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
     lines.append(f"{t / 1e6:.4f},{n},{100 * t / tot:.2f},\"{k[:120]}\"")
