@@ -211,6 +211,14 @@ def run_ours(args):
             "kernel_share_of_step": round(avg_ms / (r_e2e["ms"] / args.steps), 4),
             "waves_ms_per_step": [round(x, 4) for x in per_wave_ms],
             "all_waves_ms_per_step": round(sum(all_ms) / max(1, len(all_ms)), 4)}
+    if rank == 0:
+        # the same numerator against measured L2 bandwidth, because the nodes and triangle records a
+        # wave touches are served by L1/L2, not by HBM (the measured DRAM bytes are in `traffic`)
+        l2 = eng.probe_read_bandwidth(48 << 20, 100)
+        hbm_rd = eng.probe_read_bandwidth(2 << 30, 3)
+        roof["l2"] = {"peak": round(l2, 1), "frac": round(achieved / l2, 4), "unit": "GB/s", "hbm_read_same_kernel": round(hbm_rd, 1),
+                      "peak_source": "measured in this run (rts_probe_read_bandwidth): 128-bit L1-bypassing loads over an L2-resident 48 MB buffer; "
+                                     "hbm_read_same_kernel = the same kernel over 2 GB"}
     prof = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(prof):
         try:

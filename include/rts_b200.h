@@ -126,6 +126,10 @@ int rts_get_stats(rts_engine *e, rts_stats *out);
 int rts_get_wave_profile(rts_engine *e, uint32_t cap, float *ms, uint64_t *segments, uint32_t *n);
 /* Cumulative number of CUDA kernels this engine has launched (every <<<>>> of the library). */
 int rts_kernel_launches(rts_engine *e, uint64_t *out);
+/* Measurement aid (bench.py roofline): read bandwidth in GB/s of a `bytes`-sized device buffer streamed
+ * `reps` times with 128-bit loads that bypass L1 — L2 bandwidth when the buffer fits the 126 MB L2, HBM bandwidth
+ * when it is several times larger.  Blocks until the measurement is done. */
+int rts_probe_read_bandwidth(rts_engine *e, uint64_t bytes, uint32_t reps, double *gbs);
 /* RTS_OUT_BINS: non-empty bins sorted by (rx, path). *n is the total even when cap is smaller. */
 int rts_get_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n);
 /* RTS_OUT_BINS: the responses the reference would emit for this pulse (ray_tracer.cpp:1289-1320): one per

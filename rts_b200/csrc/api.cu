@@ -688,6 +688,55 @@ extern "C" int rts_kernel_launches(rts_engine *e, uint64_t *out)
     return RTS_OK;
 }
 
+// Read bandwidth of a buffer that stays resident in L2: every CTA streams the whole buffer `reps` times with 128-bit
+// loads (the access width of the node and triangle fetches), so after the first pass all sectors are L2 hits.
+__global__ void __launch_bounds__(512) k_probe_read(const uint4 *__restrict__ buf, size_t n16, uint32_t reps, uint32_t *sink)
+{
+    uint32_t acc = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (uint32_t r = 0; r < reps; r++)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i + 3 * stride < n16; i += 4 * stride) {
+            uint4 a, b, c, d;    // ld.global.cg: cached in L2 only, so the figure is L2 -> SM bandwidth, not L1 hits
+            asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(buf + i));
+            asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(buf + i + stride));
+            asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(buf + i + 2 * stride));
+            asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(d.x), "=r"(d.y), "=r"(d.z), "=r"(d.w) : "l"(buf + i + 3 * stride));
+            acc ^= a.x ^ a.y ^ a.z ^ a.w ^ b.x ^ b.y ^ b.z ^ b.w ^ c.x ^ c.y ^ c.z ^ c.w ^ d.x ^ d.y ^ d.z ^ d.w;
+        }
+    if (acc == 0x9e3779b9u) *sink = acc;     // keeps the loads alive
+}
+
+extern "C" int rts_probe_read_bandwidth(rts_engine *e, uint64_t bytes, uint32_t reps, double *gbs)
+{
+    if (!e || !gbs || bytes < (1u << 20) || reps == 0) return rts_fail(RTS_ERR_ARG, "bad argument");
+    RTS_CUDA(cudaSetDevice(e->device));
+    int sms = 0;
+    RTS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, e->device));
+    const unsigned grid = (unsigned)sms * 4u, block = 512u;
+    const size_t quantum = (size_t)grid * block * 4u * 16u;        // whole unrolled iterations only
+    const size_t n = std::max<size_t>(1, bytes / quantum) * quantum;
+    void *buf = nullptr;
+    uint32_t *sink = nullptr;
+    RTS_CUDA(cudaMalloc(&buf, n + quantum));
+    RTS_CUDA(cudaMalloc(&sink, 4));
+    RTS_CUDA(cudaMemsetAsync(buf, 1, n + quantum, e->stream));
+    cudaEvent_t a, b;
+    RTS_CUDA(cudaEventCreate(&a));
+    RTS_CUDA(cudaEventCreate(&b));
+    k_probe_read<<<grid, block, 0, e->stream>>>((const uint4 *)buf, n / 16 + 1, 2, sink);      // warm L2
+    RTS_CUDA(cudaEventRecord(a, e->stream));
+    k_probe_read<<<grid, block, 0, e->stream>>>((const uint4 *)buf, n / 16 + 1, reps, sink);
+    RTS_CUDA(cudaEventRecord(b, e->stream));
+    e->launches += 2;
+    RTS_CUDA(cudaEventSynchronize(b));
+    float ms = 0.f;
+    RTS_CUDA(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(buf); cudaFree(sink);
+    *gbs = (double)n * reps / (ms * 1e-3) / 1e9;
+    return RTS_OK;
+}
+
 extern "C" int rts_get_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
 {
     if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");

@@ -229,15 +229,18 @@ __global__ void k_raster_setup(const __grid_constant__ WaveParams P)
             if (area > RTS_RASTER_SMALL) {
                 const unsigned per_row = (unsigned)((F.y1 - F.y0) / F.ystep + 1);
                 const unsigned rows = max(1u, RTS_RASTER_CHUNK / per_row);
-                for (int z = F.z0; z <= F.z1; z += (int)rows) {
-                    const unsigned at = atomicAdd(&P.raster_ctl->n_items, 1u);
-                    if (at < P.raster_item_cap) {
+                // one reservation for all of the footprint's chunks (a triangle that fills the image has thousands:
+                // an atomic per chunk would serialise them on one thread), then independent stores
+                const unsigned n_chunks = (unsigned)(F.z1 - F.z0) / rows + 1u;
+                const unsigned at = atomicAdd(&P.raster_ctl->n_items, n_chunks);
+                if (at < P.raster_item_cap && n_chunks <= P.raster_item_cap - at) {
+                    for (unsigned c = 0; c < n_chunks; c++) {
+                        const int z = F.z0 + (int)(c * rows);
                         RasterItem it; it.pos = pos; it.z0 = (unsigned)z; it.z1 = (unsigned)min(F.z1, z + (int)rows - 1); it.pad = 0;
-                        P.raster_items[at] = it;
-                    } else {
-                        area = 1ull << 56;   // too many chunks: turn the path off
-                        break;
+                        P.raster_items[at + c] = it;
                     }
+                } else {
+                    area = 1ull << 56;   // too many chunks: turn the path off
                 }
             }
         }

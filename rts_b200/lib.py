@@ -51,7 +51,7 @@ EXPORTS = [
     "rts_rx_sphere_from_desc", "rts_result_sizes", "rts_rect_mesh", "rts_sphere_mesh", "rts_file_mesh",
     "rts_rotation_matrix", "rts_scene_set_targets", "rts_scene_set_poses", "rts_scene_rebuild", "rts_scene_bvh_info",
     "rts_scene_get_world_vertices", "rts_scene_get_tri_bounds", "rts_scene_check_bvh", "rts_trace_pulse",
-    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_kernel_launches", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_get_received", "rts_bins_device", "rts_finalise_bins", "rts_aggregate",
+    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_kernel_launches", "rts_probe_read_bandwidth", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_get_received", "rts_bins_device", "rts_finalise_bins", "rts_aggregate",
 ]
 
 _lib = None
@@ -95,6 +95,7 @@ def load() -> C.CDLL:
     lib.rts_get_stats.argtypes = [vp, P(RtsStats)]
     lib.rts_get_wave_profile.argtypes = [vp, u32, P(C.c_float), P(u64), P(u32)]
     lib.rts_kernel_launches.argtypes = [vp, P(u64)]
+    lib.rts_probe_read_bandwidth.argtypes = [vp, u64, u32, P(dbl)]
     lib.rts_get_bins.argtypes = [vp, P(RtsBin), u32, P(u32)]
     lib.rts_get_responses.argtypes = [vp, P(RtsResponse), u32, P(u32)]
     lib.rts_get_records.argtypes = [vp, vp, P(i32), P(dbl), P(i32)]
@@ -259,6 +260,12 @@ class Engine:
         v = C.c_uint64()
         _check(self._lib.rts_kernel_launches(self._h, C.byref(v)))
         return int(v.value)
+
+    def probe_read_bandwidth(self, nbytes: int, reps: int = 50) -> float:
+        """GB/s of 128-bit loads over a buffer of nbytes streamed reps times (L2-resident below ~100 MB)."""
+        v = C.c_double()
+        _check(self._lib.rts_probe_read_bandwidth(self._h, nbytes, reps, C.byref(v)))
+        return float(v.value)
 
     def bins(self) -> np.ndarray:
         n = C.c_uint32()
