@@ -58,7 +58,7 @@ struct RayQueue {
 struct RasterCtl {
     unsigned long long area;   // summed footprint (candidate ray/triangle pairs) of this batch
     unsigned n_items;          // row chunks of large footprints
-    unsigned pad;
+    unsigned next_item;        // work counter of k_raster_big (chunks are taken dynamically: their sizes differ a lot)
 };
 struct RasterItem { unsigned pos, z0, z1, pad; };
 

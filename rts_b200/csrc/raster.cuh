@@ -279,8 +279,11 @@ __global__ void k_raster_big(const __grid_constant__ WaveParams P)
     if (!raster_on(P)) return;
     const unsigned n_items = min(P.raster_ctl->n_items, P.raster_item_cap);
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (unsigned it = warp; it < n_items; it += n_warps) {
+    for (;;) {
+        unsigned it = 0;
+        if (lane == 0) it = atomicAdd(&P.raster_ctl->next_item, 1u);
+        it = __shfl_sync(0xffffffffu, it, 0);
+        if (it >= n_items) break;
         const RasterItem I = P.raster_items[it];
         TriFoot F;
         if (!tri_footprint(P, I.pos, F)) continue;
