@@ -68,6 +68,7 @@ def compare_bins(gbins, obins, rtol=SUM_RTOL):
         denom = np.maximum(np.abs(b), 1e-300)
         rel = np.abs(a - b) / denom
         rel = np.where((a == 0) & (b == 0), 0.0, rel)
+        rel = np.where(np.isnan(a) & np.isnan(b), 0.0, rel)    # sqrt of a negative power (negative reflection coefficient) on both sides
         out[f + "_max_rel"] = float(rel.max()) if len(rel) else 0.0
     return out
 
