@@ -242,10 +242,15 @@ static Hit closest_bvh(const Scene &s, const RayF &ray, const D3 &o, const D3 &d
         const BvhNode &nd = s.nodes[stack[--sp]];
         // slab test in fp64, padded generously (conservative: never prunes a box the exact
         // triangle test could accept; NaN from 0*inf is ignored by fmin/fmax)
+        // The box is first grown by delta = 1e-12 * (|box| + |o|) per axis: the fp64 triangle test accepts hits a few
+        // ulps outside the exact triangle (a ray running along the shared edge of two triangles, d.y ~ 1e-17), and
+        // a box that ends exactly on that edge must not prune them — exhaustive search is the truth this mode has
+        // to reproduce (tests/test_oracle_bvh.py).
         double tn = -INFINITY, tf = INFINITY;
         for (int a = 0; a < 3; a++) {
-            double t0 = (nd.lo[a] - oo[a]) * inv[a];
-            double t1 = (nd.hi[a] - oo[a]) * inv[a];
+            const double delta = 1e-12 * (fmax(fabs(nd.lo[a]), fabs(nd.hi[a])) + fabs(oo[a])) + 1e-300;
+            double t0 = ((nd.lo[a] - delta) - oo[a]) * inv[a];
+            double t1 = ((nd.hi[a] + delta) - oo[a]) * inv[a];
             tn = fmax(tn, fmin(fmin(t0, t1), INFINITY));
             tf = fmin(tf, fmax(fmax(t0, t1), -INFINITY));
         }

@@ -78,3 +78,26 @@ def test_random_soups_match_the_exhaustive_oracle(engine, seed):
             del os.environ["RTS_NO_RASTER"]
         parity.assert_records_equal(parity.compare_records(recs2, orc, spec, f"fuzz/{seed}/bvh"))
         assert st2["primary_projected"] == 0 and st["primary_projected"] == 1
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_moving_scenes_with_between_pulse_reuse(engine, seed):
+    """Terrain + movers from different PRNG seeds, pulses visited out of order and repeated, with the library's default
+    between-pulse reuse (kept static hits and first reflections, partial refit): every pulse equals the oracle run on
+    that pulse's world-space meshes."""
+    rng = np.random.default_rng(77 + seed)
+    ms = scenes.terrain_scene(n=int(rng.integers(72, 120)), cells_x=int(rng.integers(24, 64)), cells_y=int(rng.integers(12, 32)),
+                              movers=int(rng.integers(1, 9)), n_rx=int(rng.integers(1, 4)), seed=0x52545301 + 17 * seed)
+    engine.set_targets(ms.base)
+    order = [0, 1, 1, 4, 2, 2, 7, 3]
+    for i, p in enumerate(order):
+        engine.set_poses(*ms.poses(p))
+        spec = ms.spec_for(p)
+        flags = L.RTS_OUT_BINS | (L.RTS_ASYNC if i % 2 else 0)
+        engine.trace(spec, flags)
+        st = engine.stats()
+        obins, ost = O.trace_bins(ms.world_targets(p), spec, use_bvh=True)
+        for k in ("segments", "hits", "shaded_hits", "captured"):
+            assert st[k] == ost[k], (seed, i, p, k, st[k], ost[k])
+        parity.assert_bins_close(parity.compare_bins(engine.bins(), obins))
+    assert engine.check_bvh() == 0

@@ -46,3 +46,16 @@ def test_sharded_trace_covers_the_same_rays():
         assert np.array_equal(full["results"][f][sel], part["results"][f][sel])
     assert part["stats"]["primary_rays"] == 700
     assert (part["results"]["reflDepth"][:500] == 0).all() and (part["tri_path"][:500] == -1).all()
+
+
+def test_bvh_keeps_rays_that_run_along_a_shared_triangle_edge():
+    """An odd launch grid puts one column of rays in the plane y = 0 (d.y ~ 1e-17), which is a cell boundary of the
+    terrain: the fp64 triangle test accepts hits there by a rounding error's margin, and node boxes that end exactly on
+    y = 0 used to prune them (found by tests/test_gpu_fuzz.py, where the GPU agreed with exhaustive search)."""
+    ms = scenes.terrain_scene(n=115, cells_x=47, cells_y=24, movers=3, n_rx=2, seed=0x52545301 + 51)
+    targets, spec = ms.world_targets(0), ms.spec_for(0)
+    a = O.trace(targets, spec, use_bvh=False)
+    b = O.trace(targets, spec, use_bvh=True)
+    _same_rays(a, b, spec, np.arange(spec.rays))
+    for k in ("segments", "hits", "shaded_hits", "captured"):
+        assert a["stats"][k] == b["stats"][k], k
