@@ -519,7 +519,9 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     }
 
     // queues: a batch of primaries and up to three live chains per primary with refraction
-    const uint64_t batch = std::min<uint64_t>(n_primary_total ? n_primary_total : 1, 1ull << 24);
+    uint64_t batch_max = 1ull << 24;
+    if (const char *b = getenv("RTS_BATCH")) { const long long v = atoll(b); if (v >= 32 && v <= (1ll << 24)) batch_max = (uint64_t)v; }   // tests: batching at small sizes
+    const uint64_t batch = std::min<uint64_t>(n_primary_total ? n_primary_total : 1, batch_max);
     const uint64_t cap = batch * (rMax ? 3 : 1);
     {
         int rc = trace_alloc_queues(e, cap);
@@ -559,7 +561,10 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     // primary-ray tiling (trace.cu: k_wave): with nx == 1 the shard-local index space is a (y,z) plane whose rows
     // hold ny/stride of this shard's rays; whole bands of four rows are walked in 8x4 tiles
     P.swz_w = 0; P.swz_limit = 0;
-    if (p->nx == 1 && !getenv("RTS_NO_TILES") && p->ny % stride == 0 && (p->ny / stride) % 8 == 0 && (p->ny / stride) >= 8) {
+    // Not when the projected primary wave is on: its batches take their rays in index order, and a batch whose guard
+    // trips falls back to k_wave<PRIMARY> — which must then cover exactly that batch's indices, not a tile permutation
+    // of them that reaches into the neighbouring batches (found by tests/test_gpu_fuzz.py with RTS_BATCH).
+    if (!use_raster && p->nx == 1 && !getenv("RTS_NO_TILES") && p->ny % stride == 0 && (p->ny / stride) % 8 == 0 && (p->ny / stride) >= 8) {
         P.swz_w = (uint32_t)(p->ny / stride);
         P.swz_limit = n_primary_total / (4ull * P.swz_w) * (4ull * P.swz_w);
     }

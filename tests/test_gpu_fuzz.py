@@ -78,6 +78,16 @@ def test_random_soups_match_the_exhaustive_oracle(engine, seed):
             del os.environ["RTS_NO_RASTER"]
         parity.assert_records_equal(parity.compare_records(recs2, orc, spec, f"fuzz/{seed}/bvh"))
         assert st2["primary_projected"] == 0 and st["primary_projected"] == 1
+    # the launch cut into batches of an odd size (RTS_BATCH: the 2^24-ray batching of large launches at test size)
+    import os
+    os.environ["RTS_BATCH"] = str(257 + 64 * seed)
+    try:
+        recs3, gbins3, st3 = parity.run_gpu_records(engine, targets, spec)
+    finally:
+        del os.environ["RTS_BATCH"]
+    parity.assert_records_equal(parity.compare_records(recs3, orc, spec, f"fuzz/{seed}/batched"))
+    parity.assert_bins_close(parity.compare_bins(gbins3, obins))
+    assert st3["segments"] == st["segments"] and st3["hits"] == st["hits"]
 
 
 @pytest.mark.parametrize("seed", range(6))
