@@ -111,3 +111,44 @@ def test_random_moving_scenes_with_between_pulse_reuse(engine, seed):
             assert st[k] == ost[k], (seed, i, p, k, st[k], ost[k])
         parity.assert_bins_close(parity.compare_bins(engine.bins(), obins))
     assert engine.check_bvh() == 0
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_shards_builders_and_changing_launches(seed, monkeypatch):
+    """Random ray shards (begin / count / stride), forced topology builders and leaf sizes, and a transmitter that moves
+    between pulses (so everything kept between pulses must be dropped): records and bins equal the oracle's for the
+    same shard."""
+    rng = np.random.default_rng(5000 + seed)
+    monkeypatch.setenv("RTS_BVH", ["lbvh", "ploc"][seed % 2])
+    monkeypatch.setenv("RTS_LEAF_MAX", str(int(rng.integers(1, 5))))
+    targets, spec = _case(100 + seed)
+    with L.Engine(0) as eng:
+        eng.set_targets(targets)
+        for pulse in range(3):
+            s = PulseSpec(**{**spec.__dict__})
+            s.ray_begin = int(rng.integers(0, spec.rays // 2))
+            s.ray_count = int(rng.integers(0, spec.rays // 2)) if pulse != 1 else 0
+            s.ray_stride = int(rng.choice([0, 1, 2, 3, 5, 8]))
+            if pulse:
+                s.tx_origin = tuple(np.asarray(spec.tx_origin) + rng.normal(0, 3.0, 3))
+                s.tx_dir = (spec.tx_dir[0] + float(rng.normal(0, 0.05)), spec.tx_dir[1] + float(rng.normal(0, 0.05)))
+            orc = O.trace(targets, s, use_bvh=False)
+            st = eng.trace(s, L.RTS_OUT_RECORDS | L.RTS_OUT_BINS)
+            recs = eng.records()
+            # rays outside the shard keep each side's buffer defaults: compare the shard's own result slots
+            stride = max(1, s.ray_stride)
+            end = min(s.rays, s.ray_begin + s.ray_count) if s.ray_count else s.rays
+            sel = np.arange(s.ray_begin, end, stride)
+            rows = np.concatenate([sel + k * s.rays for k in range(s.slots)])
+            sub = PulseSpec(**{**s.__dict__})
+            sub.grid = (1, 1, len(sel))
+            orc_sel = {"edge": orc["edge"][sel], "results": orc["results"][rows], "tri_path": orc["tri_path"][rows],
+                       "targ_intersect": orc["targ_intersect"][rows], "rcs_angle": orc["rcs_angle"][rows]}
+            recs_sel = (recs[0][rows], recs[1][rows], recs[2][rows] if recs[2] is not None else None, recs[3][rows])
+            assert len(sel) == st["primary_rays"]
+            parity.assert_records_equal(parity.compare_records(recs_sel, orc_sel, sub, f"shards/{seed}/{pulse}"))
+            for k in ("primary_rays", "segments", "hits", "shaded_hits", "refracted"):
+                assert st[k] == orc["stats"][k], (k, st[k], orc["stats"][k])
+            obins, _ = O.trace_bins(targets, s, use_bvh=False)
+            parity.assert_bins_close(parity.compare_bins(eng.bins(), obins))
+            assert eng.check_bvh() == 0
