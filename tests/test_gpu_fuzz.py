@@ -190,3 +190,40 @@ def test_random_rigid_motion_of_soups(seed):
             obins, _ = O.trace_bins(world, s, use_bvh=False)
             parity.assert_bins_close(parity.compare_bins(eng.bins(), obins))
             assert eng.check_bvh() == 0
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_random_post_process_and_responses(engine, seed):
+    """Per-target RCS and antenna gains on random soups: the fused bins / rts_get_responses, the two-phase path
+    (rts_get_received -> host callbacks -> rts_aggregate) and the oracle's literal host flow (post-process, O(R^2)
+    aggregation, sort + unique: ray_tracer.cpp:1190-1320) all give the same responses."""
+    rng = np.random.default_rng(4000 + seed)
+    targets, spec = _case(300 + seed)
+    for t in targets:                                   # powers stay positive so that sqrt(P) and the comparisons are meaningful
+        t.refl_coeff = abs(t.refl_coeff) if t.refl_coeff != 0 else 0.5
+    spec.targ_rcs = rng.uniform(0.2, 9.0, len(targets))
+    spec.gain_tx, spec.gain_rx = float(rng.uniform(1, 40)), float(rng.uniform(1, 40))
+    engine.set_targets(targets)
+    engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_OUT_BINS)
+    gbins, got = engine.bins(), engine.responses()
+    obins, _ = O.trace_bins(targets, spec, use_bvh=False)
+    parity.assert_bins_close(parity.compare_bins(gbins, obins))
+    r = O.trace(targets, spec, use_bvh=False)
+    rx_res, rx_rows, rx_slots = O.postprocess(r["results"], r["targ_intersect"], spec, rcs_per_target=spec.targ_rcs,
+                                              gain=spec.gain_tx * spec.gain_rx)
+    if len(rx_res) == 0:
+        assert len(got) == 0 and len(gbins) == 0
+        return
+    want = O.responses(O.aggregate(rx_res, rx_rows, spec, literal=True), rx_slots)
+    assert len(got) == len(want)
+    assert np.array_equal(got["rx"], want["rx"]) and np.array_equal(got["slot"], want["slot"])
+    for f in ("power", "delay", "doppler", "phase"):
+        assert np.allclose(got[f], want[f], rtol=1e-5, atol=1e-300), f
+    # two-phase: the received rays compacted on the device, the callbacks on the host, the aggregation on the device
+    d_res, d_ti, _, d_slots = engine.received()
+    assert np.array_equal(d_slots, rx_slots.astype(np.uint64))
+    a = engine.aggregate(rx_res, rx_rows, spec.cspeed, spec.carrier, ray_total=spec.ray_total)
+    two = O.responses(a, rx_slots)
+    assert np.array_equal(two["slot"], want["slot"])
+    for f in ("power", "delay", "doppler", "phase"):
+        assert np.allclose(two[f], want[f], rtol=1e-5, atol=1e-300), f
