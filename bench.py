@@ -33,6 +33,8 @@ sys.path.insert(0, ROOT)
 N_GRID = 4096
 B_SEG_1M = 1632.0          # algorithmic bytes per traced segment, T = 1M (SURVEY.md §8d / BASELINE.md §3)
 B_CAPTURE = 40.0           # five fp64 bin updates per captured ray
+WORKLOAD = ("C4: 1,000,000-triangle terrain + 16 moving targets, per-pulse pose update + BVH refit, "
+            f"(1,{N_GRID},{N_GRID}) rays per GPU per pulse, maxRefl=3, 1 Rx, fused bins")
 
 
 def log(*a):
@@ -237,8 +239,7 @@ def run_ours(args):
             "metric": "Mrays/s (3-bounce, 1M-tri scene)", "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(r_dev["ms"] / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C4: 1,000,000-triangle terrain + 16 moving targets, per-pulse pose update + BVH refit, "
-                                   f"(1,{N_GRID},{N_GRID}) rays per GPU per pulse, maxRefl=3, 1 Rx, fused bins"
+            "config": {"workload": WORKLOAD
                                    + (f", launch grid (1,{N_GRID * world},{N_GRID}) ray-sharded round-robin, NCCL all-reduce of bins" if world > 1 else ""),
                        "triangles": int(sum(len(t.tris) for t in ms.base)), "rays_per_step": int(rays_per_step_total),
                        "segments_per_ray": round(seg_per_ray, 4), "captured_per_step": int(r_e2e["captured"] / args.steps),
@@ -292,7 +293,17 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_api as O
     ms = build_scene(1)
-    stride = args.cpu_stride or 4
+    stride = args.cpu_stride
+    if not stride:
+        # bounded sample: a probe step at stride 16 gives the host's rate; the stride of the run is then chosen so that
+        # all warm-up + timed steps together take about 100 s of oracle time, whatever K, W and the core count are
+        spec = ms.spec_for(0)
+        spec.ray_begin, spec.ray_count, spec.ray_stride = 0, N_GRID * N_GRID, 16
+        _, st = O.trace_bins(ms.world_targets(0), spec, use_bvh=True)
+        rate = st["primary_rays"] / (st["ms_trace"] * 1e-3)
+        want = N_GRID * N_GRID * (args.warmup + args.steps) / (rate * 100.0)
+        stride = int(min(64, max(2, -(-want // 1))))
+        log(f"[bench] reference arm: {rate / 1e6:.2f} Mrays/s on the probe step -> every {stride}th ray per step")
     total_rays, total_s, per = 0, 0.0, []
     for i in range(args.warmup + args.steps):
         pulse = i
@@ -309,7 +320,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "Mrays/s (3-bounce, 1M-tri scene)", "value": round(v, 4), "unit": "Mrays/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(sum(per) / len(per), 2), "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "C4: 1,000,000-triangle terrain + 16 moving targets, maxRefl=3, 1 Rx (CPU oracle, bounded sample)"},
+           "config": {"workload": WORKLOAD, "triangles": int(sum(len(t.tris) for t in ms.base)), "rays_per_step": N_GRID * N_GRID,
+                      "reference_arm": "CPU oracle port (OpenMP, oracle BVH rebuilt for every pulse's poses), bounded sample: " + sample},
            "cpu_baseline": {"value": round(v, 4), "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
            "e2e": {"value": round(v, 4), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out), flush=True)
@@ -321,7 +333,7 @@ def main():
     ap.add_argument("--steps", type=int, default=128)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--cpu-stride", type=int, default=0, help="oracle sample: every n-th primary ray (0 = 1 for cpu_baseline, 4 for --impl reference)")
+    ap.add_argument("--cpu-stride", type=int, default=0, help="oracle sample: every n-th primary ray (0 = 1 for cpu_baseline; for --impl reference 0 = chosen so that the run takes about 100 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
