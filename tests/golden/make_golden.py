@@ -15,7 +15,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import oracle_api as O  # noqa: E402
 from test_oracle_reference import CASES  # noqa: E402
 
-SIZES = {"plate": 8, "plate_refl2": 6, "trihedral": 8, "trihedral_refl1": 6, "slab": 6, "slab_interp_n13": 6, "slab_thin_refl0": 5}
+SIZES = {"plate": 8, "plate_refl2": 6, "trihedral": 8, "trihedral_refl1": 6, "slab": 6, "slab_interp_n13": 6, "slab_thin_refl0": 5,
+         "soup_1": 7, "soup_4": 8, "soup_18": 7}
 
 if __name__ == "__main__":
     assert O.have_ref(), "build oracle/_ref first: make -C oracle ref"

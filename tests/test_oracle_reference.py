@@ -12,6 +12,7 @@ import numpy as np
 import pytest
 
 import oracle_api as O
+import soups
 from rts_b200 import scenes
 from rts_b200.abi import RAY_RECORD
 
@@ -25,6 +26,10 @@ CASES = {
     "slab": lambda n: scenes.slab(n=n, cubic=True),
     "slab_interp_n13": lambda n: scenes.slab(n=n, cubic=True, interpolate=True, refr_index=1.3, max_refl=3),
     "slab_thin_refl0": lambda n: scenes.slab(n=n, cubic=True, thickness=0.004, max_refl=1),
+    # random triangle soups (tests/soups.py): several targets, mixed materials and normal conventions, moving targets
+    "soup_1": lambda n: soups.case(1, cubic_n=n),      # refraction, 4 targets
+    "soup_4": lambda n: soups.case(4, cubic_n=n),      # smooth shading, reflections only
+    "soup_18": lambda n: soups.case(18, cubic_n=n),    # refraction + smooth shading
 }
 
 
@@ -51,6 +56,18 @@ def test_oracle_matches_reference_sources(name):
     a, b = O.trace(targets, spec), O.ref_trace(targets, spec)
     _same(a, b)
     assert a["stats"]["segments"] == b["segments"]
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/libref_rts.so not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", range(20))
+def test_oracle_matches_reference_sources_on_random_soups(seed):
+    """The restatement against the reference's own programs on inputs nobody arranged: random triangle soups."""
+    targets, spec = soups.case(seed, cubic_n=8 + seed % 3)
+    a, b = O.trace(targets, spec, use_bvh=False), O.ref_trace(targets, spec)
+    _same(a, b)
+    assert a["stats"]["segments"] == b["segments"]
+    c = O.trace(targets, spec, use_bvh=True)            # and the oracle's BVH mode against both
+    _same(c, b)
 
 
 @pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref/libref_rts.so not built (needs /root/reference)")
