@@ -64,3 +64,10 @@ if later:
     out["k_wave_later_dram_bytes_per_launch"] = gb(later[0]["dram__bytes_read.sum"]) + gb(later[0]["dram__bytes_write.sum"])
 json.dump(out, open(os.path.join(out_dir, "r01_traffic.json"), "w"))
 print(out)
+# ---- one from-scratch step, kernel by kernel (the nine launches of the full capture are the traced part of one step):
+# the share of the step the roofline kernel takes, to set beside bench.py's roofline.kernel_share_of_step
+step = [(d["Kernel Name"], float(d["gpu__time_duration.sum"].split()[0]) * {"ms": 1.0, "us": 1e-3, "s": 1e3}[d["gpu__time_duration.sum"].split()[1]]) for d in summ]
+tot_step = sum(t for _, t in step)
+json.dump({"source": "the nine consecutive launches of the ncu --set full capture = every wave / projection kernel of one from-scratch step (pose update, refit and bin emission, ~0.15 ms, not captured)",
+           "total_ms": round(tot_step, 4), "kernels": [{"kernel": k, "ms": round(t, 4), "share_pct": round(100 * t / tot_step, 2)} for k, t in step]},
+          open(os.path.join(out_dir, f"{tag}_step_breakdown.json"), "w"), indent=1)
