@@ -93,7 +93,7 @@ extern "C" int rts_create(int device, rts_engine **out)
     }
     memset(e->h_rb, 0, sizeof(Readback));
     cudaMalloc(&e->d_wave_segs, sizeof(unsigned long long) * 32);
-    cudaMalloc(&e->d_counts, sizeof(unsigned long long) * 64);
+    cudaMalloc(&e->d_counts, sizeof(unsigned long long) * 96);
     cudaMalloc(&e->d_counters, sizeof(Counters));
     cudaMalloc(&e->d_rx, sizeof(RxDev) * RTS_MAX_RX);
     *out = e;
@@ -573,14 +573,15 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     memset(&kept_params, 0, sizeof(kept_params));
     for (uint64_t done = 0; done < n_primary_total; done += batch) {
         const uint64_t nb = std::min<uint64_t>(batch, n_primary_total - done);
-        // d_counts: [0..31] queue counts per wave, [32..63] work counters per wave
-        RTS_CUDA(cudaMemsetAsync(e->d_counts, 0, sizeof(unsigned long long) * 64, st));
+        // d_counts: [0..31] queue counts per wave, [32..63] work counters per wave, [64..95] queue counts from the far end
+        RTS_CUDA(cudaMemsetAsync(e->d_counts, 0, sizeof(unsigned long long) * 96, st));
         for (uint32_t w = 0; w < max_waves && w < 31; w++) {
             WaveParams Q = P;
             Q.ray_begin = begin; Q.ray_stride = stride; Q.n_primary = nb; Q.batch_base = done;
             Q.in = e->q[w & 1]; Q.out = e->q[(w + 1) & 1];
             Q.in_count = e->d_counts + w;
             Q.out_count = e->d_counts + w + 1;
+            if (rMax && !getenv("RTS_ONE_ENDED_QUEUE")) { Q.in_back = e->d_counts + 64 + w; Q.out_back = e->d_counts + 64 + w + 1; }
             Q.work_counter = e->d_counts + 32 + w;
             Q.wave_index = w;
             if (single_batch) cudaEventRecord(e->wave_ev[w], st);

@@ -136,7 +136,8 @@ __device__ __forceinline__ bool near_movers(const WaveParams &P, const d3 &o, co
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_WAVE_MIN_BLOCKS) k_wave1_fill(const __grid_constant__ WaveParams P)
 {
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned n_in = (unsigned)*P.in_count;
+    const unsigned n_front = (unsigned)*P.in_count;
+    const unsigned n_in = n_front + (P.in_back ? (unsigned)*P.in_back : 0u);
     unsigned *work = reinterpret_cast<unsigned *>(P.fill_counter);
     unsigned ovf = 0;
     for (;;) {
@@ -144,8 +145,8 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_WAVE_MIN_BLOCKS) k_wave1_f
         if (lane == 0) base = atomicAdd(work, 32u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= n_in) break;
-        const unsigned idx = base + lane;
-        if (idx >= n_in) continue;
+        if (base + lane >= n_in) continue;
+        const unsigned idx = queue_slot(P, base + lane, n_front);
         Ray r;
         load_ray_geom(P.in, idx, r);
         if (!(r.meta & M_COH)) continue;
@@ -163,11 +164,13 @@ template <bool RECORDS>
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_wave1_kept(const __grid_constant__ WaveParams P)
 {
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned n_in = (unsigned)*P.in_count;
+    const unsigned n_front = (unsigned)*P.in_count;
+    const unsigned n_in = n_front + (P.in_back ? (unsigned)*P.in_back : 0u);
     Local L = {0, 0, 0, 0, 0};
     unsigned served = 0;
     const unsigned stride = gridDim.x * blockDim.x;
-    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_in; idx += stride) {
+    for (unsigned entry = blockIdx.x * blockDim.x + threadIdx.x; entry < n_in; entry += stride) {
+        const unsigned idx = queue_slot(P, entry, n_front);
         Ray r;
         r.meta = __ldcs(P.in.meta + idx);
         bool mine = (r.meta & M_COH) != 0;

@@ -115,6 +115,11 @@ struct WaveParams {
     RayQueue in, out;
     const unsigned long long *in_count;
     unsigned long long *out_count;
+    // With refraction the queue is filled from both ends: reflected rays from slot 0 upwards (in_count / out_count),
+    // refracted children from slot capacity-1 downwards (in_back / out_back), so that a warp of the next wave holds one
+    // kind of ray.  Entry i of the wave is slot i for i < *in_count, else slot capacity-1-(i-*in_count).  nullptr: one end.
+    const unsigned long long *in_back;
+    unsigned long long *out_back;
     unsigned long long out_capacity;
     unsigned long long *work_counter;
     // outputs
@@ -248,7 +253,7 @@ struct rts_engine {
     RayQueue q[2] = {};
     void *q_slab[2] = {nullptr, nullptr};
     uint64_t q_capacity = 0;
-    unsigned long long *d_counts = nullptr;   // [64] queue counts + work counters
+    unsigned long long *d_counts = nullptr;   // [96] queue counts (front), work counters, queue counts (back)
     Counters *d_counters = nullptr;
     RxDev *d_rx = nullptr;
     int wave_grid = 0, wave_grid_primary = 0;

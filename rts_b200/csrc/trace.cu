@@ -91,6 +91,23 @@ __device__ __forceinline__ void push_ray(const WaveParams &P, const Ray &r, unsi
     else overflow++;
 }
 
+// The same from the far end of the queue (refracted children when the queue is filled from both ends).
+__device__ __forceinline__ void push_ray_back(const WaveParams &P, const Ray &r, unsigned &overflow)
+{
+    cg::coalesced_group g = cg::coalesced_threads();
+    unsigned long long base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(P.out_back, (unsigned long long)g.size());
+    base = g.shfl(base, 0);
+    const unsigned long long i = base + g.thread_rank();
+    if (i < P.out_capacity) store_ray(P.out, P.out_capacity - 1ull - i, r, (P.flags & RTS_OUT_RECORDS) != 0, P.rMax != 0);
+    else overflow++;
+}
+// Slot of entry i of the incoming wave (see WaveParams::in_back).
+__device__ __forceinline__ unsigned queue_slot(const WaveParams &P, unsigned i, unsigned n_front)
+{
+    return i < n_front ? i : (unsigned)P.out_capacity - 1u - (i - n_front);
+}
+
 // ray_tracer.cu:158-204 with the launch-invariant trigonometry hoisted to the host (WaveParams).
 __device__ __forceinline__ d3 primary_direction(const WaveParams &P, uint32_t ix, uint32_t iy, uint32_t iz)
 {
@@ -452,7 +469,8 @@ __device__ __forceinline__ bool shade(const WaveParams &P, Ray &r, const HitRec 
             }
             }
             c.meta = m_make(reflDepth, c_refr, cslot, end, false, col + 1);
-            push_ray(P, c, L.overflow); // :268
+            if (P.out_back) push_ray_back(P, c, L.overflow); // :268
+            else push_ray(P, c, L.overflow);
         }
     }
 
@@ -646,7 +664,8 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
     if (PRIMARY && P.raster_ctl && raster_on(P)) return;   // the projected primary wave (raster.cuh) did this batch
     const unsigned lane = threadIdx.x & 31u;
     // queue capacity and batch size are < 2^26, so 32-bit indices and a 32-bit work counter suffice
-    const unsigned n_all = PRIMARY ? (unsigned)P.n_primary : (unsigned)*P.in_count;
+    const unsigned n_front = PRIMARY ? (unsigned)P.n_primary : (unsigned)*P.in_count;
+    const unsigned n_all = n_front + ((!PRIMARY && P.in_back) ? (unsigned)*P.in_back : 0u);
     const unsigned n_in = (!PRIMARY && P.todo_list) ? (unsigned)*P.todo_count : n_all;
     unsigned *work = reinterpret_cast<unsigned *>(P.work_counter);
     Local L = {0, 0, 0, 0, 0};
@@ -689,7 +708,8 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
             r.dx = d.x; r.dy = d.y; r.dz = d.z;
             r.meta = m_make(0, 0, 0, false, true, 0);
         } else {
-            if (P.todo_list) idx = P.todo_list[idx];         // the rays k_wave1_kept left for a full trace (coherent.cuh)
+            if (P.todo_list) idx = P.todo_list[idx];         // the rays k_wave1_kept left for a full trace (coherent.cuh): slots
+            else idx = queue_slot(P, idx, n_front);
             load_ray_geom(P.in, idx, r);
             r.meta &= ~M_COH;
         }
