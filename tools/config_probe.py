@@ -5,6 +5,22 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from rts_b200 import scenes, lib as L
 
+ORACLE = "--oracle" in sys.argv          # also time the CPU oracle (BVH mode, OpenMP, all host cores) on the same pulse
+if ORACLE:
+    sys.argv.remove("--oracle")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as O
+
+
+def oracle_line(targets, spec):
+    """the oracle on the GPU box's host cores, same pulse, in the same run."""
+    if not ORACLE:
+        return {}
+    t0 = time.time()
+    bins, st = O.trace_bins(targets, spec, use_bvh=True)
+    return {"oracle_Mrays/s": round(st["primary_rays"] / st["ms_trace"] / 1e3, 3), "oracle_cores": int(O.oracle().orc_num_threads()),
+            "oracle_segments": st["segments"], "oracle_bins": len(bins), "oracle_wall_s": round(time.time() - t0, 1)}
+
 def main():
     eng = L.Engine(0)
     cases = [("C1 flat plate 256x256, 1 bounce", scenes.flat_plate(n=256)),
@@ -22,11 +38,15 @@ def main():
             if best is None or st["ms_trace"] < best["ms_trace"]:
                 best = st
         bins = eng.bins()
-        print(json.dumps({"config": name, "triangles": int(sum(len(x.tris) for x in t)), "rays": best["primary_rays"], "segments": best["segments"],
-                          "refracted": best["refracted"], "captured": best["captured"], "bins": len(bins), "ms_trace": round(best["ms_trace"], 3),
-                          "Mrays/s": round(best["primary_rays"] / best["ms_trace"] / 1e3, 1),
-                          "Msegments/s": round(best["segments"] / best["ms_trace"] / 1e3, 1),
-                          "waves": [(round(a, 3), b) for a, b in eng.wave_profile()]}))
+        line = {"config": name, "triangles": int(sum(len(x.tris) for x in t)), "rays": best["primary_rays"], "segments": best["segments"],
+                "refracted": best["refracted"], "captured": best["captured"], "bins": len(bins), "ms_trace": round(best["ms_trace"], 3),
+                "Mrays/s": round(best["primary_rays"] / best["ms_trace"] / 1e3, 1),
+                "Msegments/s": round(best["segments"] / best["ms_trace"] / 1e3, 1),
+                "waves": [(round(a, 3), b) for a, b in eng.wave_profile()]}
+        line.update(oracle_line(t, s))
+        if "oracle_Mrays/s" in line:
+            line["gpu_over_oracle"] = round(line["Mrays/s"] / line["oracle_Mrays/s"], 1)
+        print(json.dumps(line), flush=True)
     if not only or only == "C5":
         c5_shard(eng)
 
@@ -44,12 +64,19 @@ def c5_shard(eng, world=8, rank=3, pulses=4):
         if best is None or st["ms_trace"] < best["ms_trace"]:
             best = st
     bins = eng.bins()
-    print(json.dumps({"config": f"C5 multistatic: rank {rank} of {world}'s share of a (1,10000,10000) pulse, 8 Rx, 1M-triangle terrain + movers",
-                      "triangles": int(sum(len(x.tris) for x in ms.base)), "rays": best["primary_rays"], "segments": best["segments"],
-                      "captured": best["captured"], "bins": len(bins), "ms_trace": round(best["ms_trace"], 3),
-                      "Mrays/s": round(best["primary_rays"] / best["ms_trace"] / 1e3, 1),
-                      "Msegments/s": round(best["segments"] / best["ms_trace"] / 1e3, 1),
-                      "waves": [(round(a, 3), b) for a, b in eng.wave_profile()]}))
+    line = {"config": f"C5 multistatic: rank {rank} of {world}'s share of a (1,10000,10000) pulse, 8 Rx, 1M-triangle terrain + movers",
+            "triangles": int(sum(len(x.tris) for x in ms.base)), "rays": best["primary_rays"], "segments": best["segments"],
+            "captured": best["captured"], "bins": len(bins), "ms_trace": round(best["ms_trace"], 3),
+            "Mrays/s": round(best["primary_rays"] / best["ms_trace"] / 1e3, 1),
+            "Msegments/s": round(best["segments"] / best["ms_trace"] / 1e3, 1),
+            "waves": [(round(a, 3), b) for a, b in eng.wave_profile()]}
+    if ORACLE:      # every 4th ray of the share keeps the CPU leg to a few seconds
+        sp = ms.spec_for(pulses - 1)
+        sp.ray_begin, sp.ray_count, sp.ray_stride = rank, 0, world * 4
+        line.update(oracle_line(ms.world_targets(pulses - 1), sp))
+        line["oracle_sample"] = "every 4th ray of the share"
+        line["gpu_over_oracle"] = round(line["Mrays/s"] / line["oracle_Mrays/s"], 1)
+    print(json.dumps(line), flush=True)
 
 if __name__ == "__main__":
     main()
