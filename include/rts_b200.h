@@ -79,6 +79,12 @@ const char *rts_version(void);
 int         rts_abi_sizes(uint32_t sizes[10]);
 /* Run subsequent work of this engine on a caller-provided cudaStream_t (NULL = engine's own). */
 int         rts_set_stream(rts_engine *e, void *cuda_stream);
+/* Tuning / test switches (no counterpart in the reference, whose only knobs are MaxThreads / MaxBlocks,
+ * ray_tracer.cpp:512).  The environment variable RTS_<NAME> gives an option its initial value when the engine is created;
+ * the environment is never read again afterwards.  Names: "bvh" (0 = choose by SAH cost, 1 = Morton radix tree, 2 = PLOC),
+ * "leaf_max" (1..8), "no_chain", "no_raster", "no_tiles", "one_ended_queue", "debug_raster", "no_static_hits",
+ * "no_kept_reflections", "no_split", "split_below" (rays), "no_graph", "batch" (primaries per batch, 0 = 2^24). */
+int         rts_set_option(rts_engine *e, const char *name, int64_t value);
 
 /* ---- host helpers (pure host code, usable without a GPU) ---- */
 /* Receiver sphere centre and angular window: ray_tracer.cpp:894-918. */
@@ -124,6 +130,10 @@ int rts_get_stats(rts_engine *e, rts_stats *out);
 /* Per-bounce-wave profile of the last pulse: device milliseconds (CUDA events on the engine's stream) and
  * the number of ray segments each wave traced, summed over ray batches.  *n = number of waves. */
 int rts_get_wave_profile(rts_engine *e, uint32_t cap, float *ms, uint64_t *segments, uint32_t *n);
+/* Device milliseconds of the second wave's two kernels in the last pulse (split.cuh): ms[0] = k_traverse (closest-hit
+ * queries of every first reflection), ms[1] = k_shade_wave (closest_hit / miss / bins of the survivors); both 0 when
+ * that wave ran as the fused kernel.  The wave-level figure of rts_get_wave_profile also holds kernels that returned at once. */
+int rts_get_split_profile(rts_engine *e, float ms[2]);
 /* Cumulative number of CUDA kernels this engine has launched (every <<<>>> of the library). */
 int rts_kernel_launches(rts_engine *e, uint64_t *out);
 /* Measurement aid (bench.py roofline): read bandwidth in GB/s of a `bytes`-sized device buffer streamed
@@ -142,6 +152,14 @@ int rts_get_responses(rts_engine *e, rts_response *out, uint32_t cap, uint32_t *
  *   results [ray_total] · targ_intersect [ray_total*D] · rcs_angle [ray_total*D*2] · tri_path [ray_total*W] */
 int rts_get_records(rts_engine *e, rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle,
                     int32_t *tri_path);
+
+/* RTS_OUT_RECORDS: the same arrays for the rays of the last pulse's shard only (pulse->ray_begin / ray_count / ray_stride: one
+ * rank's share of a large launch, or a strided sample), gathered on the device.  *n_shard = rays in the shard; ray k of the
+ * shard (launch index ray_begin + k*ray_stride) has its result slot s at index k + s*n_shard:
+ *   results [M*n_shard] · targ_intersect [M*n_shard*D] · rcs_angle [M*n_shard*D*2] · tri_path [M*n_shard*W]
+ * Call with every array NULL for the count; any array may be NULL. */
+int rts_get_records_shard(rts_engine *e, uint64_t *n_shard, rts_ray_record *results, int32_t *targ_intersect,
+                          double *rcs_angle, int32_t *tri_path);
 
 /* RTS_OUT_RECORDS: only the received rays (received >= 0), compacted on the device in result-slot order — the
  * h_rx_results / h_rx_intersects arrays the reference's host loop collects (ray_tracer.cpp:1190-1221) before it applies

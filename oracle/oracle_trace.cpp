@@ -756,9 +756,11 @@ extern "C" void orc_rx_sphere_from_desc(const rts_rx_desc *desc, rts_rx_sphere *
     out->max_phi = h_Rx_elevation + desc->phi_span / 2;
 }
 
-extern "C" int orc_trace(const rts_target_mesh *targets, uint32_t n_targets, const rts_pulse *pulse, int use_bvh,
-                         rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle, int32_t *tri_path,
-                         uint8_t *edge_flags, rts_stats *stats)
+// compact: the arrays hold the shard's rays only — ray k of the shard (launch index ray_begin + k*ray_stride) has its
+// slot s at index k + s*n_shard, rows likewise, edge flag at k — instead of launch-indexed arrays of the whole grid
+static int trace_impl(const rts_target_mesh *targets, uint32_t n_targets, const rts_pulse *pulse, int use_bvh,
+                      rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle, int32_t *tri_path,
+                      uint8_t *edge_flags, rts_stats *stats, bool compact)
 {
     if (!pulse || (!targets && n_targets)) return -1;
     if (pulse->max_refl + (pulse->max_refr ? 2u : 0u) > RTS_MAX_DEPTH) return -2;
@@ -768,7 +770,11 @@ extern "C" int orc_trace(const rts_target_mesh *targets, uint32_t n_targets, con
     const bool bvh = use_bvh && scene.has_bvh;
     Launch L;
     setup_launch(L, scene, pulse);
-    const uint64_t ray_total = L.R3 * L.M;
+    uint64_t b, e, stride;
+    shard_bounds(pulse, L.R3, b, e, stride);
+    const int64_t nIter = (int64_t)((e - b + stride - 1) / stride);
+    const uint64_t span = compact ? (uint64_t)nIter : L.R3;     // distance between a ray's result slots
+    const uint64_t ray_total = span * L.M;
 
     // host-side defaults (ray_tracer.cpp:854-868)
     if (targ_intersect)
@@ -779,26 +785,24 @@ extern "C" int orc_trace(const rts_target_mesh *targets, uint32_t n_targets, con
         for (uint64_t i = 0; i < ray_total * L.W; i++) tri_path[i] = -1;
     if (results) memset(results, 0, sizeof(rts_ray_record) * ray_total);
 
-    uint64_t b, e, stride;
-    shard_bounds(pulse, L.R3, b, e, stride);
     uint64_t segs = 0, hits = 0, shaded = 0, refr = 0, multi = 0, edges = 0, nrays = 0, captured = 0;
-    const int64_t nIter = (int64_t)((e - b + stride - 1) / stride);
 #pragma omp parallel for schedule(dynamic, 1024) reduction(+ : segs, hits, shaded, refr, multi, edges, nrays, captured)
     for (int64_t it = 0; it < nIter; it++) {
         const uint64_t rayIndex = b + (uint64_t)it * stride;
+        const uint64_t at = compact ? (uint64_t)it : rayIndex;
         RayOut out;
         rts_ray_record local[RTS_MAX_DEPTH + 4];
-        out.res = results ? results + rayIndex : local;
-        out.res_stride = results ? L.R3 : 1;
-        out.ti = targ_intersect ? targ_intersect + rayIndex * L.D : nullptr;
-        out.rcs = rcs_angle ? rcs_angle + rayIndex * L.D * 2 : nullptr;
-        out.tp = tri_path ? tri_path + rayIndex * L.W : nullptr;
-        out.row_stride = L.R3;
+        out.res = results ? results + at : local;
+        out.res_stride = results ? span : 1;
+        out.ti = targ_intersect ? targ_intersect + at * L.D : nullptr;
+        out.rcs = rcs_angle ? rcs_angle + at * L.D * 2 : nullptr;
+        out.tp = tri_path ? tri_path + at * L.W : nullptr;
+        out.row_stride = span;
         out.edge = 0;
         out.segments = out.hits = out.shaded = out.refracted = out.multi = 0;
         ray_generation(L, rayIndex, out, bvh);
         for (uint32_t k = 0; k < L.M; k++) captured += out.res[(uint64_t)k * out.res_stride].received >= 0;
-        if (edge_flags) edge_flags[rayIndex] = out.edge;
+        if (edge_flags) edge_flags[at] = out.edge;
         segs += out.segments; hits += out.hits; shaded += out.shaded; refr += out.refracted; multi += out.multi;
         edges += (out.edge & ORC_EDGE_TRI) ? 1 : 0;
         nrays++;
@@ -809,6 +813,20 @@ extern "C" int orc_trace(const rts_target_mesh *targets, uint32_t n_targets, con
         stats->captured = captured; stats->multi_captured = multi; stats->edge_rays = edges; stats->refracted = refr;
     }
     return 0;
+}
+
+extern "C" int orc_trace(const rts_target_mesh *targets, uint32_t n_targets, const rts_pulse *pulse, int use_bvh,
+                         rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle, int32_t *tri_path,
+                         uint8_t *edge_flags, rts_stats *stats)
+{
+    return trace_impl(targets, n_targets, pulse, use_bvh, results, targ_intersect, rcs_angle, tri_path, edge_flags, stats, false);
+}
+
+extern "C" int orc_trace_shard(const rts_target_mesh *targets, uint32_t n_targets, const rts_pulse *pulse, int use_bvh,
+                               rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle, int32_t *tri_path,
+                               uint8_t *edge_flags, rts_stats *stats)
+{
+    return trace_impl(targets, n_targets, pulse, use_bvh, results, targ_intersect, rcs_angle, tri_path, edge_flags, stats, true);
 }
 
 extern "C" int orc_trace_bins(const rts_target_mesh *targets, uint32_t n_targets, const rts_pulse *pulse, int use_bvh,
@@ -935,4 +953,6 @@ extern "C" int orc_trace_bins(const rts_target_mesh *targets, uint32_t n_targets
 }
 
 extern "C" int orc_num_threads(void) { return omp_get_max_threads(); }
+// torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; a timed oracle run states its thread count itself
+extern "C" void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 extern "C" const char *orc_version(void) { return "rts-oracle 1 (scalar C++/OpenMP restatement; test infrastructure)"; }

@@ -61,6 +61,13 @@ int orc_trace(const rts_target_mesh *targets, uint32_t n_targets, const rts_puls
               rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle, int32_t *tri_path,
               uint8_t *edge_flags, rts_stats *stats);
 
+/* The same launch with compact outputs for a shard of a large grid: n_shard = number of rays the shard selects
+ * (ray_begin / ray_count / ray_stride); ray k of the shard has result slot s at index k + s*n_shard
+ *   results [M*n_shard] · targ_intersect [M*n_shard*D] · rcs_angle [M*n_shard*D*2] · tri_path [M*n_shard*W] · edge_flags [n_shard] */
+int orc_trace_shard(const rts_target_mesh *targets, uint32_t n_targets, const rts_pulse *pulse, int use_bvh,
+                    rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle, int32_t *tri_path,
+                    uint8_t *edge_flags, rts_stats *stats);
+
 /* Launch + host post-process (RCS = pulse->targ_rcs[k] or 1, Gt/Gr = pulse->gain_tx/gain_rx or 1) + binned aggregation without materialising
  * per-ray arrays.  bins sorted by (rx, path).  Returns number of bins in *n_bins (may exceed cap). */
 int orc_trace_bins(const rts_target_mesh *targets, uint32_t n_targets, const rts_pulse *pulse, int use_bvh,
@@ -110,6 +117,7 @@ int orc_file_mesh(const char *v_file, const char *n_file, float yaw, float pitch
 void orc_vertex_rotation(double *xyz, uint32_t n, float yaw, float pitch, float roll);
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);   /* OpenMP threads of the following orc_trace calls (n <= 0: unchanged) */
 const char *orc_version(void);
 
 #ifdef __cplusplus

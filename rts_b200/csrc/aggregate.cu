@@ -137,6 +137,28 @@ __global__ void k_gather_received(const unsigned *__restrict__ idx, unsigned n, 
     }
 }
 
+// ---- the records of one shard, compacted: ray k of the shard (launch index begin + k*stride) has slot s at k + s*n ----
+__global__ void k_gather_shard(unsigned long long n, uint32_t M, unsigned long long R3, unsigned long long begin, unsigned long long stride,
+                               uint32_t D, uint32_t W, const rts_ray_record *__restrict__ res, const int32_t *__restrict__ ti,
+                               const double *__restrict__ rcs, const int32_t *__restrict__ tp, rts_ray_record *__restrict__ o_res,
+                               int32_t *__restrict__ o_ti, double *__restrict__ o_rcs, int32_t *__restrict__ o_tp)
+{
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long item = t / 9;
+    const unsigned piece = (unsigned)(t % 9);
+    if (item >= n * M) return;
+    const unsigned long long k = item % n, s = item / n;
+    const unsigned long long src = begin + k * stride + s * R3;
+    if (o_res) reinterpret_cast<double2 *>(o_res + item)[piece] = reinterpret_cast<const double2 *>(res + src)[piece];
+    if (piece == 0) {
+        for (uint32_t c = 0; c < D; c++) {
+            if (o_ti) o_ti[item * D + c] = ti[src * D + c];
+            if (o_rcs) { o_rcs[(item * D + c) * 2] = rcs[(src * D + c) * 2]; o_rcs[(item * D + c) * 2 + 1] = rcs[(src * D + c) * 2 + 1]; }
+        }
+        if (o_tp) for (uint32_t c = 0; c < W; c++) o_tp[item * W + c] = tp[src * W + c];
+    }
+}
+
 // ---- drop-in aggregator (rs::kernel_wrapper) ----
 // Open-addressing table keyed by (receiver, path row); a slot stores the index of the ray that
 // claimed it and later arrivals compare rows against that representative.
@@ -203,7 +225,10 @@ __global__ void k_accumulate(const rts_ray_record *__restrict__ res, uint32_t R,
         }
     }
     if (rx < n_rx_slots) {
-        auto part = cg::labeled_partition(g, rx);
+        // a group of the threads that are here: records with received < 0 (which the reference's kernel tolerates) skip
+        // this branch, and a partition of the outer group would wait for them
+        cg::coalesced_group g2 = cg::coalesced_threads();
+        auto part = cg::labeled_partition(g2, rx);
         const double a0 = cg::reduce(part, 1.0, cg::plus<double>());
         const double a1 = cg::reduce(part, amp, cg::plus<double>());
         const double a2 = cg::reduce(part, delay, cg::plus<double>());
@@ -418,6 +443,47 @@ done:
 #undef AGG_CUDA
     cudaFree(d_res); cudaFree(d_rows); cudaFree(d_pm); cudaFree(d_table); cudaFree(d_slot); cudaFree(d_gmin);
     cudaFree(d_rmin); cudaFree(d_gs); cudaFree(d_rs); cudaFree(d_acc);
+    return rc;
+}
+
+// The last RTS_OUT_RECORDS pulse's records for the rays of its shard only (a strided sample or one rank's share of a
+// large launch), gathered on the device: the caller never touches the launch-sized arrays.
+int agg_get_records_shard(rts_engine *e, uint64_t *n_shard, rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle,
+                          int32_t *tri_path)
+{
+    const uint64_t n = e->last_n_primary;
+    const uint32_t M = e->last_sizes.slots, D = e->last_sizes.depth_total, W = e->last_sizes.tri_cols;
+    if (n_shard) *n_shard = n;
+    if (!n || (!results && !targ_intersect && !rcs_angle && !tri_path)) return RTS_OK;
+    cudaStream_t st = e->stream;
+    rts_ray_record *o_res = nullptr;
+    int32_t *o_ti = nullptr, *o_tp = nullptr;
+    double *o_rcs = nullptr;
+    int rc = RTS_OK;
+    const size_t items = (size_t)n * M;
+#define SH_CUDA(call)                                                                                           \
+    do {                                                                                                        \
+        cudaError_t _e = (call);                                                                                \
+        if (_e != cudaSuccess) {                                                                                \
+            rc = rts_fail(RTS_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            goto done;                                                                                          \
+        }                                                                                                       \
+    } while (0)
+    if (results) SH_CUDA(cudaMalloc(&o_res, sizeof(rts_ray_record) * items));
+    if (targ_intersect && D) SH_CUDA(cudaMalloc(&o_ti, sizeof(int32_t) * items * D));
+    if (rcs_angle && D) SH_CUDA(cudaMalloc(&o_rcs, sizeof(double) * 2 * items * D));
+    if (tri_path) SH_CUDA(cudaMalloc(&o_tp, sizeof(int32_t) * items * W));
+    { k_gather_shard<<<blocks_for((uint64_t)items * 9, 256), 256, 0, st>>>(n, M, e->last_sizes.rays, e->last_begin, e->last_stride, D, W, e->d_results,
+                                                                         e->d_targ_intersect, e->d_rcs_angle, e->d_tri_path, o_res, o_ti, o_rcs, o_tp); e->launches++; }
+    SH_CUDA(cudaGetLastError());
+    if (o_res) SH_CUDA(cudaMemcpyAsync(results, o_res, sizeof(rts_ray_record) * items, cudaMemcpyDeviceToHost, st));
+    if (o_ti) SH_CUDA(cudaMemcpyAsync(targ_intersect, o_ti, sizeof(int32_t) * items * D, cudaMemcpyDeviceToHost, st));
+    if (o_rcs) SH_CUDA(cudaMemcpyAsync(rcs_angle, o_rcs, sizeof(double) * 2 * items * D, cudaMemcpyDeviceToHost, st));
+    if (o_tp) SH_CUDA(cudaMemcpyAsync(tri_path, o_tp, sizeof(int32_t) * items * W, cudaMemcpyDeviceToHost, st));
+    SH_CUDA(cudaStreamSynchronize(st));
+done:
+#undef SH_CUDA
+    cudaFree(o_res); cudaFree(o_ti); cudaFree(o_rcs); cudaFree(o_tp);
     return rc;
 }
 

@@ -5,6 +5,7 @@
 // the wavefront launch sequence, result hand-off.  Also exports the C++ symbol
 // rs::kernel_wrapper with the reference's exact signature (aggregation.cuh:18-23).
 #include "engine.h"
+#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -57,6 +58,32 @@ extern "C" int rts_result_sizes(const rts_pulse *p, rts_sizes *out)
 }
 
 // ---------------------------------------------------------------------------------------------
+static int set_option(rts_engine *e, const char *name, long long v)
+{
+    Knobs &k = e->knobs;
+    if (!strcmp(name, "bvh")) e->builder_forced = (v == 1 || v == 2) ? (int)v : 0;           // 1 = Morton radix tree, 2 = PLOC, 0 = by SAH cost
+    else if (!strcmp(name, "leaf_max")) { if (v < 1 || v > 8) return rts_fail(RTS_ERR_ARG, "leaf_max must be 1..8"); e->leaf_max = (int)v; }
+    else if (!strcmp(name, "no_chain")) k.no_chain = v != 0;
+    else if (!strcmp(name, "no_raster")) k.no_raster = v != 0;
+    else if (!strcmp(name, "no_tiles")) k.no_tiles = v != 0;
+    else if (!strcmp(name, "one_ended_queue")) k.one_ended_queue = v != 0;
+    else if (!strcmp(name, "debug_raster")) k.debug_raster = v != 0;
+    else if (!strcmp(name, "no_static_hits")) k.no_static_hits = v != 0;
+    else if (!strcmp(name, "no_kept_reflections")) k.no_kept_reflections = v != 0;
+    else if (!strcmp(name, "no_split")) k.no_split = v != 0;
+    else if (!strcmp(name, "split_below")) { if (v < 0 || v > (1ll << 30)) return rts_fail(RTS_ERR_ARG, "split_below out of range"); k.split_below = (uint32_t)v; }
+    else if (!strcmp(name, "no_graph")) k.no_graph = v != 0;
+    else if (!strcmp(name, "batch")) { if (v != 0 && (v < 32 || v > (1ll << 24))) return rts_fail(RTS_ERR_ARG, "batch must be 0 or 32..2^24"); k.batch = v; }
+    else return rts_fail(RTS_ERR_ARG, "unknown option '%s'", name);
+    return RTS_OK;
+}
+
+extern "C" int rts_set_option(rts_engine *e, const char *name, int64_t value)
+{
+    if (!e || !name) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    return set_option(e, name, (long long)value);
+}
+
 extern "C" int rts_create(int device, rts_engine **out)
 {
     if (!out) return rts_fail(RTS_ERR_ARG, "out is NULL");
@@ -81,10 +108,19 @@ extern "C" int rts_create(int device, rts_engine **out)
         return rts_fail(RTS_ERR_CUDA, "cudaStreamCreate failed");
     }
     e->stream = e->own_stream;
-    if (const char *b = getenv("RTS_BVH")) e->builder_forced = !strcmp(b, "ploc") ? 2 : (!strcmp(b, "lbvh") ? 1 : 0);
-    if (const char *lm = getenv("RTS_LEAF_MAX")) { int v = atoi(lm); if (v >= 1 && v <= 8) e->leaf_max = v; }
+    // tuning / test switches: the environment is read here, once; afterwards only rts_set_option changes them
+    for (const char *name : {"bvh", "leaf_max", "no_chain", "no_raster", "no_tiles", "one_ended_queue", "debug_raster", "no_static_hits",
+                             "no_kept_reflections", "no_split", "split_below", "no_graph", "batch"}) {
+        std::string env = "RTS_";
+        for (const char *c = name; *c; c++) env += (char)toupper(*c);
+        if (const char *v = getenv(env.c_str())) {
+            if (!strcmp(name, "bvh")) e->builder_forced = !strcmp(v, "ploc") ? 2 : (!strcmp(v, "lbvh") ? 1 : 0);
+            else set_option(e, name, atoll(v));
+        }
+    }
     for (auto &ev : e->ev) cudaEventCreate(&ev);
     for (auto &ev : e->wave_ev) cudaEventCreate(&ev);
+    for (auto &ev : e->split_ev) cudaEventCreate(&ev);
     for (auto &s : e->stage) cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->sah_ev, cudaEventDisableTiming);
     if (cudaMallocHost((void **)&e->h_rb, sizeof(Readback)) != cudaSuccess) {
@@ -122,11 +158,12 @@ extern "C" void rts_destroy(rts_engine *e)
     cudaStreamSynchronize(e->stream);
     free_scene(e);
     for (int k = 0; k < 2; k++) if (e->q_slab[k]) cudaFree(e->q_slab[k]);
-    void *ptrs[] = {e->d_todo, e->d_w1_static, e->d_target_box, e->d_mover_nodes, e->d_dirs, e->d_hits, e->d_hits_static, e->d_raster_ctl, e->d_raster_ctl_static, e->d_raster_items, e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count, e->d_rx_sums, e->d_rx_mins,
+    void *ptrs[] = {e->d_trav_hits, e->d_todo, e->d_w1_static, e->d_target_box, e->d_mover_nodes, e->d_dirs, e->d_hits, e->d_hits_static, e->d_raster_ctl, e->d_raster_ctl_static, e->d_raster_items, e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count, e->d_rx_sums, e->d_rx_mins,
                     e->d_results, e->d_targ_intersect, e->d_tri_path, e->d_rcs_angle};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->wave_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->split_ev) if (ev) cudaEventDestroy(ev);
     for (auto &s : e->stage) { if (s.done) cudaEventDestroy(s.done); if (s.host) cudaFreeHost(s.host); }
     if (e->sah_ev) cudaEventDestroy(e->sah_ev);
     if (e->h_rb) cudaFreeHost(e->h_rb);
@@ -410,11 +447,11 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     if (p->n_rx && !p->rx) return rts_fail(RTS_ERR_ARG, "rx is NULL");
     if (p->n_targets && !p->targ_vel) return rts_fail(RTS_ERR_ARG, "targ_vel is NULL");
     if (!p->nx || !p->ny || !p->nz) return rts_fail(RTS_ERR_ARG, "empty launch grid");
+    if (p->max_refl > 12) return rts_fail(RTS_ERR_CAPACITY, "max_refl %u too deep for the ray-state encoding (12)", p->max_refl);   // before any size arithmetic
     rts_sizes sz;
     rts_result_sizes(p, &sz);
     if (sz.depth_total > RTS_MAX_DEPTH) return rts_fail(RTS_ERR_CAPACITY, "depth_total %u > %u", sz.depth_total, RTS_MAX_DEPTH);
     if (sz.rays >= (1ull << 32)) return rts_fail(RTS_ERR_CAPACITY, "%llu primary rays per launch exceed 2^32", (unsigned long long)sz.rays);
-    if (p->max_refl + 3 > 15) return rts_fail(RTS_ERR_CAPACITY, "max_refl %u too deep for the ray-state encoding", p->max_refl);
     RTS_CUDA(cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
 
@@ -460,7 +497,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     P.key_all = 0;
     for (uint32_t c = 0; c < sz.depth_total; c++) P.key_all += P.powB[c];
     P.flags = flags;
-    P.chain_below = getenv("RTS_NO_CHAIN") ? 0u : (1u << 18);
+    P.chain_below = e->knobs.no_chain ? 0u : (1u << 18);
 
     // receivers, target velocities, per-target RCS: through the pinned staging ring, no waiting
     {
@@ -519,8 +556,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     }
 
     // queues: a batch of primaries and up to three live chains per primary with refraction
-    uint64_t batch_max = 1ull << 24;
-    if (const char *b = getenv("RTS_BATCH")) { const long long v = atoll(b); if (v >= 32 && v <= (1ll << 24)) batch_max = (uint64_t)v; }   // tests: batching at small sizes
+    const uint64_t batch_max = e->knobs.batch ? (uint64_t)e->knobs.batch : 1ull << 24;   // knob: batching at test sizes
     const uint64_t batch = std::min<uint64_t>(n_primary_total ? n_primary_total : 1, batch_max);
     const uint64_t cap = batch * (rMax ? 3 : 1);
     {
@@ -529,7 +565,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     }
     // primary visibility by projection (raster.cuh; RTS_NO_RASTER=1 turns it off): launches whose rays form one image
     // (nx == 1) with a forward image plane; node/triangle counting needs the traversal
-    const bool use_raster = p->nx == 1 && !P.single_ray && e->n_tris > 0 && !(flags & RTS_COUNT_NODES) && !getenv("RTS_NO_RASTER") &&
+    const bool use_raster = p->nx == 1 && !P.single_ray && e->n_tris > 0 && !(flags & RTS_COUNT_NODES) && !e->knobs.no_raster &&
                             P.beamStart[0] > 1e-6 && (p->ny == 1 || P.slope[1] != 0.0) && (p->nz == 1 || P.slope[2] != 0.0) &&
                             n_primary_total > 0;
     P.lat_w = 0; P.lat_c0 = 0; P.lat_g0 = 0;
@@ -546,6 +582,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     P.counters = e->d_counters;
     RTS_CUDA(cudaMemsetAsync(e->d_counters, 0, sizeof(Counters), st));
 
+    e->split_timed = false;
     cudaEventRecord(e->ev[0], st);
     if (records) {
         int rc = agg_fill_records(e, sz.ray_total, sz.depth_total, sz.tri_cols);
@@ -564,7 +601,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     // Not when the projected primary wave is on: its batches take their rays in index order, and a batch whose guard
     // trips falls back to k_wave<PRIMARY> — which must then cover exactly that batch's indices, not a tile permutation
     // of them that reaches into the neighbouring batches (found by tests/test_gpu_fuzz.py with RTS_BATCH).
-    if (!use_raster && p->nx == 1 && !getenv("RTS_NO_TILES") && p->ny % stride == 0 && (p->ny / stride) % 8 == 0 && (p->ny / stride) >= 8) {
+    if (!use_raster && p->nx == 1 && !e->knobs.no_tiles && p->ny % stride == 0 && (p->ny / stride) % 8 == 0 && (p->ny / stride) >= 8) {
         P.swz_w = (uint32_t)(p->ny / stride);
         P.swz_limit = n_primary_total / (4ull * P.swz_w) * (4ull * P.swz_w);
     }
@@ -581,7 +618,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
             Q.in = e->q[w & 1]; Q.out = e->q[(w + 1) & 1];
             Q.in_count = e->d_counts + w;
             Q.out_count = e->d_counts + w + 1;
-            if (rMax && !getenv("RTS_ONE_ENDED_QUEUE")) { Q.in_back = e->d_counts + 64 + w; Q.out_back = e->d_counts + 64 + w + 1; }
+            if (rMax && !e->knobs.one_ended_queue) { Q.in_back = e->d_counts + 64 + w; Q.out_back = e->d_counts + 64 + w + 1; }
             Q.work_counter = e->d_counts + 32 + w;
             Q.wave_index = w;
             if (single_batch) cudaEventRecord(e->wave_ev[w], st);
@@ -595,6 +632,11 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
                 Q.w1_static = kept_params.w1_static; Q.hits_static = kept_params.hits_static; Q.moving_flags = kept_params.moving_flags;
                 trace_wave_grid(e);
                 int rr = trace_launch_kept(e, Q, records);
+                if (rr) return rr;
+            }
+            if (w >= 1 && !e->knobs.no_split) {   // the two-kernel form for waves that are large (split.cuh); decided on the device
+                Q.split_below = e->knobs.split_below;
+                int rr = trace_launch_split(e, Q, records);
                 if (rr) return rr;
             }
             int rc = trace_launch_wave(e, Q, w == 0, records);
@@ -619,6 +661,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     e->pulse_primary = n_primary_total; e->pulse_waves = waves;
     e->have_pulse = true; e->last_flags = flags; e->last_sizes = sz;
     e->last_B = (uint32_t)B; e->last_D = sz.depth_total; e->last_nrx = p->n_rx;
+    e->last_begin = begin; e->last_stride = stride; e->last_n_primary = n_primary_total;
     e->bins_finalised = !(flags & RTS_NO_FINALISE);
     e->bins_eager = false;
     if ((flags & RTS_OUT_BINS) && e->bins_finalised) {
@@ -642,6 +685,11 @@ int pulse_collect(rts_engine *e)
     for (int w = 0; w < 32; w++) e->wave_ms[w] = 0.f;
     if (e->pulse_single_batch)
         for (uint32_t w = 0; w < e->n_waves; w++) cudaEventElapsedTime(&e->wave_ms[w], e->wave_ev[w], e->wave_ev[w + 1]);
+    e->split_ms[0] = e->split_ms[1] = 0.f;
+    if (e->split_timed) {
+        cudaEventElapsedTime(&e->split_ms[0], e->split_ev[0], e->split_ev[1]);
+        cudaEventElapsedTime(&e->split_ms[1], e->split_ev[1], e->split_ev[2]);
+    }
     collect_refit_time(e);
     rts_stats &s = e->stats;
     memset(&s, 0, sizeof(s));
@@ -651,7 +699,7 @@ int pulse_collect(rts_engine *e)
     s.ms_trace = ms; s.ms_update = e->bvh_info.ms_refit; s.ms_total = ms;
     // the guard of raster.cuh, evaluated on the last batch's control block (16 candidates per ray)
     s.primary_projected = (e->pulse_raster && e->h_rb->raster.area + e->h_rb->raster_static.area <= 16ull * std::min<uint64_t>(e->pulse_primary, 1ull << 24)) ? 1u : 0u;
-    if (getenv("RTS_DEBUG_RASTER") && e->pulse_raster)
+    if (e->knobs.debug_raster && e->pulse_raster)
         fprintf(stderr, "[raster] candidates %llu (+ %llu kept from the static pass), %u row chunks, projected %u\n", e->h_rb->raster.area, e->h_rb->raster_static.area, e->h_rb->raster.n_items, s.primary_projected);
     if (c.overflow) return rts_fail(RTS_ERR_CAPACITY, "%llu ray states dropped (queue/stack overflow)", (unsigned long long)c.overflow);
     return RTS_OK;
@@ -684,6 +732,15 @@ extern "C" int rts_get_wave_profile(rts_engine *e, uint32_t cap, float *ms, uint
         if (ms) ms[w] = e->wave_ms[w];
         if (segments) segments[w] = e->wave_segs[w];
     }
+    return RTS_OK;
+}
+
+extern "C" int rts_get_split_profile(rts_engine *e, float ms[2])
+{
+    if (!e || !ms) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    if (!e->have_pulse) return rts_fail(RTS_ERR_STATE, "no pulse traced yet");
+    pulse_collect(e);
+    ms[0] = e->split_ms[0]; ms[1] = e->split_ms[1];
     return RTS_OK;
 }
 
@@ -828,6 +885,17 @@ extern "C" int rts_get_records(rts_engine *e, rts_ray_record *results, int32_t *
     return RTS_OK;
 }
 
+extern "C" int rts_get_records_shard(rts_engine *e, uint64_t *n_shard, rts_ray_record *results, int32_t *targ_intersect,
+                                     double *rcs_angle, int32_t *tri_path)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    if (!e->have_pulse || !(e->last_flags & RTS_OUT_RECORDS)) return rts_fail(RTS_ERR_STATE, "last pulse did not produce records");
+    RTS_CUDA(cudaSetDevice(e->device));
+    int rc = pulse_collect(e);
+    if (rc) return rc;
+    return agg_get_records_shard(e, n_shard, results, targ_intersect, rcs_angle, tri_path);
+}
+
 extern "C" int rts_get_received(rts_engine *e, uint64_t cap, uint64_t *n, uint64_t *slots, rts_ray_record *results,
                                 int32_t *targ_intersect, double *rcs_angle)
 {
@@ -881,5 +949,3 @@ void kernel_wrapper(PerRayData *h_rx_results_arr, int *h_rx_intersects_arr, unsi
     }
 }
 } // namespace rs
-
-int agg_finalise_bins(rts_engine *) { return RTS_OK; }

@@ -136,8 +136,8 @@ __device__ __forceinline__ bool near_movers(const WaveParams &P, const d3 &o, co
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_WAVE_MIN_BLOCKS) k_wave1_fill(const __grid_constant__ WaveParams P)
 {
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned n_front = (unsigned)*P.in_count;
-    const unsigned n_in = n_front + (P.in_back ? (unsigned)*P.in_back : 0u);
+    const unsigned n_front = (unsigned)min(*P.in_count, P.out_capacity);
+    const unsigned n_in = n_front + (P.in_back ? (unsigned)min(*P.in_back, P.out_capacity - n_front) : 0u);
     unsigned *work = reinterpret_cast<unsigned *>(P.fill_counter);
     unsigned ovf = 0;
     for (;;) {
@@ -164,8 +164,8 @@ template <bool RECORDS>
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_wave1_kept(const __grid_constant__ WaveParams P)
 {
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned n_front = (unsigned)*P.in_count;
-    const unsigned n_in = n_front + (P.in_back ? (unsigned)*P.in_back : 0u);
+    const unsigned n_front = (unsigned)min(*P.in_count, P.out_capacity);
+    const unsigned n_in = n_front + (P.in_back ? (unsigned)min(*P.in_back, P.out_capacity - n_front) : 0u);
     Local L = {0, 0, 0, 0, 0};
     unsigned served = 0;
     const unsigned stride = gridDim.x * blockDim.x;

@@ -163,6 +163,12 @@ struct WaveParams {
     unsigned long long *fill_counter;       // work counter of k_wave1_fill
     uint32_t *todo_list;                    // queue indices k_wave1_kept leaves to the ordinary wave kernel (nullptr: all)
     unsigned long long *todo_count;
+    // split later waves (split.cuh): k_traverse answers the closest-hit query of every queued ray into trav_hits[slot]
+    // (fp32 t bits << 32 | leaf position; TRAV_MISS = no hit but a receiver sphere is crossed; TRAV_DEAD = nothing left
+    // to do), k_shade_wave then shades / captures the survivors.  split_below: waves with fewer rays stay with the fused
+    // kernel (which returns at once for the others when split_on is set).
+    unsigned long long *trav_hits;
+    uint32_t split_on, split_below, split_keep_all;
 };
 
 // ---- engine ---------------------------------------------------------------------------------
@@ -191,12 +197,24 @@ struct DirsKey {
     double c[30];   // origin, beamStart, slope, Rot, Rot1, boresight
 };
 
+// Tuning / test switches: read from the environment once in rts_create, changed afterwards only through rts_set_option.
+struct Knobs {
+    int no_chain = 0, no_raster = 0, no_tiles = 0, one_ended_queue = 0, debug_raster = 0, no_static_hits = 0,
+        no_kept_reflections = 0, no_split = 0, no_graph = 0;
+    long long batch = 0;           // 0 = default 2^24 primaries per batch
+    uint32_t split_below = 1u << 18;   // later waves with at least this many rays run as k_traverse + k_shade_wave
+};
+
 struct rts_engine {
     int device = 0;
+    Knobs knobs;
     int num_sms = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     cudaEvent_t ev[6] = {};
     cudaEvent_t wave_ev[34] = {};
+    cudaEvent_t split_ev[3] = {};      // around k_traverse and k_shade_wave of the second wave
+    bool split_timed = false;
+    float split_ms[2] = {};
     unsigned long long *d_wave_segs = nullptr;
     float wave_ms[32] = {};
     unsigned long long wave_segs[32] = {};
@@ -256,7 +274,7 @@ struct rts_engine {
     unsigned long long *d_counts = nullptr;   // [96] queue counts (front), work counters, queue counts (back)
     Counters *d_counters = nullptr;
     RxDev *d_rx = nullptr;
-    int wave_grid = 0, wave_grid_primary = 0;
+    int wave_grid = 0, wave_grid_primary = 0, trav_grid = 0;
 
     // primary visibility by projection
     double *d_dirs = nullptr;
@@ -276,6 +294,8 @@ struct rts_engine {
     BvhNode *d_mover_nodes = nullptr;
     uint32_t *d_todo = nullptr;
     uint64_t todo_alloc = 0;
+    unsigned long long *d_trav_hits = nullptr;   // split.cuh: one hit word per queue slot
+    uint64_t trav_alloc = 0;
     bool coh_on = false, coh_fill = false, w1_valid = false;
     uint32_t w1_builds = 0, w1_interp = 0, w1_dmax = 0, w1_rmax = 0;
 
@@ -307,6 +327,7 @@ struct rts_engine {
     uint32_t last_flags = 0;
     rts_sizes last_sizes = {};
     uint32_t last_B = 1, last_D = 0, last_nrx = 0;
+    uint64_t last_begin = 0, last_stride = 1, last_n_primary = 0;   // the shard of the last pulse
     rts_stats stats = {};
 };
 
@@ -337,18 +358,20 @@ int pulse_collect(rts_engine *e);                   // fold the read-back of an 
 // trace.cu
 int trace_alloc_queues(rts_engine *e, uint64_t capacity);
 int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool records);
+int trace_launch_split(rts_engine *e, WaveParams &p, bool records);   // k_traverse + k_shade_wave ahead of the fused kernel
 int trace_raster_alloc(rts_engine *e, uint64_t batch);     // buffers of the projected primary wave
 int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_batch);   // enqueue it (before the BVH primary wave)
 int trace_launch_kept(rts_engine *e, WaveParams &p, bool records);   // second wave: rays served from the kept first-reflection hits
 int trace_wave_grid(rts_engine *e);
 
 // aggregate.cu
-int agg_finalise_bins(rts_engine *e);
 int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n);
 int agg_emit_bins_async(rts_engine *e);
 int agg_fill_records(rts_engine *e, uint64_t ray_total, uint32_t D, uint32_t W);
 int agg_get_received(rts_engine *e, uint64_t cap, uint64_t *n, uint64_t *slots, rts_ray_record *results, int32_t *targ_intersect,
                      double *rcs_angle);
+int agg_get_records_shard(rts_engine *e, uint64_t *n_shard, rts_ray_record *results, int32_t *targ_intersect, double *rcs_angle,
+                          int32_t *tri_path);
 int agg_kernel_wrapper(rts_engine *e, rts_ray_record *rx_results, const int32_t *rx_intersects, uint32_t received,
                        uint32_t depth_total, double cspeed, double carrier, double *npath, double *power,
                        double *doppler, double *delay, double *phase, int32_t *path_match);

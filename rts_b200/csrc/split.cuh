@@ -1,0 +1,244 @@
+// split.cuh — the later bounce waves as two kernels (included inside trace.cu's anonymous namespace, after coherent.cuh).
+//
+// The fused k_wave keeps a ray's whole shading state in reach of the traversal loop: 80 registers, 6 CTAs of 128
+// threads per SM, and a traversal that is latency-bound at that occupancy (profiles/r01_k_wave_ncu_full.json: 37 %
+// warps active, 52 % issue slots, 24 of 32 lanes).  Here the closest-hit query (OptiX traversal + the intersect
+// program, triangle_mesh.cu:121-200) is a kernel of its own:
+//
+//   k_traverse     persistent warps; a lane that has finished its ray takes the next one at once (the warp refills as
+//                  soon as RTS_FETCH_THRESH lanes are idle) instead of waiting for the slowest of 32 rays; only origin
+//                  and direction are read (48 of the 88 queued bytes).  Result: one 64-bit word per queue slot —
+//                  (fp32 t bits << 32 | leaf position) for a hit, TRAV_MISS when nothing is hit but the ray crosses some
+//                  receiver's sphere (the discriminant test of miss(), ray_tracer.cu:288-296, same arithmetic), TRAV_DEAD
+//                  when nothing is hit and no sphere is crossed: such a ray changes no output outside records mode.
+//   k_shade_wave   streams the hit words in queue order and runs closest_hit / miss / bin accumulation (the code of the
+//                  fused kernel) for the survivors only.
+//
+// Which of the two forms serves a wave is decided on the device from the wave's size: waves below split_below rays
+// are launch-latency-bound and stay with the fused kernel (which follows reflections in place).  Results are
+// bit-identical: same traversal arithmetic, same closest-hit rule, same shading code.
+
+#ifndef RTS_TRAV_MIN_BLOCKS
+#define RTS_TRAV_MIN_BLOCKS 8
+#endif
+#ifndef RTS_FETCH_THRESH
+#define RTS_FETCH_THRESH 8u            // idle lanes that make a warp fetch new rays
+#endif
+#ifndef RTS_TRAV_CHUNK
+#define RTS_TRAV_CHUNK 64u             // rays a warp reserves from the global work counter at a time
+#endif
+
+constexpr unsigned long long TRAV_MISS = ~0ull;
+constexpr unsigned long long TRAV_DEAD = ~0ull - 1ull;
+
+// discriminant of the ray / receiver-sphere quadratic exactly as miss() forms it (ray_tracer.cu:288-296)
+__device__ __forceinline__ double rx_discriminant(const d3 &po, const d3 &dir, const RxDev &rx)
+{
+    const double A = (dir.x) * (dir.x) + (dir.y) * (dir.y) + (dir.z) * (dir.z);
+    const double B = 2 * (((po.x - rx.cx) * dir.x) + ((po.y - rx.cy) * dir.y) + ((po.z - rx.cz) * dir.z));
+    const double C = po.x * po.x + po.y * po.y + po.z * po.z + (rx.cx * rx.cx) + (rx.cy * rx.cy) + (rx.cz * rx.cz) -
+                     2 * ((rx.cx * po.x) + (rx.cy * po.y) + (rx.cz * po.z)) - rx.radius * rx.radius;
+    return B * B - 4 * A * C;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_TRAV_MIN_BLOCKS) k_traverse(const __grid_constant__ WaveParams P)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned n_front = (unsigned)min(*P.in_count, P.out_capacity);
+    const unsigned n_all = n_front + (P.in_back ? (unsigned)min(*P.in_back, P.out_capacity - n_front) : 0u);
+    const unsigned n_in = P.todo_list ? (unsigned)*P.todo_count : n_all;
+    if (n_in < P.split_below || P.n_tris == 0) return;        // thin wave: the fused kernel behind this one takes it
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(P.wave_segs + P.wave_index, (unsigned long long)n_all);
+        atomicAdd(&P.counters->segments, (unsigned long long)n_all);
+    }
+    unsigned *work = reinterpret_cast<unsigned *>(P.work_counter);
+    constexpr int SENT = 0x7fffffff;
+    constexpr unsigned FULL = 0xffffffffu;
+    const double tmin_d = (double)SCENE_EPS, tmax_d = (double)RT_DEFAULT_MAX_F;
+    // Register budget: the node loop needs the eight packed slab constants, the triangle test needs the fp64 ray and
+    // ~50 registers of fp64 temporaries — never both.  So the constants are parked in shared memory when a ray is
+    // fetched and re-read after every leaf visit (volatile: the old values are dead across the leaf code), and the fp64
+    // origin / direction are re-read from the queue (L1/L2-resident: this warp fetched them) when a leaf is reached.
+    __shared__ ulonglong2 s_const[4][RTS_WAVE_BLOCK];
+    int stack[RTS_STACK_DEPTH];
+    int sp = 0, cur = SENT;
+    bool have = false;
+    unsigned idx = 0;
+    u64 inv_xy = 0, noi_xy = 0, ainv_xy = 0, e_xy = 0, inv_zz = 0, noi_zz = 0, ainv_zz = 0, e_zz = 0;
+    float best_t = RT_DEFAULT_MAX_F, best_pad = CUDART_INF_F;
+    int best_pos = -1;
+    uint32_t best_id = 0xffffffffu;
+    unsigned chunk_next = 0, chunk_end = 0;   // warp-uniform: the warp's reservation of queue entries
+    bool exhausted = false;
+    unsigned n_nodes = 0, n_tris = 0;
+
+    for (;;) {
+        const unsigned need = __ballot_sync(FULL, !have);
+        if (need) {
+            const unsigned n_need = __popc(need);
+            if (n_need >= RTS_FETCH_THRESH && !(exhausted && chunk_next >= chunk_end)) {
+                if (chunk_next >= chunk_end) {
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(work, RTS_TRAV_CHUNK);
+                    base = __shfl_sync(FULL, base, 0);
+                    chunk_next = min(base, n_in);
+                    chunk_end = min(base + RTS_TRAV_CHUNK, n_in);
+                    if (base + RTS_TRAV_CHUNK >= n_in) exhausted = true;
+                }
+                const unsigned avail = chunk_end - chunk_next;
+                const unsigned rank = __popc(need & ((1u << lane) - 1u));
+                if (!have && rank < avail) {
+                    const unsigned entry = chunk_next + rank;
+                    idx = P.todo_list ? P.todo_list[entry] : queue_slot(P, entry, n_front);
+                    const float oo[3] = {(float)__ldg(P.in.f[F_OX] + idx), (float)__ldg(P.in.f[F_OY] + idx), (float)__ldg(P.in.f[F_OZ] + idx)};
+                    const float dd[3] = {(float)__ldg(P.in.f[F_DX] + idx), (float)__ldg(P.in.f[F_DY] + idx), (float)__ldg(P.in.f[F_DZ] + idx)};
+                    float inv[3], noi[3], ainv[3], E[3];
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {          // the constants of traverse(): same error bound
+                        if (!(fabsf(dd[a]) >= 1e-20f)) {
+                            inv[a] = 0.f; noi[a] = 0.f; ainv[a] = 0.f; E[a] = CUDART_INF_F;
+                        } else {
+                            float r;
+                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(dd[a]));
+                            inv[a] = r;
+                            noi[a] = -(oo[a] * r);
+                            ainv[a] = fabsf(r);
+                            E[a] = 9.5367431640625e-07f * ((P.scene_abs[a] + fabsf(oo[a])) * ainv[a]) + 1e-30f;
+                        }
+                    }
+                    inv_xy = pk2(inv[0], inv[1]); noi_xy = pk2(noi[0], noi[1]); ainv_xy = pk2(ainv[0], ainv[1]); e_xy = pk2(E[0], E[1]);
+                    inv_zz = pk2(inv[2], inv[2]); noi_zz = pk2(noi[2], noi[2]); ainv_zz = pk2(ainv[2], ainv[2]); e_zz = pk2(E[2], E[2]);
+                    s_const[0][threadIdx.x] = make_ulonglong2(inv_xy, noi_xy);
+                    s_const[1][threadIdx.x] = make_ulonglong2(ainv_xy, e_xy);
+                    s_const[2][threadIdx.x] = make_ulonglong2(inv_zz, noi_zz);
+                    s_const[3][threadIdx.x] = make_ulonglong2(ainv_zz, e_zz);
+                    best_t = RT_DEFAULT_MAX_F; best_pad = CUDART_INF_F; best_pos = -1; best_id = 0xffffffffu;
+                    sp = 0; cur = P.root_ref;
+                    have = true;
+                }
+                chunk_next += min(n_need, avail);
+            }
+            if (exhausted && chunk_next >= chunk_end && !__any_sync(FULL, have)) break;
+        }
+        // descend until this lane stands on a leaf or has nothing left (the "while-while" loop of traverse())
+        while ((unsigned)cur < (unsigned)SENT) {
+            if (COUNT) n_nodes++;
+            const ulonglong2 *np = reinterpret_cast<const ulonglong2 *>(P.nodes + cur);
+            const ulonglong2 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
+            const int2 refs = __ldg(reinterpret_cast<const int2 *>(np + 3));
+            const u64 T0 = fma2(q0.x, inv_xy, noi_xy), H0 = fma2(q0.y, ainv_xy, e_xy);
+            const u64 T1 = fma2(q1.x, inv_xy, noi_xy), H1 = fma2(q1.y, ainv_xy, e_xy);
+            const u64 Tz = fma2(q2.x, inv_zz, noi_zz), Hz = fma2(q2.y, ainv_zz, e_zz);
+            float n0x, n0y, f0x, f0y, n1x, n1y, f1x, f1y, nz0, nz1, fz0, fz1;
+            upk2(sub2(T0, H0), n0x, n0y); upk2(add2(T0, H0), f0x, f0y);
+            upk2(sub2(T1, H1), n1x, n1y); upk2(add2(T1, H1), f1x, f1y);
+            upk2(sub2(Tz, Hz), nz0, nz1); upk2(add2(Tz, Hz), fz0, fz1);
+            const float tn0 = fmaxf(fmaxf(n0x, n0y), nz0), tf0 = fminf(fminf(f0x, f0y), fz0);
+            const float tn1 = fmaxf(fmaxf(n1x, n1y), nz1), tf1 = fminf(fminf(f1x, f1y), fz1);
+            const bool h0 = fmaxf(tn0, 0.f) <= fminf(tf0, best_pad);
+            const bool h1 = fmaxf(tn1, 0.f) <= fminf(tf1, best_pad);
+            if (h0 & h1) {
+                const bool swap = tn1 < tn0;
+                if (sp < RTS_STACK_DEPTH) stack[sp++] = swap ? refs.x : refs.y;
+                else atomicAdd(&P.counters->overflow, 1ull);    // never seen; not worth a register
+                cur = swap ? refs.y : refs.x;
+            } else if (h0) cur = refs.x;
+            else if (h1) cur = refs.y;
+            else cur = sp ? stack[--sp] : SENT;
+        }
+        __syncwarp();
+        if (have) {
+            unsigned il;   // idx, laundered: otherwise the six queue addresses formed at fetch time stay live across the node loop (12 registers)
+            asm volatile("mov.u32 %0, %1;" : "=r"(il) : "r"(idx));
+            const d3 o = mk3(__ldg(P.in.f[F_OX] + il), __ldg(P.in.f[F_OY] + il), __ldg(P.in.f[F_OZ] + il));
+            const d3 dir = mk3(__ldg(P.in.f[F_DX] + il), __ldg(P.in.f[F_DY] + il), __ldg(P.in.f[F_DZ] + il));
+            if (cur < 0) {
+                const int code = ~cur;
+                const int first = code >> 3, cnt = (code & 7) + 1;
+                for (int k = 0; k < cnt; k++) {
+                    if (COUNT) n_tris++;
+                    const Tri T = load_tri(P.trirec, first + k);
+                    double t;
+                    if (tri_accept(T, o, dir, tmin_d, tmax_d, t)) {
+                        const float tf = (float)t;
+                        if (tf > SCENE_EPS && (tf < best_t || (tf == best_t && T.id < best_id))) {
+                            best_t = tf; best_pos = first + k; best_id = T.id;
+                            best_pad = tf * 1.000001f;
+                        }
+                    }
+                }
+                cur = sp ? stack[--sp] : SENT;
+            }
+            if (cur == SENT) {                         // this ray's closest hit is known
+                unsigned long long word;
+                if (best_pos >= 0) word = ((unsigned long long)__float_as_uint(best_t) << 32) | (unsigned long long)(uint32_t)best_pos;
+                else {
+                    bool keep = P.split_keep_all != 0;
+                    for (unsigned j = 0; j < P.n_rx && !keep; j++) keep = rx_discriminant(o, dir, P.rx[j]) > 0.f;
+                    word = keep ? TRAV_MISS : TRAV_DEAD;
+                }
+                __stcs(P.trav_hits + idx, word);
+                have = false;
+            }
+            {
+                // back to the node loop: the slab constants come back from shared memory (also on the path of a finished
+                // ray, so that on no path the old values have to survive the triangle code above)
+                const unsigned a0 = (unsigned)__cvta_generic_to_shared(&s_const[0][threadIdx.x]);
+                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(inv_xy), "=l"(noi_xy) : "r"(a0));
+                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(ainv_xy), "=l"(e_xy) : "r"(a0 + (unsigned)sizeof(ulonglong2) * RTS_WAVE_BLOCK));
+                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(inv_zz), "=l"(noi_zz) : "r"(a0 + 2u * (unsigned)sizeof(ulonglong2) * RTS_WAVE_BLOCK));
+                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(ainv_zz), "=l"(e_zz) : "r"(a0 + 3u * (unsigned)sizeof(ulonglong2) * RTS_WAVE_BLOCK));
+            }
+        }
+    }
+    if (COUNT) {
+        unsigned long long *c = reinterpret_cast<unsigned long long *>(P.counters);
+        const unsigned a = __reduce_add_sync(FULL, n_nodes), b = __reduce_add_sync(FULL, n_tris);
+        if (lane == 0) { atomicAdd(c + 7, (unsigned long long)a); atomicAdd(c + 8, (unsigned long long)b); }
+    }
+}
+
+// The shading half: queue order, survivors only.
+template <bool RECORDS>
+__global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_shade_wave(const __grid_constant__ WaveParams P)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned n_front = (unsigned)min(*P.in_count, P.out_capacity);
+    const unsigned n_all = n_front + (P.in_back ? (unsigned)min(*P.in_back, P.out_capacity - n_front) : 0u);
+    const unsigned n_in = P.todo_list ? (unsigned)*P.todo_count : n_all;
+    if (n_in < P.split_below || P.n_tris == 0) return;
+    Local L = {0, 0, 0, 0, 0};
+    const unsigned stride = gridDim.x * blockDim.x;
+    for (unsigned entry = blockIdx.x * blockDim.x + threadIdx.x; entry < n_in; entry += stride) {
+        const unsigned idx = P.todo_list ? P.todo_list[entry] : queue_slot(P, entry, n_front);
+        const unsigned long long word = __ldcs(P.trav_hits + idx);
+        if (word == TRAV_DEAD) continue;
+        Ray r;
+        load_ray_geom(P.in, idx, r);
+        r.meta &= ~M_COH;
+        load_ray_rest(P.in, idx, r, RECORDS, P.rMax != 0);
+        if (word != TRAV_MISS) {
+            HitRec h;
+            h.pos = (int)(uint32_t)word; h.t = __uint_as_float((unsigned)(word >> 32)); h.id = 0;
+            L.a += C_HIT;
+            shade<RECORDS>(P, r, h, L, false);
+        } else {
+            const int received = miss<RECORDS>(P, r, L);
+            if (received >= 0) {
+                L.a += C_CAPTURED;
+                if (P.flags & RTS_OUT_BINS) accumulate_bin(P, r, received);
+            }
+        }
+    }
+    unsigned long long *c = reinterpret_cast<unsigned long long *>(P.counters);
+    const unsigned f[7] = {(unsigned)(L.a & 0x1fffff), (unsigned)((L.a >> 21) & 0x1fffff), (unsigned)(L.a >> 42),
+                           (unsigned)(L.b & 0x1fffff), (unsigned)((L.b >> 21) & 0x1fffff), (unsigned)(L.b >> 42), L.overflow};
+    const int slot[7] = {1, 2, 3, 4, 5, 6, 9};
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+        const unsigned x = __reduce_add_sync(0xffffffffu, f[k]);
+        if (lane == 0 && x) atomicAdd(c + slot[k], (unsigned long long)x);
+    }
+}

@@ -657,6 +657,7 @@ __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r
 
 #include "raster.cuh"
 #include "coherent.cuh"
+#include "split.cuh"
 
 template <bool PRIMARY, bool RECORDS, bool COUNT, bool CHAIN>
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_PRIMARY : RTS_WAVE_MIN_BLOCKS) k_wave(const __grid_constant__ WaveParams P)
@@ -664,9 +665,11 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
     if (PRIMARY && P.raster_ctl && raster_on(P)) return;   // the projected primary wave (raster.cuh) did this batch
     const unsigned lane = threadIdx.x & 31u;
     // queue capacity and batch size are < 2^26, so 32-bit indices and a 32-bit work counter suffice
-    const unsigned n_front = PRIMARY ? (unsigned)P.n_primary : (unsigned)*P.in_count;
-    const unsigned n_all = n_front + ((!PRIMARY && P.in_back) ? (unsigned)*P.in_back : 0u);
+    // a queue that overflowed in the previous wave holds out_capacity entries, however far its counters ran on
+    const unsigned n_front = PRIMARY ? (unsigned)P.n_primary : (unsigned)min(*P.in_count, P.out_capacity);
+    const unsigned n_all = n_front + ((!PRIMARY && P.in_back) ? (unsigned)min(*P.in_back, P.out_capacity - n_front) : 0u);
     const unsigned n_in = (!PRIMARY && P.todo_list) ? (unsigned)*P.todo_count : n_all;
+    if (!PRIMARY && P.split_on && n_in >= P.split_below && P.n_tris != 0) return;   // k_traverse + k_shade_wave did this wave (split.cuh)
     unsigned *work = reinterpret_cast<unsigned *>(P.work_counter);
     Local L = {0, 0, 0, 0, 0};
     // Thin late waves (a few thousand rays whose latency, not throughput, sets the launch time) follow their
@@ -807,6 +810,38 @@ int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool rec
     return RTS_OK;
 }
 
+// The two-kernel form of a later wave (split.cuh), enqueued ahead of the fused kernel; each of the three decides from
+// the wave's size on the device whether it is the one to run.
+int trace_launch_split(rts_engine *e, WaveParams &p, bool records)
+{
+    if (e->trav_alloc < e->q_capacity) {
+        if (e->d_trav_hits) cudaFree(e->d_trav_hits);
+        e->d_trav_hits = nullptr; e->trav_alloc = 0;
+        RTS_CUDA(cudaMalloc(&e->d_trav_hits, sizeof(unsigned long long) * e->q_capacity));
+        e->trav_alloc = e->q_capacity;
+    }
+    if (!e->trav_grid) {
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<false>, RTS_WAVE_BLOCK, 0);
+        e->trav_grid = e->num_sms * (occ > 0 ? occ : 1);
+    }
+    p.trav_hits = e->d_trav_hits;
+    p.split_on = 1;
+    // p.split_below: set by the caller (knob; default 2^18 rays)
+    p.split_keep_all = records ? 1u : 0u;
+    const bool timed = p.wave_index == 1 && e->split_ev[0];   // the second wave's two kernels, timed apart (rts_get_split_profile)
+    if (timed) cudaEventRecord(e->split_ev[0], e->stream);
+    if (p.flags & RTS_COUNT_NODES) k_traverse<true><<<e->trav_grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
+    else k_traverse<false><<<e->trav_grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
+    if (timed) cudaEventRecord(e->split_ev[1], e->stream);
+    if (records) k_shade_wave<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
+    else k_shade_wave<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
+    if (timed) { cudaEventRecord(e->split_ev[2], e->stream); e->split_timed = true; }
+    RTS_CUDA(cudaGetLastError());
+    e->launches += 2;
+    return RTS_OK;
+}
+
 #define RTS_RASTER_ITEM_CAP (1u << 20)
 
 int trace_raster_alloc(rts_engine *e, uint64_t batch)
@@ -877,7 +912,7 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     // triangles of the moving targets on top of a copy.  Needs the moving-target lists of the partial refit (bvh.cu).
     uint32_t n_moving = 0;
     for (uint32_t k = 0; k < e->n_targets; k++) n_moving += e->moving[k] ? 1u : 0u;
-    const bool cacheable = reuse && single_batch && !getenv("RTS_NO_STATIC_HITS") && (n_moving == 0 || e->partial_ready);
+    const bool cacheable = reuse && single_batch && !e->knobs.no_static_hits && (n_moving == 0 || e->partial_ready);
     e->coh_on = false;
     if (cacheable) {
         const bool valid = e->static_valid && same_launch && e->static_scene_version == e->scene_version &&
@@ -898,7 +933,7 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
         }
         p.raster_static = (const RasterCtl *)e->d_raster_ctl_static;
         // kept first-reflection hits (coherent.cuh): same conditions, plus few enough movers to test their boxes one by one
-        e->coh_on = n_moving <= 32 && p.dMax >= 2 && !getenv("RTS_NO_KEPT_REFLECTIONS");
+        e->coh_on = n_moving <= 32 && p.dMax >= 2 && !e->knobs.no_kept_reflections;
         if (e->coh_on) {
             const bool w1_ok = valid && e->w1_valid && e->w1_builds == e->builds && e->w1_interp == p.interpolate &&
                                e->w1_dmax == p.dMax && e->w1_rmax == p.rMax;

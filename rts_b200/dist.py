@@ -61,7 +61,16 @@ _views = {}
 
 def allreduce_bins(engine, device, group=None):
     """All-reduce the engine's bins in place over NCCL, then mark them final (myKernel2 runs at collection).
-    The zero-copy views are cached per (engine, device pointers)."""
+    The zero-copy views are cached per (engine, device pointers).
+
+    Ordering: NCCL enqueues on torch's current stream of `device`, the engine on its own stream.  The helper makes the
+    two the same stream (engine.set_stream, once — it waits for the engine's earlier work), so that the all-reduce runs
+    behind the pulse that filled the bins (also an RTS_ASYNC one) and rts_finalise_bins behind the all-reduce."""
+    import torch
+
+    cur = torch.cuda.current_stream(device).cuda_stream or 1     # 0 is the legacy default stream: its explicit handle is cudaStreamLegacy (0x1)
+    if getattr(engine, "_stream", None) != cur:
+        engine.set_stream(cur)
     key = (id(engine),) + tuple(engine.bins_device())
     if key not in _views:
         _views.clear()

@@ -47,11 +47,11 @@ class RtsBvhInfo(C.Structure):
 
 #: every symbol include/rts_b200.h declares (tests/test_abi.py checks the library exports them all)
 EXPORTS = [
-    "rts_create", "rts_destroy", "rts_last_error", "rts_version", "rts_abi_sizes", "rts_set_stream",
+    "rts_create", "rts_destroy", "rts_last_error", "rts_version", "rts_abi_sizes", "rts_set_stream", "rts_set_option",
     "rts_rx_sphere_from_desc", "rts_result_sizes", "rts_rect_mesh", "rts_sphere_mesh", "rts_file_mesh",
     "rts_rotation_matrix", "rts_scene_set_targets", "rts_scene_set_poses", "rts_scene_rebuild", "rts_scene_bvh_info",
     "rts_scene_get_world_vertices", "rts_scene_get_tri_bounds", "rts_scene_check_bvh", "rts_trace_pulse",
-    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_kernel_launches", "rts_probe_read_bandwidth", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_get_received", "rts_bins_device", "rts_finalise_bins", "rts_aggregate",
+    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_get_split_profile", "rts_kernel_launches", "rts_probe_read_bandwidth", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_get_records_shard", "rts_get_received", "rts_bins_device", "rts_finalise_bins", "rts_aggregate",
 ]
 
 _lib = None
@@ -74,6 +74,7 @@ def load() -> C.CDLL:
     lib.rts_version.restype = C.c_char_p
     lib.rts_abi_sizes.argtypes = [P(u32)]
     lib.rts_set_stream.argtypes = [vp, vp]
+    lib.rts_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.rts_rx_sphere_from_desc.argtypes = [P(RtsRxDesc), P(RtsRxSphere)]
     lib.rts_rx_sphere_from_desc.restype = None
     lib.rts_result_sizes.argtypes = [P(RtsPulse), P(RtsSizes)]
@@ -94,11 +95,13 @@ def load() -> C.CDLL:
     lib.rts_sync.argtypes = [vp]
     lib.rts_get_stats.argtypes = [vp, P(RtsStats)]
     lib.rts_get_wave_profile.argtypes = [vp, u32, P(C.c_float), P(u64), P(u32)]
+    lib.rts_get_split_profile.argtypes = [vp, P(C.c_float)]
     lib.rts_kernel_launches.argtypes = [vp, P(u64)]
     lib.rts_probe_read_bandwidth.argtypes = [vp, u64, u32, P(dbl)]
     lib.rts_get_bins.argtypes = [vp, P(RtsBin), u32, P(u32)]
     lib.rts_get_responses.argtypes = [vp, P(RtsResponse), u32, P(u32)]
     lib.rts_get_records.argtypes = [vp, vp, P(i32), P(dbl), P(i32)]
+    lib.rts_get_records_shard.argtypes = [vp, P(u64), vp, P(i32), P(dbl), P(i32)]
     lib.rts_get_received.argtypes = [vp, u64, P(u64), P(u64), vp, P(i32), P(dbl)]
     lib.rts_bins_device.argtypes = [vp, P(vp), P(u64), P(vp), P(u64)]
     lib.rts_finalise_bins.argtypes = [vp]
@@ -175,6 +178,7 @@ class Engine:
         _check(self._lib.rts_create(int(device), C.byref(self._h)))
         self._scene: Optional[CScene] = None
         self._pulse: Optional[CPulse] = None
+        self._stream = None            # cudaStream_t the engine was last pointed at (None: its own)
 
     def close(self):
         if self._h:
@@ -256,6 +260,12 @@ class Engine:
         _check(self._lib.rts_get_wave_profile(self._h, 32, ms, seg, C.byref(n)))
         return [(float(ms[i]), int(seg[i])) for i in range(n.value)]
 
+    def split_profile(self):
+        """(ms of k_traverse, ms of k_shade_wave) of the last pulse's second wave; (0, 0) when it ran fused."""
+        ms = (C.c_float * 2)()
+        _check(self._lib.rts_get_split_profile(self._h, ms))
+        return float(ms[0]), float(ms[1])
+
     def kernel_launches(self) -> int:
         v = C.c_uint64()
         _check(self._lib.rts_kernel_launches(self._h, C.byref(v)))
@@ -298,6 +308,23 @@ class Engine:
             tp.ctypes.data_as(C.POINTER(C.c_int32)) if tri_path else None))
         return res, ti[:, :D], (rc[:, :D] if rcs else None), tp
 
+    def records_shard(self, rcs=True, tri_path=True):
+        """Records of the last pulse's shard only, compact: ray k of the shard has slot s at index k + s*n_shard.
+        Returns (results, targ_intersect, rcs_angle, tri_path, n_shard)."""
+        spec = self._pulse.spec
+        ns = C.c_uint64()
+        _check(self._lib.rts_get_records_shard(self._h, C.byref(ns), None, None, None, None))
+        n, D, W = int(ns.value) * spec.slots, spec.depth_total, spec.tri_cols
+        res = np.zeros(n, dtype=RAY_RECORD)
+        ti = np.zeros((n, max(D, 1)), dtype=np.int32)
+        rc = np.zeros((n, max(D, 1), 2)) if rcs else None
+        tp = np.zeros((n, W), dtype=np.int32) if tri_path else None
+        _check(self._lib.rts_get_records_shard(
+            self._h, C.byref(ns), res.ctypes.data_as(C.c_void_p), ti.ctypes.data_as(C.POINTER(C.c_int32)),
+            rc.ctypes.data_as(C.POINTER(C.c_double)) if rcs else None,
+            tp.ctypes.data_as(C.POINTER(C.c_int32)) if tri_path else None))
+        return res, ti[:, :D], (rc[:, :D] if rcs else None), tp, int(ns.value)
+
     def received(self):
         """Received rays only, in slot order: (results, targ_intersect [R,D], rcs_angle [R,D,2], slots [R])
         — ray_tracer.cpp:1190-1221 before the RCS / gain callbacks."""
@@ -325,8 +352,14 @@ class Engine:
     def finalise_bins(self):
         _check(self._lib.rts_finalise_bins(self._h))
 
+    def set_option(self, name: str, value: int):
+        """Tuning / test switch (include/rts_b200.h: rts_set_option); RTS_<NAME> in the environment sets the initial value."""
+        _check(self._lib.rts_set_option(self._h, name.encode(), int(value)))
+
     def set_stream(self, cuda_stream: int):
-        _check(self._lib.rts_set_stream(self._h, C.c_void_p(cuda_stream)))
+        """Run the engine's work on this cudaStream_t (0 / None: back to the engine's own stream); waits for earlier work."""
+        _check(self._lib.rts_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+        self._stream = cuda_stream or None
 
     def aggregate(self, rx_results: np.ndarray, rx_intersects: np.ndarray, cspeed: float, carrier: float, ray_total: int):
         """rs::kernel_wrapper contract (aggregation.cu:103-184): returns dict of the written-back arrays."""

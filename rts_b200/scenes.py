@@ -14,10 +14,30 @@ from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from . import lib
 from .abi import PulseSpec, Target
 
 C0 = 299792458.0
+
+
+class _Helpers:
+    """Where rect_mesh / sphere_mesh / rotation_matrix / rx_sphere_from_desc come from: the product library's host
+    helpers by default (loaded on first use).  bench.py's reference arm installs the oracle's own restatements with
+    set_helpers() so that the reference process never maps librts_b200.so."""
+    _impl = None
+
+    def __getattr__(self, name):
+        if _Helpers._impl is None:
+            from . import lib as _lib
+            _Helpers._impl = _lib
+        return getattr(_Helpers._impl, name)
+
+
+lib = _Helpers()
+
+
+def set_helpers(module) -> None:
+    """Use `module` (rect_mesh, sphere_mesh, rotation_matrix, rx_sphere_from_desc) for the generated geometry."""
+    _Helpers._impl = module
 
 
 def _rx(position, azimuth, elevation, radius, theta_span=2.0, phi_span=2.0):

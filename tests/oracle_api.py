@@ -57,7 +57,10 @@ def oracle() -> C.CDLL:
         lib.orc_file_mesh.argtypes = [C.c_char_p, C.c_char_p] + [C.c_float] * 3 + tail
         lib.orc_vertex_rotation.argtypes = [P(dbl), u32, C.c_float, C.c_float, C.c_float]
         lib.orc_vertex_rotation.restype = None
+        lib.orc_trace_shard.argtypes = lib.orc_trace.argtypes
         lib.orc_num_threads.restype = C.c_int
+        lib.orc_set_num_threads.argtypes = [C.c_int]
+        lib.orc_set_num_threads.restype = None
         lib.orc_version.restype = C.c_char_p
         _oracle = lib
     return _oracle
@@ -97,6 +100,33 @@ def trace(targets, spec: PulseSpec, use_bvh=False):
     assert rc == 0, rc
     D = spec.depth_total
     return dict(results=res, targ_intersect=ti[:, :D], rcs_angle=rcs[:, :D], tri_path=tp, edge=edge, stats=st.as_dict())
+
+
+def shard_size(spec: PulseSpec) -> int:
+    """Number of primary rays a spec's ray_begin / ray_count / ray_stride select (api.cu / shard_bounds)."""
+    rays = spec.rays
+    b = min(spec.ray_begin, rays)
+    e = min(rays, spec.ray_begin + spec.ray_count) if spec.ray_count else rays
+    s = spec.ray_stride or 1
+    return max(0, (max(e, b) - b + s - 1) // s)
+
+
+def trace_shard(targets, spec: PulseSpec, use_bvh=True):
+    """Oracle launch of a shard of a large grid with compact outputs: ray k of the shard has slot s at k + s*n_shard."""
+    cs, cp = CScene(targets), CPulse(spec, len(targets))
+    n_sh, M, D, W = shard_size(spec), spec.slots, spec.depth_total, spec.tri_cols
+    n = n_sh * M
+    res = np.zeros(n, dtype=RAY_RECORD)
+    ti = np.zeros((n, max(D, 1)), dtype=np.int32)
+    rcs = np.zeros((n, max(D, 1), 2))
+    tp = np.zeros((n, W), dtype=np.int32)
+    edge = np.zeros(n_sh, dtype=np.uint8)
+    st = RtsStats()
+    rc = oracle().orc_trace_shard(cs.array, cs.n, C.byref(cp.c), int(use_bvh), res.ctypes.data_as(C.c_void_p),
+                                  ti.ctypes.data_as(C.POINTER(C.c_int32)), rcs.ctypes.data_as(C.POINTER(C.c_double)),
+                                  tp.ctypes.data_as(C.POINTER(C.c_int32)), edge.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(st))
+    assert rc == 0, rc
+    return dict(results=res, targ_intersect=ti[:, :D], rcs_angle=rcs[:, :D], tri_path=tp, edge=edge, stats=st.as_dict(), n_shard=n_sh)
 
 
 def trace_bins(targets, spec: PulseSpec, use_bvh=True, cap=1 << 16):
@@ -221,6 +251,19 @@ def sphere_mesh(subdivs, radius, yaw=0.0, pitch=0.0, roll=0.0):
 
 def file_mesh(v_file, n_file, yaw=0.0, pitch=0.0, roll=0.0):
     return _mesh(oracle().orc_file_mesh, str(v_file).encode(), str(n_file).encode(), C.c_float(yaw), C.c_float(pitch), C.c_float(roll))
+
+
+def rotation_matrix(yaw, pitch, roll) -> np.ndarray:
+    """Rz*Ry*Rx with the reference's float angles (ray_tracer.cpp:156-162): the rotated unit vectors are R's columns."""
+    e = np.eye(3)
+    oracle().orc_vertex_rotation(e.ctypes.data_as(C.POINTER(C.c_double)), 3, C.c_float(yaw), C.c_float(pitch), C.c_float(roll))
+    return np.ascontiguousarray(e.T)
+
+
+def set_num_threads(n: int) -> int:
+    """OpenMP threads of the following oracle runs; returns the count in effect."""
+    oracle().orc_set_num_threads(int(n))
+    return int(oracle().orc_num_threads())
 
 
 def rx_sphere_from_desc(position, azimuth, elevation, radius, theta_span, phi_span) -> RtsRxSphere:

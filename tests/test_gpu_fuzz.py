@@ -32,24 +32,41 @@ def test_random_soups_match_the_exhaustive_oracle(engine, seed):
     assert engine.check_bvh() == 0
     # the same launch through the BVH primary wave instead of the projection must give the same records
     if spec.grid[0] == 1:
-        import os
-        os.environ["RTS_NO_RASTER"] = "1"
+        engine.set_option("no_raster", 1)
         try:
             recs2, gbins2, st2 = parity.run_gpu_records(engine, targets, spec)
         finally:
-            del os.environ["RTS_NO_RASTER"]
+            engine.set_option("no_raster", 0)
         parity.assert_records_equal(parity.compare_records(recs2, orc, spec, f"fuzz/{seed}/bvh"))
         assert st2["primary_projected"] == 0 and st["primary_projected"] == 1
     # the launch cut into batches of an odd size (RTS_BATCH: the 2^24-ray batching of large launches at test size)
-    import os
-    os.environ["RTS_BATCH"] = str(257 + 64 * seed)
+    engine.set_option("batch", 257 + 64 * seed)
     try:
         recs3, gbins3, st3 = parity.run_gpu_records(engine, targets, spec)
     finally:
-        del os.environ["RTS_BATCH"]
+        engine.set_option("batch", 0)
     parity.assert_records_equal(parity.compare_records(recs3, orc, spec, f"fuzz/{seed}/batched"))
     parity.assert_bins_close(parity.compare_bins(gbins3, obins))
     assert st3["segments"] == st["segments"] and st3["hits"] == st["hits"]
+    # every later wave through the two-kernel form (split.cuh: k_traverse + k_shade_wave), which large waves take by
+    # themselves: records mode keeps every ray, bins-only mode drops the rays that can no longer change an output
+    engine.set_option("split_below", 0)
+    try:
+        recs4, gbins4, st4 = parity.run_gpu_records(engine, targets, spec)
+        st5 = engine.trace(spec, L.RTS_OUT_BINS | L.RTS_NO_REUSE)
+        gbins5 = engine.bins()
+        engine.set_option("no_raster", 1)
+        st6 = engine.trace(spec, L.RTS_OUT_BINS | L.RTS_COUNT_NODES)
+        gbins6 = engine.bins()
+    finally:
+        engine.set_option("split_below", 1 << 18)
+        engine.set_option("no_raster", 0)
+    parity.assert_records_equal(parity.compare_records(recs4, orc, spec, f"fuzz/{seed}/split"))
+    parity.assert_bins_close(parity.compare_bins(gbins4, obins))
+    parity.assert_bins_close(parity.compare_bins(gbins5, obins))
+    parity.assert_bins_close(parity.compare_bins(gbins6, obins))
+    for k in ("segments", "hits", "shaded_hits", "refracted", "captured"):
+        assert st4[k] == st[k] and st5[k] == st[k] and st6[k] == st[k], (k, st[k], st4[k], st5[k], st6[k])
 
 
 @pytest.mark.parametrize("seed", range(6))
@@ -62,6 +79,7 @@ def test_random_moving_scenes_with_between_pulse_reuse(engine, seed):
                               movers=int(rng.integers(1, 9)), n_rx=int(rng.integers(1, 4)), seed=0x52545301 + 17 * seed)
     engine.set_targets(ms.base)
     order = [0, 1, 1, 4, 2, 2, 7, 3]
+    engine.set_option("split_below", 0 if seed % 2 else 1 << 18)    # odd seeds: later waves through k_traverse + k_shade_wave
     for i, p in enumerate(order):
         engine.set_poses(*ms.poses(p))
         spec = ms.spec_for(p)
@@ -72,6 +90,7 @@ def test_random_moving_scenes_with_between_pulse_reuse(engine, seed):
         for k in ("segments", "hits", "shaded_hits", "captured"):
             assert st[k] == ost[k], (seed, i, p, k, st[k], ost[k])
         parity.assert_bins_close(parity.compare_bins(engine.bins(), obins))
+    engine.set_option("split_below", 1 << 18)
     assert engine.check_bvh() == 0
 
 

@@ -318,10 +318,12 @@ def test_projected_primary_wave_is_bit_identical(engine, name, monkeypatch):
     engine.set_targets(targets)
     for shard in ((0, 0, 0), (1, 0, 4)):
         spec.ray_begin, spec.ray_count, spec.ray_stride = shard
-        monkeypatch.setenv("RTS_NO_RASTER", "1")
-        st0 = engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_OUT_BINS)
-        a, bins_a = engine.records(), engine.bins()
-        monkeypatch.delenv("RTS_NO_RASTER", raising=False)
+        engine.set_option("no_raster", 1)
+        try:
+            st0 = engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_OUT_BINS)
+            a, bins_a = engine.records(), engine.bins()
+        finally:
+            engine.set_option("no_raster", 0)
         st1 = engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_OUT_BINS)
         b, bins_b = engine.records(), engine.bins()
         for k in ("segments", "hits", "shaded_hits", "captured", "edge_rays"):

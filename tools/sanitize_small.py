@@ -17,9 +17,9 @@ def main():
         rr = eng.received()
         if len(rr[0]):
             eng.aggregate(rr[0], rr[1], s.cspeed, s.carrier, ray_total=s.ray_total)
-        os.environ["RTS_NO_RASTER"] = "1"
+        eng.set_option("no_raster", 1)
         eng.trace(s, L.RTS_OUT_BINS)
-        del os.environ["RTS_NO_RASTER"]
+        eng.set_option("no_raster", 0)
         print(name, st["segments"], st["hits"], len(bins), len(resp), len(rr[0]))
     ms = scenes.terrain_scene(n=96, cells_x=64, cells_y=40, movers=6, n_rx=2)     # 5120 + mover triangles: partial refit path
     eng.set_targets(ms.base)
