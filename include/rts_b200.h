@@ -83,7 +83,8 @@ int         rts_set_stream(rts_engine *e, void *cuda_stream);
  * ray_tracer.cpp:512).  The environment variable RTS_<NAME> gives an option its initial value when the engine is created;
  * the environment is never read again afterwards.  Names: "bvh" (0 = choose by SAH cost, 1 = Morton radix tree, 2 = PLOC),
  * "leaf_max" (1..8), "no_chain", "no_raster", "no_tiles", "one_ended_queue", "debug_raster", "no_static_hits",
- * "no_kept_reflections", "no_split", "split_below" (rays), "no_graph", "batch" (primaries per batch, 0 = 2^24). */
+ * "no_kept_reflections", "no_split", "split_below" (rays), "no_graph", "batch" (primaries per batch, 0 = 2^24),
+ * "hash_bins" (1 = sparse bin table also where a dense one would fit), "hash_log2" (log2 of its slots, default 22). */
 int         rts_set_option(rts_engine *e, const char *name, int64_t value);
 
 /* ---- host helpers (pure host code, usable without a GPU) ---- */
@@ -175,6 +176,14 @@ int rts_get_received(rts_engine *e, uint64_t cap, uint64_t *n, uint64_t *slots, 
  *              reduction over either uint64 or int64 views is correct */
 int rts_bins_device(rts_engine *e, void **sums_device, uint64_t *n_sum_doubles, void **mins_device,
                     uint64_t *n_mins);
+/* The same for pulses whose bins live in the sparse table (more than 2^20 dense bins, or option "hash_bins"; rts_bins_device
+ * then fails with RTS_ERR_STATE).  rts_bins_compact_device gathers this GPU's occupied bins into compact device arrays —
+ * keys uint64[n] (rx * (K+1)^D + path key), sums double[n*5], mins uint64[n] — and returns n (it waits for the pulse).  The
+ * ranks exchange them (all-gather of keys -> sorted union -> SUM / MIN all-reduce over the union, rts_b200/dist.py) and hand
+ * the merged arrays (distinct keys) back with rts_bins_load_compact; then rts_finalise_bins as for the dense table.
+ * Replaces nothing in the reference, which has no multi-GPU path; it groups arbitrary path rows (aggregation.cu:43-57). */
+int rts_bins_compact_device(rts_engine *e, void **keys_device, void **sums_device, void **mins_device, uint32_t *n);
+int rts_bins_load_compact(rts_engine *e, const void *keys_device, const void *sums_device, const void *mins_device, uint32_t n);
 /* Marks the (externally reduced) bins final and enqueues their emission on the engine's stream: call it after the
  * reduction has been enqueued on that same stream (rts_set_stream) or has completed. */
 int rts_finalise_bins(rts_engine *e);

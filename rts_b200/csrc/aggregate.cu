@@ -112,6 +112,103 @@ __global__ void k_emit_bins(const double *__restrict__ sums, const unsigned long
     if (at < cap) out[at] = b;
 }
 
+// ---- sparse bins: the same three steps over the list of occupied slots ----
+__global__ void k_hash_clear(unsigned long long *__restrict__ keys, double *__restrict__ sums, unsigned long long *__restrict__ mins,
+                             const uint32_t *__restrict__ used, const unsigned *__restrict__ count)
+{
+    const unsigned n = *count;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t s = used[i];
+        keys[s] = ~0ull;
+#pragma unroll
+        for (int k = 0; k < 5; k++) sums[(size_t)s * 5 + k] = 0.0;
+        mins[s] = 0x7f7f7f7f7f7f7f7full;
+    }
+}
+__global__ void k_hash_rx_totals(const unsigned long long *__restrict__ keys, const double *__restrict__ sums,
+                                 const unsigned long long *__restrict__ mins, const uint32_t *__restrict__ used,
+                                 const unsigned *__restrict__ count, unsigned long long bins_per_rx, uint32_t n_rx,
+                                 double *__restrict__ rx_sums, unsigned long long *__restrict__ rx_mins)
+{
+    const unsigned n = *count;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t s = used[i];
+        const uint32_t rx = (uint32_t)(keys[s] / bins_per_rx);
+        if (rx >= n_rx || !(sums[(size_t)s * 5] > 0)) continue;
+#pragma unroll
+        for (int k = 0; k < 5; k++) atomicAdd(rx_sums + rx * 5 + k, sums[(size_t)s * 5 + k]);
+        atomicMin(rx_mins + rx, mins[s]);
+    }
+}
+__global__ void k_hash_emit(const unsigned long long *__restrict__ keys, const double *__restrict__ sums,
+                            const unsigned long long *__restrict__ mins, const uint32_t *__restrict__ used,
+                            const unsigned *__restrict__ count, unsigned long long bins_per_rx, uint32_t B, uint32_t D,
+                            const double *__restrict__ rx_sums, const unsigned long long *__restrict__ rx_mins,
+                            rts_bin *__restrict__ out, uint32_t *__restrict__ out_count, uint32_t cap)
+{
+    const unsigned n = *count;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t g = used[i];
+        if (!(sums[(size_t)g * 5] > 0)) continue;
+        const uint32_t rx = (uint32_t)(keys[g] / bins_per_rx);
+        unsigned long long key = keys[g] % bins_per_rx;
+        rts_bin b;
+        b.rx = (int32_t)rx;
+        const bool direct = key == 0;
+        for (uint32_t c = 0; c < RTS_MAX_DEPTH; c++) {
+            b.path[c] = c < D ? (int32_t)(key % B) - 1 : -1;
+            if (c < D) key /= B;
+        }
+        b.direct = direct ? 1 : 0;
+        const double *s = direct ? rx_sums + rx * 5 : sums + (size_t)g * 5;
+        b.npath = s[0]; b.sum_sqrt_power = s[1]; b.sum_delay = s[2]; b.sum_phase = s[3]; b.sum_doppler = s[4];
+        b.min_slot = direct ? rx_mins[rx] : mins[g];
+        b.own_min_slot = mins[g];
+        b.power = pow(b.sum_sqrt_power / b.npath, 2);
+        b.delay = b.sum_delay / b.npath;
+        b.phase = b.sum_phase / b.npath;
+        b.doppler = b.sum_doppler / b.npath;
+        const uint32_t at = atomicAdd(out_count, 1u);
+        if (at < cap) out[at] = b;
+    }
+}
+
+// occupied slots -> compact arrays (keys, five sums, representative slot), for an exchange between GPUs
+__global__ void k_hash_compact(const unsigned long long *__restrict__ keys, const double *__restrict__ sums,
+                               const unsigned long long *__restrict__ mins, const uint32_t *__restrict__ used, unsigned n,
+                               unsigned long long *__restrict__ o_keys, double *__restrict__ o_sums, unsigned long long *__restrict__ o_mins)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = used[i];
+    o_keys[i] = keys[s];
+#pragma unroll
+    for (int k = 0; k < 5; k++) o_sums[(size_t)i * 5 + k] = sums[(size_t)s * 5 + k];
+    o_mins[i] = mins[s];
+}
+// compact arrays (distinct keys) -> the cleared table
+__global__ void k_hash_load(const unsigned long long *__restrict__ i_keys, const double *__restrict__ i_sums,
+                            const unsigned long long *__restrict__ i_mins, unsigned n, unsigned long long *__restrict__ keys,
+                            double *__restrict__ sums, unsigned long long *__restrict__ mins, uint32_t *__restrict__ used,
+                            unsigned *__restrict__ count, unsigned long long mask, unsigned long long *overflow)
+{
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long bin = i_keys[i];
+    unsigned long long h = bin * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+    unsigned long long at = h & mask, probes = 0;
+    for (;; at = (at + 1ull) & mask) {
+        const unsigned long long cur = atomicCAS(keys + at, ~0ull, bin);
+        if (cur == ~0ull) { used[atomicAdd(count, 1u)] = (uint32_t)at; break; }
+        if (cur == bin) break;
+        if (++probes > mask) { atomicAdd(overflow, 1ull); return; }
+    }
+#pragma unroll
+    for (int k = 0; k < 5; k++) atomicAdd(sums + (size_t)at * 5 + k, i_sums[(size_t)i * 5 + k]);
+    atomicMin(mins + at, i_mins[i]);
+}
+
 // ---- received rays, compacted (first half of the host loop ray_tracer.cpp:1190-1258) ----
 struct IsReceived {
     const rts_ray_record *res;
@@ -294,20 +391,100 @@ static void sort_bins(rts_bin *out, uint32_t got)
     });
 }
 
+// The sparse bin table of a pulse: allocated on first use, afterwards cleared by walking the previous pulse's list of
+// occupied slots — clearing, like emission, costs what is occupied, not the table size.
+int agg_hash_prepare(rts_engine *e, uint64_t slots)
+{
+    cudaStream_t st = e->stream;
+    if (e->hash_alloc < slots) {
+        void **ptrs[] = {(void **)&e->d_hash_keys, (void **)&e->d_hash_used, (void **)&e->d_hash_count};
+        for (void **p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+        e->hash_alloc = 0; e->hash_ready = false;
+        RTS_CUDA(cudaMalloc(&e->d_hash_keys, sizeof(unsigned long long) * slots));
+        RTS_CUDA(cudaMalloc(&e->d_hash_used, sizeof(uint32_t) * slots));
+        RTS_CUDA(cudaMalloc(&e->d_hash_count, sizeof(unsigned)));
+        e->hash_alloc = slots;
+    }
+    if (e->hash_ready) {
+        k_hash_clear<<<64, 256, 0, st>>>(e->d_hash_keys, e->d_bin_sums, e->d_bin_mins, e->d_hash_used, e->d_hash_count);
+        e->launches++;
+    } else {
+        RTS_CUDA(cudaMemsetAsync(e->d_hash_keys, 0xff, sizeof(unsigned long long) * slots, st));
+        RTS_CUDA(cudaMemsetAsync(e->d_bin_sums, 0, sizeof(double) * 5 * slots, st));
+        RTS_CUDA(cudaMemsetAsync(e->d_bin_mins, 0x7f, sizeof(unsigned long long) * slots, st));
+    }
+    RTS_CUDA(cudaMemsetAsync(e->d_hash_count, 0, sizeof(unsigned), st));
+    e->hash_ready = true;
+    return RTS_OK;
+}
+
+// Sparse bins, multi-GPU: this rank's occupied bins as compact device arrays (the count comes back to the host: the caller
+// sizes its all-gather with it), and the way back — the table refilled from the merged arrays of all ranks.
+int agg_hash_compact(rts_engine *e, void **keys, void **sums, void **mins, uint32_t *n)
+{
+    cudaStream_t st = e->stream;
+    unsigned count = 0;
+    RTS_CUDA(cudaMemcpyAsync(&count, e->d_hash_count, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    RTS_CUDA(cudaStreamSynchronize(st));
+    if (e->compact_alloc < count) {
+        void **ptrs[] = {(void **)&e->d_ckeys, (void **)&e->d_csums, (void **)&e->d_cmins};
+        for (void **p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+        const size_t cap = std::max<size_t>(1024, (size_t)count * 2);
+        RTS_CUDA(cudaMalloc(&e->d_ckeys, sizeof(unsigned long long) * cap));
+        RTS_CUDA(cudaMalloc(&e->d_csums, sizeof(double) * 5 * cap));
+        RTS_CUDA(cudaMalloc(&e->d_cmins, sizeof(unsigned long long) * cap));
+        e->compact_alloc = cap;
+    }
+    if (count) {
+        k_hash_compact<<<blocks_for(count, 256), 256, 0, st>>>(e->d_hash_keys, e->d_bin_sums, e->d_bin_mins, e->d_hash_used, count,
+                                                              e->d_ckeys, e->d_csums, e->d_cmins);
+        e->launches++;
+        RTS_CUDA(cudaGetLastError());
+    }
+    if (keys) *keys = e->d_ckeys;
+    if (sums) *sums = e->d_csums;
+    if (mins) *mins = e->d_cmins;
+    if (n) *n = count;
+    return RTS_OK;
+}
+
+int agg_hash_load(rts_engine *e, const void *keys, const void *sums, const void *mins, uint32_t n)
+{
+    cudaStream_t st = e->stream;
+    int rc = agg_hash_prepare(e, e->n_bins_dense);
+    if (rc) return rc;
+    if (n > e->n_bins_dense) return rts_fail(RTS_ERR_CAPACITY, "%u merged bins exceed the sparse table's %llu slots (option hash_log2)", n, (unsigned long long)e->n_bins_dense);
+    if (n) {
+        k_hash_load<<<blocks_for(n, 256), 256, 0, st>>>((const unsigned long long *)keys, (const double *)sums, (const unsigned long long *)mins, n,
+                                                       e->d_hash_keys, e->d_bin_sums, e->d_bin_mins, e->d_hash_used, e->d_hash_count,
+                                                       e->n_bins_dense - 1ull, reinterpret_cast<unsigned long long *>(e->d_counters) + 9);
+        e->launches++;
+        RTS_CUDA(cudaGetLastError());
+    }
+    return RTS_OK;
+}
+
 // receiver totals (direct-ray rule) + myKernel2 + compaction of the non-empty bins into d_bins_out, enqueued
 static int enqueue_emit(rts_engine *e, uint32_t cap)
 {
     const uint64_t nb = e->n_bins_dense;
     const uint32_t n_rx = e->last_nrx, B = e->last_B, D = e->last_D;
-    const uint64_t per_rx = nb / n_rx;
+    const uint64_t per_rx = e->bins_hashed ? e->bins_per_rx : nb / n_rx;
     if (!e->d_rx_sums) {
         RTS_CUDA(cudaMalloc(&e->d_rx_sums, sizeof(double) * 5 * RTS_MAX_RX));
         RTS_CUDA(cudaMalloc(&e->d_rx_mins, sizeof(unsigned long long) * RTS_MAX_RX));
     }
     RTS_CUDA(cudaMemsetAsync(e->d_rx_sums, 0, sizeof(double) * 5 * n_rx, e->stream));
     RTS_CUDA(cudaMemsetAsync(e->d_rx_mins, 0xff, sizeof(unsigned long long) * n_rx, e->stream));
-    dim3 grid((unsigned)std::min<uint64_t>(64, (per_rx + 255) / 256), n_rx);
-    { k_rx_totals<<<grid, 256, 0, e->stream>>>(e->d_bin_sums, e->d_bin_mins, per_rx, n_rx, e->d_rx_sums, e->d_rx_mins); e->launches++; }
+    if (e->bins_hashed) {
+        k_hash_rx_totals<<<64, 256, 0, e->stream>>>(e->d_hash_keys, e->d_bin_sums, e->d_bin_mins, e->d_hash_used, e->d_hash_count, per_rx, n_rx,
+                                                    e->d_rx_sums, e->d_rx_mins);
+        e->launches++;
+    } else {
+        dim3 grid((unsigned)std::min<uint64_t>(64, (per_rx + 255) / 256), n_rx);
+        k_rx_totals<<<grid, 256, 0, e->stream>>>(e->d_bin_sums, e->d_bin_mins, per_rx, n_rx, e->d_rx_sums, e->d_rx_mins);
+        e->launches++;
+    }
     const uint64_t want = std::max<uint64_t>(cap, 1);
     if (e->bins_out_alloc < want) {
         if (e->d_bins_out) cudaFree(e->d_bins_out);
@@ -317,8 +494,15 @@ static int enqueue_emit(rts_engine *e, uint32_t cap)
     }
     if (!e->d_bins_out_count) RTS_CUDA(cudaMalloc(&e->d_bins_out_count, sizeof(uint32_t)));
     RTS_CUDA(cudaMemsetAsync(e->d_bins_out_count, 0, sizeof(uint32_t), e->stream));
-    { k_emit_bins<<<blocks_for(nb, 256), 256, 0, e->stream>>>(e->d_bin_sums, e->d_bin_mins, nb, per_rx, B, D, e->d_rx_sums, e->d_rx_mins,
-                                                           e->d_bins_out, e->d_bins_out_count, cap); e->launches++; }
+    if (e->bins_hashed) {
+        k_hash_emit<<<64, 256, 0, e->stream>>>(e->d_hash_keys, e->d_bin_sums, e->d_bin_mins, e->d_hash_used, e->d_hash_count, per_rx, B, D,
+                                               e->d_rx_sums, e->d_rx_mins, e->d_bins_out, e->d_bins_out_count, cap);
+        e->launches++;
+    } else {
+        k_emit_bins<<<blocks_for(nb, 256), 256, 0, e->stream>>>(e->d_bin_sums, e->d_bin_mins, nb, per_rx, B, D, e->d_rx_sums, e->d_rx_mins,
+                                                             e->d_bins_out, e->d_bins_out_count, cap);
+        e->launches++;
+    }
     RTS_CUDA(cudaGetLastError());
     return RTS_OK;
 }
@@ -329,7 +513,7 @@ int agg_emit_bins_async(rts_engine *e)
 {
     e->bins_eager = false;
     const uint64_t nb = e->n_bins_dense;
-    if (!nb || !e->last_nrx || nb > (1ull << 18)) return RTS_OK;
+    if (!nb || !e->last_nrx || (!e->bins_hashed && nb > (1ull << 18))) return RTS_OK;
     if (!e->h_bins && cudaMallocHost((void **)&e->h_bins, sizeof(rts_bin) * RTS_EAGER_BINS) != cudaSuccess) { e->h_bins = nullptr; return RTS_OK; }
     int rc = enqueue_emit(e, RTS_EAGER_BINS);
     if (rc) return rc;

@@ -73,6 +73,8 @@ static int set_option(rts_engine *e, const char *name, long long v)
     else if (!strcmp(name, "no_split")) k.no_split = v != 0;
     else if (!strcmp(name, "split_below")) { if (v < 0 || v > (1ll << 30)) return rts_fail(RTS_ERR_ARG, "split_below out of range"); k.split_below = (uint32_t)v; }
     else if (!strcmp(name, "no_graph")) k.no_graph = v != 0;
+    else if (!strcmp(name, "hash_bins")) k.hash_bins = v != 0;
+    else if (!strcmp(name, "hash_log2")) { if (v < 4 || v > 28) return rts_fail(RTS_ERR_ARG, "hash_log2 must be 4..28"); k.hash_log2 = (uint32_t)v; e->hash_ready = false; }
     else if (!strcmp(name, "batch")) { if (v != 0 && (v < 32 || v > (1ll << 24))) return rts_fail(RTS_ERR_ARG, "batch must be 0 or 32..2^24"); k.batch = v; }
     else return rts_fail(RTS_ERR_ARG, "unknown option '%s'", name);
     return RTS_OK;
@@ -110,7 +112,7 @@ extern "C" int rts_create(int device, rts_engine **out)
     e->stream = e->own_stream;
     // tuning / test switches: the environment is read here, once; afterwards only rts_set_option changes them
     for (const char *name : {"bvh", "leaf_max", "no_chain", "no_raster", "no_tiles", "one_ended_queue", "debug_raster", "no_static_hits",
-                             "no_kept_reflections", "no_split", "split_below", "no_graph", "batch"}) {
+                             "no_kept_reflections", "no_split", "split_below", "no_graph", "batch", "hash_bins", "hash_log2"}) {
         std::string env = "RTS_";
         for (const char *c = name; *c; c++) env += (char)toupper(*c);
         if (const char *v = getenv(env.c_str())) {
@@ -158,7 +160,7 @@ extern "C" void rts_destroy(rts_engine *e)
     cudaStreamSynchronize(e->stream);
     free_scene(e);
     for (int k = 0; k < 2; k++) if (e->q_slab[k]) cudaFree(e->q_slab[k]);
-    void *ptrs[] = {e->d_trav_hits, e->d_todo, e->d_w1_static, e->d_target_box, e->d_mover_nodes, e->d_dirs, e->d_hits, e->d_hits_static, e->d_raster_ctl, e->d_raster_ctl_static, e->d_raster_items, e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count, e->d_rx_sums, e->d_rx_mins,
+    void *ptrs[] = {e->d_ckeys, e->d_csums, e->d_cmins, e->d_hash_keys, e->d_hash_used, e->d_hash_count, e->d_trav_hits, e->d_todo, e->d_w1_static, e->d_target_box, e->d_mover_nodes, e->d_dirs, e->d_hits, e->d_hits_static, e->d_raster_ctl, e->d_raster_ctl_static, e->d_raster_items, e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count, e->d_rx_sums, e->d_rx_mins,
                     e->d_results, e->d_targ_intersect, e->d_tri_path, e->d_rcs_angle};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -527,21 +529,31 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     // bins
     if (flags & RTS_OUT_BINS) {
         const uint64_t per_rx = P.powB[sz.depth_total];
-        const uint64_t nb = per_rx * std::max<uint32_t>(1, p->n_rx);
-        if (per_rx > (1ull << 24) || nb > (1ull << 24))
-            return rts_fail(RTS_ERR_CAPACITY, "dense bin table (%u targets+1)^%u x %u receivers = %llu bins exceeds 2^24",
-                            e->n_targets, sz.depth_total, p->n_rx, (unsigned long long)nb);
+        if (per_rx > (~0ull >> 1) / std::max<uint32_t>(1, p->n_rx))
+            return rts_fail(RTS_ERR_CAPACITY, "bin key (%u targets+1)^%u x %u receivers does not fit 63 bits", e->n_targets, sz.depth_total, p->n_rx);
+        // dense table while it is small; beyond 2^20 bins (the reference groups arbitrary path rows, aggregation.cu:43-57) a
+        // hash table whose per-pulse cost follows the number of occupied bins
+        e->bins_hashed = e->knobs.hash_bins || per_rx * std::max<uint32_t>(1, p->n_rx) > (1ull << 20);
+        e->bins_per_rx = per_rx;
+        const uint64_t nb = e->bins_hashed ? (1ull << e->knobs.hash_log2) : per_rx * std::max<uint32_t>(1, p->n_rx);
         if (e->bins_alloc < nb) {
             if (e->d_bin_sums) cudaFree(e->d_bin_sums);
             if (e->d_bin_mins) cudaFree(e->d_bin_mins);
-            e->d_bin_sums = nullptr; e->d_bin_mins = nullptr; e->bins_alloc = 0;
+            e->d_bin_sums = nullptr; e->d_bin_mins = nullptr; e->bins_alloc = 0; e->hash_ready = false;
             RTS_CUDA(cudaMalloc(&e->d_bin_sums, sizeof(double) * 5 * nb));
             RTS_CUDA(cudaMalloc(&e->d_bin_mins, sizeof(unsigned long long) * nb));
             e->bins_alloc = nb;
         }
         e->n_bins_dense = p->n_rx ? nb : 0;
-        RTS_CUDA(cudaMemsetAsync(e->d_bin_sums, 0, sizeof(double) * 5 * nb, st));
-        RTS_CUDA(cudaMemsetAsync(e->d_bin_mins, 0x7f, sizeof(unsigned long long) * nb, st)); // empty = 0x7f7f…7f: positive as int64, so a signed MIN all-reduce keeps it last
+        if (e->bins_hashed) {
+            int rc = agg_hash_prepare(e, nb);
+            if (rc) return rc;
+            P.hash_keys = e->d_hash_keys; P.hash_used = e->d_hash_used; P.hash_count = e->d_hash_count;
+        } else {
+            e->hash_ready = false;   // the dense table shares the arrays
+            RTS_CUDA(cudaMemsetAsync(e->d_bin_sums, 0, sizeof(double) * 5 * nb, st));
+            RTS_CUDA(cudaMemsetAsync(e->d_bin_mins, 0x7f, sizeof(unsigned long long) * nb, st)); // empty = 0x7f7f…7f: positive as int64, so a signed MIN all-reduce keeps it last
+        }
         P.bin_sums = e->d_bin_sums; P.bin_mins = e->d_bin_mins; P.n_bins = e->n_bins_dense;
     } else {
         e->n_bins_dense = 0;
@@ -849,11 +861,30 @@ extern "C" int rts_bins_device(rts_engine *e, void **sums, uint64_t *n_sum, void
 {
     if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
     if (!e->have_pulse || !(e->last_flags & RTS_OUT_BINS)) return rts_fail(RTS_ERR_STATE, "last pulse did not produce bins");
+    if (e->bins_hashed) return rts_fail(RTS_ERR_STATE, "the last pulse used the sparse bin table: exchange it with rts_bins_compact_device / rts_bins_load_compact");
     if (sums) *sums = e->d_bin_sums;
     if (n_sum) *n_sum = e->n_bins_dense * 5;
     if (mins) *mins = e->d_bin_mins;
     if (n_mins) *n_mins = e->n_bins_dense;
     return RTS_OK;
+}
+
+extern "C" int rts_bins_compact_device(rts_engine *e, void **keys_device, void **sums_device, void **mins_device, uint32_t *n)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    if (!e->have_pulse || !(e->last_flags & RTS_OUT_BINS)) return rts_fail(RTS_ERR_STATE, "last pulse did not produce bins");
+    if (!e->bins_hashed) return rts_fail(RTS_ERR_STATE, "the last pulse used the dense bin table: rts_bins_device");
+    RTS_CUDA(cudaSetDevice(e->device));
+    return agg_hash_compact(e, keys_device, sums_device, mins_device, n);
+}
+
+extern "C" int rts_bins_load_compact(rts_engine *e, const void *keys_device, const void *sums_device, const void *mins_device, uint32_t n)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    if (!e->have_pulse || !(e->last_flags & RTS_OUT_BINS) || !e->bins_hashed) return rts_fail(RTS_ERR_STATE, "last pulse did not use the sparse bin table");
+    if (n && (!keys_device || !sums_device || !mins_device)) return rts_fail(RTS_ERR_ARG, "NULL array");
+    RTS_CUDA(cudaSetDevice(e->device));
+    return agg_hash_load(e, keys_device, sums_device, mins_device, n);
 }
 
 extern "C" int rts_finalise_bins(rts_engine *e)

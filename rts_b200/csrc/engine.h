@@ -127,6 +127,11 @@ struct WaveParams {
     double *bin_sums;               // [n_bins*5]
     unsigned long long *bin_mins;   // [n_bins]
     uint64_t n_bins;
+    // sparse bins (when n_rx * (K+1)^D is too large for a dense table): open-addressing table over the same sums / mins
+    // arrays, keyed by rx * (K+1)^D + path key; hash_used lists the occupied slots (emission and clearing cost what is occupied)
+    unsigned long long *hash_keys;  // [n_bins] (n_bins = table size, a power of two); ~0 = empty; nullptr: dense table
+    uint32_t *hash_used;            // [n_bins]
+    unsigned *hash_count;
     rts_ray_record *results;        // records mode
     int32_t *targ_intersect;
     double *rcs_angle;
@@ -202,6 +207,8 @@ struct Knobs {
     int no_chain = 0, no_raster = 0, no_tiles = 0, one_ended_queue = 0, debug_raster = 0, no_static_hits = 0,
         no_kept_reflections = 0, no_split = 0, no_graph = 0;
     long long batch = 0;           // 0 = default 2^24 primaries per batch
+    int hash_bins = 0;             // 1: sparse (hashed) bins also where a dense table would fit
+    uint32_t hash_log2 = 22;       // slots of the sparse bin table
     uint32_t split_below = 1u << 18;   // later waves with at least this many rays run as k_traverse + k_shade_wave
 };
 
@@ -302,7 +309,15 @@ struct rts_engine {
     // outputs
     double *d_bin_sums = nullptr;
     unsigned long long *d_bin_mins = nullptr;
-    uint64_t n_bins_dense = 0, bins_alloc = 0;
+    uint64_t n_bins_dense = 0, bins_alloc = 0;   // n_bins_dense: entries of the table in use (dense bins, or slots of the hash table)
+    bool bins_hashed = false, hash_ready = false;
+    unsigned long long *d_hash_keys = nullptr;
+    uint32_t *d_hash_used = nullptr;
+    unsigned *d_hash_count = nullptr;
+    uint64_t hash_alloc = 0, bins_per_rx = 0;
+    unsigned long long *d_ckeys = nullptr, *d_cmins = nullptr;   // compact copies of the occupied bins (multi-GPU exchange)
+    double *d_csums = nullptr;
+    uint64_t compact_alloc = 0;
     rts_bin *d_bins_out = nullptr, *h_bins = nullptr;   // h_bins: pinned
     bool bins_eager = false;
     double *d_rx_sums = nullptr;
@@ -366,6 +381,9 @@ int trace_wave_grid(rts_engine *e);
 
 // aggregate.cu
 int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n);
+int agg_hash_prepare(rts_engine *e, uint64_t slots);   // allocate / clear the sparse bin table for a pulse
+int agg_hash_compact(rts_engine *e, void **keys, void **sums, void **mins, uint32_t *n);
+int agg_hash_load(rts_engine *e, const void *keys, const void *sums, const void *mins, uint32_t n);
 int agg_emit_bins_async(rts_engine *e);
 int agg_fill_records(rts_engine *e, uint64_t ray_total, uint32_t D, uint32_t W);
 int agg_get_received(rts_engine *e, uint64_t cap, uint64_t *n, uint64_t *slots, rts_ray_record *results, int32_t *targ_intersect,

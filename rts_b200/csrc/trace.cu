@@ -635,7 +635,7 @@ __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r
     const double amp = sqrt(pw);
     const unsigned long long bin = (unsigned long long)received * P.powB[P.D] + r.key;
     const unsigned long long slot = (unsigned long long)r.ray + (unsigned long long)m_slot(r.meta) * P.R3;
-    if (bin >= P.n_bins) return;
+    if (!P.hash_keys && bin >= P.n_bins) return;
     cg::coalesced_group g = cg::coalesced_threads();
     auto part = cg::labeled_partition(g, bin);
     const double s_n = cg::reduce(part, 1.0, cg::plus<double>());
@@ -645,13 +645,30 @@ __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r
     const double s_f = cg::reduce(part, dopHz, cg::plus<double>());
     const unsigned long long s_m = cg::reduce(part, slot, cg::less<unsigned long long>());
     if (part.thread_rank() == 0) {
-        double *b = P.bin_sums + bin * 5;
+        unsigned long long at = bin;
+        if (P.hash_keys) {   // sparse table: find or claim the bin's slot (linear probing; a claimed slot is listed once)
+            const unsigned long long mask = P.n_bins - 1ull;
+            unsigned long long h = bin * 0x9E3779B97F4A7C15ull;
+            h ^= h >> 29;
+            at = h & mask;
+            unsigned long long probes = 0;
+            for (;; at = (at + 1ull) & mask) {
+                unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(P.hash_keys + at);
+                if (cur == ~0ull) {
+                    cur = atomicCAS(P.hash_keys + at, ~0ull, bin);
+                    if (cur == ~0ull) { P.hash_used[atomicAdd(P.hash_count, 1u)] = (uint32_t)at; break; }
+                }
+                if (cur == bin) break;
+                if (++probes > mask) { atomicAdd(&P.counters->overflow, 1ull); return; }   // table full: reported as RTS_ERR_CAPACITY
+            }
+        }
+        double *b = P.bin_sums + at * 5;
         atomicAdd(b + 0, s_n);
         atomicAdd(b + 1, s_a);
         atomicAdd(b + 2, s_d);
         atomicAdd(b + 3, s_p);
         atomicAdd(b + 4, s_f);
-        atomicMin(P.bin_mins + bin, s_m);
+        atomicMin(P.bin_mins + at, s_m);
     }
 }
 

@@ -80,6 +80,81 @@ def allreduce_bins(engine, device, group=None):
     engine.finalise_bins()
 
 
+def exchange_sparse(keys, sums, mins, group=None):
+    """The exchange step for sparse bins ("hash -> sorted key table + all-gather of keys"): every rank
+    holds its occupied bins as compact arrays keys int64[n_r] (distinct), sums float64[n_r,5], mins int64[n_r].
+    all_gather of the counts and of the (padded) keys -> sorted union U of all ranks' keys -> each rank scatters its
+    rows to their positions in U -> all_reduce SUM over [|U|,5] and MIN over [|U|].  Returns (U, sums_U, mins_U), equal
+    on all ranks.  Works on any backend (NCCL on GPUs, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    dev = keys.device
+    n = torch.tensor([keys.numel()], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n, group=group)
+    n_max = int(max(int(c) for c in counts))
+    if n_max == 0:
+        return keys[:0], sums.reshape(-1, 5)[:0], mins[:0]
+    pad = torch.full((n_max,), -1, dtype=torch.int64, device=dev)      # keys are < 2^63: -1 never occurs
+    pad[: keys.numel()] = keys
+    gathered = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(gathered, pad, group=group)
+    union = torch.unique(torch.cat(gathered))                          # sorted
+    union = union[union >= 0]
+    at = torch.searchsorted(union, keys)
+    u_sums = torch.zeros((union.numel(), 5), dtype=torch.float64, device=dev)
+    u_mins = torch.full((union.numel(),), EMPTY_MIN, dtype=torch.int64, device=dev)
+    u_sums[at] = sums.reshape(-1, 5)
+    u_mins[at] = mins
+    dist.all_reduce(u_sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(u_mins, op=dist.ReduceOp.MIN, group=group)
+    return union, u_sums, u_mins
+
+
+def merge_compact(parts):
+    """Single-process statement of exchange_sparse for tests: list of (keys, sums[n,5], mins) tensors -> merged."""
+    import torch
+
+    keys = torch.cat([p[0] for p in parts])
+    union, inv = torch.unique(keys, return_inverse=True)
+    u_sums = torch.zeros((union.numel(), 5), dtype=torch.float64, device=keys.device)
+    u_sums.index_add_(0, inv, torch.cat([p[1].reshape(-1, 5) for p in parts]))
+    u_mins = torch.full((union.numel(),), EMPTY_MIN, dtype=torch.int64, device=keys.device)
+    u_mins.scatter_reduce_(0, inv, torch.cat([p[2] for p in parts]), reduce="amin")
+    return union, u_sums, u_mins
+
+
+def compact_bins_as_tensors(engine, device):
+    """Copies (torch-owned) of the engine's occupied sparse bins: (keys int64[n], sums float64[n,5], mins int64[n])."""
+    import torch
+
+    kp, sp, mp, n = engine.bins_compact_device()
+    if n == 0:
+        z = torch.zeros(0, dtype=torch.int64, device=device)
+        return z, torch.zeros((0, 5), dtype=torch.float64, device=device), z.clone()
+    keys = torch.as_tensor(_DevArray(kp, n, "<i8"), device=device).clone()
+    sums = torch.as_tensor(_DevArray(sp, n * 5, "<f8"), device=device).clone().reshape(n, 5)
+    mins = torch.as_tensor(_DevArray(mp, n, "<i8"), device=device).clone()
+    return keys, sums, mins
+
+
+def allreduce_bins_sparse(engine, device, group=None):
+    """allreduce_bins for pulses whose bins live in the sparse table (rts_bins_compact_device / rts_bins_load_compact)."""
+    import torch
+
+    cur = torch.cuda.current_stream(device).cuda_stream or 1
+    if getattr(engine, "_stream", None) != cur:
+        engine.set_stream(cur)
+    keys, sums, mins = compact_bins_as_tensors(engine, device)
+    union, u_sums, u_mins = exchange_sparse(keys, sums, mins, group)
+    u_sums = u_sums.contiguous()
+    engine.bins_load_compact(union.data_ptr(), u_sums.data_ptr(), u_mins.data_ptr(), union.numel())
+    engine.finalise_bins()
+    return union.numel()
+
+
 def merge_bins_numpy(parts):
     """CPU statement of the same reduction for tests: list of (sums[n,5], mins[n] uint64) -> merged."""
     sums = np.sum([p[0] for p in parts], axis=0)

@@ -51,7 +51,7 @@ EXPORTS = [
     "rts_rx_sphere_from_desc", "rts_result_sizes", "rts_rect_mesh", "rts_sphere_mesh", "rts_file_mesh",
     "rts_rotation_matrix", "rts_scene_set_targets", "rts_scene_set_poses", "rts_scene_rebuild", "rts_scene_bvh_info",
     "rts_scene_get_world_vertices", "rts_scene_get_tri_bounds", "rts_scene_check_bvh", "rts_trace_pulse",
-    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_get_split_profile", "rts_kernel_launches", "rts_probe_read_bandwidth", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_get_records_shard", "rts_get_received", "rts_bins_device", "rts_finalise_bins", "rts_aggregate",
+    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_get_split_profile", "rts_kernel_launches", "rts_probe_read_bandwidth", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_get_records_shard", "rts_get_received", "rts_bins_device", "rts_bins_compact_device", "rts_bins_load_compact", "rts_finalise_bins", "rts_aggregate",
 ]
 
 _lib = None
@@ -104,6 +104,8 @@ def load() -> C.CDLL:
     lib.rts_get_records_shard.argtypes = [vp, P(u64), vp, P(i32), P(dbl), P(i32)]
     lib.rts_get_received.argtypes = [vp, u64, P(u64), P(u64), vp, P(i32), P(dbl)]
     lib.rts_bins_device.argtypes = [vp, P(vp), P(u64), P(vp), P(u64)]
+    lib.rts_bins_compact_device.argtypes = [vp, P(vp), P(vp), P(vp), P(u32)]
+    lib.rts_bins_load_compact.argtypes = [vp, vp, vp, vp, u32]
     lib.rts_finalise_bins.argtypes = [vp]
     lib.rts_aggregate.argtypes = [vp, vp, P(i32), u32, u32, dbl, dbl, P(dbl), P(dbl), P(dbl), P(dbl), P(dbl), P(i32)]
     _lib = lib
@@ -348,6 +350,15 @@ class Engine:
         sp, mp, ns, nm = C.c_void_p(), C.c_void_p(), C.c_uint64(), C.c_uint64()
         _check(self._lib.rts_bins_device(self._h, C.byref(sp), C.byref(ns), C.byref(mp), C.byref(nm)))
         return sp.value, int(ns.value), mp.value, int(nm.value)
+
+    def bins_compact_device(self):
+        """(keys_ptr, sums_ptr, mins_ptr, n) of this GPU's occupied sparse bins as compact device arrays."""
+        kp, sp, mp, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint32()
+        _check(self._lib.rts_bins_compact_device(self._h, C.byref(kp), C.byref(sp), C.byref(mp), C.byref(n)))
+        return kp.value, sp.value, mp.value, int(n.value)
+
+    def bins_load_compact(self, keys_ptr: int, sums_ptr: int, mins_ptr: int, n: int):
+        _check(self._lib.rts_bins_load_compact(self._h, C.c_void_p(keys_ptr), C.c_void_p(sums_ptr), C.c_void_p(mins_ptr), int(n)))
 
     def finalise_bins(self):
         _check(self._lib.rts_finalise_bins(self._h))

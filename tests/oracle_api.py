@@ -111,10 +111,18 @@ def shard_size(spec: PulseSpec) -> int:
     return max(0, (max(e, b) - b + s - 1) // s)
 
 
-def trace_shard(targets, spec: PulseSpec, use_bvh=True):
-    """Oracle launch of a shard of a large grid with compact outputs: ray k of the shard has slot s at k + s*n_shard."""
+def trace_shard(targets, spec: PulseSpec, use_bvh=True, arrays=True):
+    """Oracle launch of a shard of a large grid with compact outputs: ray k of the shard has slot s at k + s*n_shard.
+    arrays=False: only the per-ray edge flags and the counters."""
     cs, cp = CScene(targets), CPulse(spec, len(targets))
     n_sh, M, D, W = shard_size(spec), spec.slots, spec.depth_total, spec.tri_cols
+    if not arrays:
+        edge = np.zeros(n_sh, dtype=np.uint8)
+        st = RtsStats()
+        rc = oracle().orc_trace_shard(cs.array, cs.n, C.byref(cp.c), int(use_bvh), None, None, None, None,
+                                      edge.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(st))
+        assert rc == 0, rc
+        return dict(edge=edge, stats=st.as_dict(), n_shard=n_sh)
     n = n_sh * M
     res = np.zeros(n, dtype=RAY_RECORD)
     ti = np.zeros((n, max(D, 1)), dtype=np.int32)

@@ -32,12 +32,20 @@ def test_reference_arm_prints_the_contract_line():
 
 @pytest.mark.gpu
 def test_gpu_arm_prints_the_contract_line():
-    out = _run(["--steps", "4", "--warmup", "3", "--cpu-stride", "64"])
+    out = _run(["--steps", "4", "--warmup", "3", "--cpu-stride", "64", "--no-ncu"])   # the ncu child is exercised by tools/profile_round.sh
     assert COMMON | {"roofline", "clocks", "gpu_launches"} <= set(out)
     assert out["n_gpus"] == 1 and out["steps"] == 4 and out["warmup"] == 3 and out["scaling"] == "weak" and out["dtype"] == "f64"
     roof = out["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(roof) and roof["bound"] == "hbm" and roof["unit"] == "GB/s"
-    assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-3
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "algorithmic", "measured"} <= set(roof) and roof["unit"] == "GB/s"
+    assert roof["bound"] in ("issue/latency", "hbm")
+    # achieved / frac / traffic are measured DRAM figures of the dominant kernel (ncu counters); the byte model of
+    # SURVEY.md §8(d) sits under "algorithmic".  A physically meaningful fraction never exceeds 1.
+    if roof["frac"] is not None:
+        assert abs(roof["frac"] - roof["achieved"] / roof["peak"]) < 1e-3 and 0 < roof["frac"] <= 1.05 and roof["traffic"] > 0
+        assert 0 < roof["issue"]["frac"] <= 1.0
+    alg = roof["algorithmic"]
+    assert alg["bytes_per_segment"] == 1632.0 and alg["bytes_per_launch"] > 0 and alg["gbs"] > 0
+    assert out["sustained"]["seconds"] >= 1.5 and out["sustained"]["value"] > 0
     assert out["gpu_launches"] > 0 and out["value"] > 0 and out["e2e"]["value"] > 0
     assert out["e2e"]["h2d_bytes_per_step"] > 0 and out["e2e"]["d2h_bytes_per_step"] > 0
     assert out["cpu_baseline"]["kind"] == "port" and "sample" in out["cpu_baseline"]

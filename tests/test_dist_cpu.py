@@ -61,3 +61,42 @@ def test_bin_allreduce_gloo_world2(tmp_path):
         assert np.array_equal(np.load(tmp_path / f"rsums{r}.npy"), esums)      # two addends: order-independent
         assert np.array_equal(np.load(tmp_path / f"rmins{r}.npy"), emins)
     assert (emins == np.uint64(rdist.EMPTY_MIN)).any()                      # bins empty on every rank stay empty
+
+
+def _sparse_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(7 + rank)
+    pool = np.arange(1, 400, dtype=np.int64) * 1_000_003          # key space shared by the ranks; each holds a subset
+    mine = np.sort(rng.choice(pool, size=int(rng.integers(0 if rank else 120, 200)), replace=False))
+    sums = rng.uniform(0.5, 2.0, size=(len(mine), 5))
+    mins = rng.integers(0, 1 << 40, size=len(mine)).astype(np.int64)
+    np.savez(os.path.join(out_dir, f"in{rank}.npz"), keys=mine, sums=sums, mins=mins)
+    u, us, um = rdist.exchange_sparse(torch.from_numpy(mine), torch.from_numpy(sums), torch.from_numpy(mins))
+    np.savez(os.path.join(out_dir, f"out{rank}.npz"), keys=u.numpy(), sums=us.numpy(), mins=um.numpy())
+    dist.destroy_process_group()
+
+
+def test_sparse_bin_exchange_gloo_world2(tmp_path):
+    """exchange_sparse: all-gather of keys -> sorted union -> SUM / MIN all-reduce of the compact arrays; every rank ends up
+    with the same merged table, equal to a host-side merge of the inputs."""
+    world = 2
+    mp.spawn(_sparse_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    ins = [np.load(tmp_path / f"in{r}.npz") for r in range(world)]
+    want = {}
+    for d in ins:
+        for k, s, m in zip(d["keys"], d["sums"], d["mins"]):
+            a = want.setdefault(int(k), [np.zeros(5), 1 << 62])
+            a[0] = a[0] + s
+            a[1] = min(a[1], int(m))
+    keys = np.array(sorted(want), dtype=np.int64)
+    for r in range(world):
+        o = np.load(tmp_path / f"out{r}.npz")
+        assert np.array_equal(o["keys"], keys)
+        assert np.allclose(o["sums"], np.stack([want[int(k)][0] for k in keys]), rtol=0, atol=1e-15)
+        assert np.array_equal(o["mins"], np.array([want[int(k)][1] for k in keys], dtype=np.int64))
+    # the single-process statement used by the GPU tests agrees
+    u, us, um = rdist.merge_compact([(torch.from_numpy(d["keys"]), torch.from_numpy(d["sums"]), torch.from_numpy(d["mins"])) for d in ins])
+    assert np.array_equal(u.numpy(), keys) and np.array_equal(um.numpy(), np.load(tmp_path / "out0.npz")["mins"])
+    assert np.allclose(us.numpy(), np.load(tmp_path / "out0.npz")["sums"], rtol=0, atol=1e-15)
