@@ -466,7 +466,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
 
     WaveParams P;
     memset(&P, 0, sizeof(P));
-    P.nodes = e->d_nodes; P.trirec = e->d_trirec; P.root_ref = e->root_ref; P.n_tris = e->n_tris;
+    P.nodes = e->d_nodes; P.qnodes = e->d_qnodes; P.qframe = e->d_qframe; P.trirec = e->d_trirec; P.root_ref = e->root_ref; P.n_tris = e->n_tris;
     P.scene_abs = e->d_scene_abs;
     P.world_normals = e->d_world_normals; P.tris = e->d_tris;
     P.t_norm_off = e->d_t_norm_off; P.t_tri_off = e->d_t_tri_off; P.t_per_face = e->d_t_per_face;

@@ -250,11 +250,47 @@ __global__ void k_fit(const int2 *__restrict__ children, const int32_t *__restri
     }
 }
 
+// Frame of the quantised nodes: the scene box plus 1/16 of its extent on every side (moving targets may wander that far
+// before a box leaves the frame and everything is quantised again), never thinner than 2^-10 of the largest extent.
+__global__ void k_qframe(const unsigned *__restrict__ scene_box, QFrame *__restrict__ frame, int only_on_overflow)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (only_on_overflow && !frame->overflow) return;
+    float lo[3], hi[3], big = 0.f;
+    for (int a = 0; a < 3; a++) {
+        lo[a] = ord2f(scene_box[a]); hi[a] = ord2f(scene_box[3 + a]);
+        if (!(lo[a] <= hi[a])) { lo[a] = 0.f; hi[a] = 0.f; }
+        big = fmaxf(big, hi[a] - lo[a]);
+    }
+    big = fmaxf(big, 1e-6f);
+    for (int a = 0; a < 3; a++) {
+        const float e = fmaxf(hi[a] - lo[a], big * 9.765625e-4f);
+        frame->lo[a] = lo[a] - 0.0625f * e;
+        frame->ext[a] = e * 1.125f;
+    }
+    // overflow stays set for k_pack_all behind this launch, which clears it
+}
+
+__global__ void k_qframe_done(QFrame *frame) { if (threadIdx.x == 0) frame->overflow = 0u; }
+
+// 15-bit plane positions of a box on the frame, rounded outward and widened by one cell (covers the traversal's
+// evaluation error, trace.cu: traverse_q); a plane that would leave the frame raises the overflow flag
+__device__ __forceinline__ uint32_t q_planes(float lo, float hi, float flo, float ext, uint32_t *overflow)
+{
+    const double s = 32768.0 / (double)ext;
+    const double a = floor(((double)lo - (double)flo) * s) - 1.0, b = ceil(((double)hi - (double)flo) * s) + 1.0;
+    if (a < 0.0 || b > 32767.0) *overflow = 1u;
+    const uint32_t qa = (uint32_t)fmin(fmax(a, 0.0), 32767.0), qb = (uint32_t)fmin(fmax(b, 0.0), 32767.0);
+    return (0x8000u | qa) | ((0x8000u | qb) << 16);
+}
+
 __global__ void k_pack(const int2 *__restrict__ children, const int2 *__restrict__ range,
                        const uint32_t *__restrict__ order, const float *__restrict__ tri_box,
                        const float *__restrict__ node_box, BvhNode *__restrict__ nodes, int n, double *sah, int leaf_max,
-                       int count, const uint32_t *__restrict__ list, uint32_t *__restrict__ flags)
+                       int count, const uint32_t *__restrict__ list, uint32_t *__restrict__ flags,
+                       QNode *__restrict__ qnodes, QFrame *__restrict__ frame, int only_on_overflow)
 {
+    if (only_on_overflow && !*reinterpret_cast<volatile uint32_t *>(&frame->overflow)) return;   // re-quantisation pass: nothing left the frame
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = i < count;
     if (live && list) { i = (int)list[i]; flags[i] = 0u; }   // partial refit: re-arm the node's arrival counter
@@ -269,10 +305,12 @@ __global__ void k_pack(const int2 *__restrict__ children, const int2 *__restrict
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(0xffffffffu, area, o);
-    if ((threadIdx.x & 31) == 0 && area > 0.0) atomicAdd(sah, area);
+    if ((threadIdx.x & 31) == 0 && area > 0.0 && !only_on_overflow) atomicAdd(sah, area);
     if (i >= n - 1) return;
     const int2 ch = children[i];
     BvhNode nd;
+    QNode qn;
+    uint32_t q_over = 0;
     int refs[2];
     float cc[2][3], hh[2][3];
 #pragma unroll
@@ -297,8 +335,17 @@ __global__ void k_pack(const int2 *__restrict__ children, const int2 *__restrict
             const double d = fmax((double)hi - (double)c0, (double)c0 - (double)lo);
             cc[c][a] = c0;
             hh[c][a] = nextafterf(__double2float_ru(d), CUDART_INF_F);
+            qn.w[3 * c + a] = q_planes(lo, hi, frame->lo[a], frame->ext[a], &q_over);
         }
     }
+    qn.ref0 = refs[0]; qn.ref1 = refs[1];
+    {
+        uint4 *qd = reinterpret_cast<uint4 *>(qnodes + i);
+        const uint4 *qs = reinterpret_cast<const uint4 *>(&qn);
+        qd[0] = qs[0]; qd[1] = qs[1];
+    }
+    if (q_over && !only_on_overflow) atomicOr(&frame->overflow, 1u);
+    if (only_on_overflow) return;          // the fp32 nodes and the SAH sum are already in place
     nd.c0x = cc[0][0]; nd.c0y = cc[0][1]; nd.h0x = hh[0][0]; nd.h0y = hh[0][1];
     nd.c1x = cc[1][0]; nd.c1y = cc[1][1]; nd.h1x = hh[1][0]; nd.h1y = hh[1][1];
     nd.c0z = cc[0][2]; nd.c1z = cc[1][2]; nd.h0z = hh[0][2]; nd.h1z = hh[1][2];
@@ -439,7 +486,7 @@ void bvh_free(rts_engine *e)
                      (void **)&e->d_nodes, (void **)&e->d_trirec, (void **)&e->d_cub_temp, (void **)&e->d_violations, (void **)&e->d_sah,
                      (void **)&e->d_moving, (void **)&e->d_vlist, (void **)&e->d_nlist, (void **)&e->d_tlist, (void **)&e->d_nodelist,
                      (void **)&e->d_list_counts, (void **)&e->d_mark, (void **)&e->d_static_box, (void **)&e->d_sah_static,
-                     (void **)&e->d_scene_abs};
+                     (void **)&e->d_scene_abs, (void **)&e->d_qnodes, (void **)&e->d_qframe};
     for (void **p : ptrs) {
         if (*p) cudaFree(*p);
         *p = nullptr;
@@ -465,6 +512,9 @@ int bvh_alloc(rts_engine *e)
     if ((rc = dalloc(&e->d_range, T))) return rc;
     if ((rc = dalloc(&e->d_fit_flags, T))) return rc;
     if ((rc = dalloc(&e->d_nodes, T))) return rc;
+    if ((rc = dalloc(&e->d_qnodes, T))) return rc;
+    if ((rc = dalloc(&e->d_qframe, 1))) return rc;
+    RTS_CUDA(cudaMemset(e->d_qframe, 0, sizeof(QFrame)));
     if ((rc = dalloc(&e->d_trirec, T))) return rc;
     if ((rc = dalloc(&e->d_violations, (size_t)1))) return rc;
     if ((rc = dalloc(&e->d_sah, (size_t)1))) return rc;
@@ -525,9 +575,11 @@ static int fit_and_pack(rts_engine *e)
                                                       e->d_fit_flags, n, n, nullptr, nullptr, nullptr); e->launches++; }
         RTS_CUDA(cudaMemsetAsync(e->d_fit_flags, 0, sizeof(uint32_t) * (size_t)n, e->stream));   // armed for partial refits
         RTS_CUDA(cudaMemsetAsync(e->d_sah, 0, sizeof(double), e->stream));
+        RTS_CUDA(cudaMemsetAsync(&e->d_qframe->overflow, 0, sizeof(uint32_t), e->stream));
+        { k_qframe<<<1, 32, 0, e->stream>>>((const unsigned *)e->d_scene_box, e->d_qframe, 0); e->launches++; }
         { k_pack<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_children, e->d_range, e->d_order, e->d_tri_box,
                                                            e->d_node_box, e->d_nodes, n, e->d_sah, e->leaf_max, n - 1, nullptr,
-                                                           nullptr); e->launches++; }
+                                                           nullptr, e->d_qnodes, e->d_qframe, 0); e->launches++; }
     }
     RTS_CUDA(cudaGetLastError());
     e->root_ref = n <= e->leaf_max ? ~((0 << 3) | (n - 1)) : 0;
@@ -580,7 +632,16 @@ static int partial_update(rts_engine *e)
         { k_tri_records<<<blocks_for(e->n_dt, bs), bs, 0, e->stream>>>(e->d_world_verts, e->d_tris, e->d_tri_target, e->d_t_vert_off, e->d_order, e->d_trirec, e->n_dt, e->d_tlist, e->d_leaf_of_tri); e->launches++; }
         { k_fit<<<blocks_for(e->n_dt, bs), bs, 0, e->stream>>>(e->d_children, e->d_parent, e->d_order, e->d_tri_box, e->d_node_box, e->d_fit_flags, n, (int)e->n_dt, e->d_tlist, e->d_leaf_of_tri, e->d_mark); e->launches++; }
     }
-    if (e->n_dnode) { k_pack<<<blocks_for(e->n_dnode, bs), bs, 0, e->stream>>>(e->d_children, e->d_range, e->d_order, e->d_tri_box, e->d_node_box, e->d_nodes, n, e->d_sah, e->leaf_max, (int)e->n_dnode, e->d_nodelist, e->d_fit_flags); e->launches++; }
+    if (e->n_dnode) {
+        k_pack<<<blocks_for(e->n_dnode, bs), bs, 0, e->stream>>>(e->d_children, e->d_range, e->d_order, e->d_tri_box, e->d_node_box, e->d_nodes, n, e->d_sah, e->leaf_max, (int)e->n_dnode, e->d_nodelist, e->d_fit_flags, e->d_qnodes, e->d_qframe, 0);
+        // a moving target has left the frame of the quantised nodes (rare: the frame has a margin of 1/16 of the scene):
+        // new frame from this pulse's scene box, every node quantised again.  Both launches return at once otherwise —
+        // decided on the device, no host synchronisation.
+        k_qframe<<<1, 32, 0, e->stream>>>((const unsigned *)e->d_scene_box, e->d_qframe, 1);
+        k_pack<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_children, e->d_range, e->d_order, e->d_tri_box, e->d_node_box, e->d_nodes, n, e->d_sah, e->leaf_max, n - 1, nullptr, nullptr, e->d_qnodes, e->d_qframe, 1);
+        k_qframe_done<<<1, 32, 0, e->stream>>>(e->d_qframe);
+        e->launches += 4;
+    }
     { k_scene_abs<<<1, 32, 0, e->stream>>>((const unsigned *)e->d_scene_box, e->d_scene_abs, e->n_tris); e->launches++; }
     RTS_CUDA(cudaGetLastError());
     return RTS_OK;

@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_WAVE_MIN_BLOCKS) k_wave1_f
         if (!(r.meta & M_COH)) continue;
         HitRec h;
         unsigned nn = 0, nt = 0;
-        traverse<false, true>(P, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz), SCENE_EPS, h, nn, nt, ovf);
+        if (RTS_QNODES) traverse_q<false, true>(P, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz), SCENE_EPS, h, nn, nt, ovf);
+        else traverse<false, true>(P, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz), SCENE_EPS, h, nn, nt, ovf);
         const uint32_t ray = __ldcs(P.in.ray + idx);
         P.w1_static[w1_pixel(P, ray)] = h.pos >= 0 ? (((unsigned long long)__float_as_uint(h.t) << 32) | (unsigned long long)(uint32_t)h.pos) : ~0ull;
     }

@@ -36,6 +36,19 @@ struct __align__(64) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 bytes");
 
+// Quantised BVH node, 32 B = 2 x 128-bit loads, for every ray that starts inside the scene (all later waves): the
+// traversal loop is bound by the L1 data pipe (128 B per clock per SM; a warp of 32 lanes fetching 64-byte nodes keeps
+// it busy for 16 clocks per visit, twice the time the visit's instructions take to issue), so the node is halved.
+// Each plane of the two child boxes is a 15-bit position on a frame around the scene: x(q) = lo + q * ext / 32768,
+// stored as h = 0x8000 | q so that one PRMT with 0x3F800000 yields the float 1 + q/32768 (k_pack; traverse_q in
+// trace.cu holds the error analysis).  Boxes are rounded outward and widened by one more cell.
+struct __align__(32) QNode {
+    uint32_t w[6];              // child 0: x, y, z; child 1: x, y, z — low half = lower plane, high half = upper plane
+    int32_t ref0, ref1;         // as in BvhNode
+};
+static_assert(sizeof(QNode) == 32, "QNode must be 32 bytes");
+struct QFrame { float lo[3], ext[3]; uint32_t overflow; uint32_t pad; };   // device-resident; overflow: a box left the frame
+
 // Leaf-ordered triangle record, 80 B = 5 x 128-bit loads: world-space fp64 vertices + ids.
 struct __align__(16) TriRec {
     double p[9];            // p0.xyz p1.xyz p2.xyz
@@ -72,6 +85,8 @@ struct RxDev { double cx, cy, cz, radius, min_theta, max_theta, min_phi, max_phi
 struct WaveParams {
     // scene
     const BvhNode *nodes;
+    const QNode *qnodes;            // the same tree, quantised (later waves)
+    const QFrame *qframe;
     const TriRec *trirec;
     int32_t root_ref;
     uint32_t n_tris;
@@ -248,6 +263,8 @@ struct rts_engine {
     int2 *d_children = nullptr, *d_range = nullptr;
     uint32_t *d_fit_flags = nullptr;
     BvhNode *d_nodes = nullptr;
+    QNode *d_qnodes = nullptr;
+    QFrame *d_qframe = nullptr;
     TriRec *d_trirec = nullptr;
     void *d_cub_temp = nullptr;
     size_t cub_temp_bytes = 0;

@@ -22,7 +22,9 @@
 #define RTS_TRAV_MIN_BLOCKS 8
 #endif
 #ifndef RTS_FETCH_THRESH
-#define RTS_FETCH_THRESH 8u            // idle lanes that make a warp fetch new rays
+#define RTS_FETCH_THRESH 32u           // idle lanes that make a warp fetch new rays (32: when all its rays are done — refilling
+                                       // lane by lane mixes rays at different tree depths in one warp, and the node fetches,
+                                       // which bound this kernel, stop coalescing: 1.44 ms at 32 against 1.74 ms at 8)
 #endif
 #ifndef RTS_TRAV_CHUNK
 #define RTS_TRAV_CHUNK 64u             // rays a warp reserves from the global work counter at a time
@@ -57,16 +59,19 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_TRAV_MIN_BLOCKS) k_travers
     constexpr int SENT = 0x7fffffff;
     constexpr unsigned FULL = 0xffffffffu;
     const double tmin_d = (double)SCENE_EPS, tmax_d = (double)RT_DEFAULT_MAX_F;
-    // Register budget: the node loop needs the eight packed slab constants, the triangle test needs the fp64 ray and
-    // ~50 registers of fp64 temporaries — never both.  So the constants are parked in shared memory when a ray is
-    // fetched and re-read after every leaf visit (volatile: the old values are dead across the leaf code), and the fp64
-    // origin / direction are re-read from the queue (L1/L2-resident: this warp fetched them) when a leaf is reached.
-    __shared__ ulonglong2 s_const[4][RTS_WAVE_BLOCK];
+    // Register budget: the node loop needs the ray's slab constants (QRay: six floats, six PRMT selectors), the triangle
+    // test needs the fp64 ray and ~50 registers of fp64 temporaries — never both.  So the constants are parked in shared
+    // memory when a ray is fetched and re-read after every leaf visit (volatile: the old values are dead across the leaf
+    // code), and the fp64 origin / direction are re-read from the queue (L1/L2-resident: this warp fetched them) when a
+    // leaf is reached.
+    __shared__ uint4 s_const[3][RTS_WAVE_BLOCK];
     int stack[RTS_STACK_DEPTH];
     int sp = 0, cur = SENT;
     bool have = false;
     unsigned idx = 0;
-    u64 inv_xy = 0, noi_xy = 0, ainv_xy = 0, e_xy = 0, inv_zz = 0, noi_zz = 0, ainv_zz = 0, e_zz = 0;
+    QRay Q;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { Q.a[k] = 0; Q.b[k] = 0; Q.sn[k] = 0; Q.sf[k] = 0; }
     float best_t = RT_DEFAULT_MAX_F, best_pad = CUDART_INF_F;
     int best_pos = -1;
     uint32_t best_id = 0xffffffffu;
@@ -92,28 +97,16 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_TRAV_MIN_BLOCKS) k_travers
                 if (!have && rank < avail) {
                     const unsigned entry = chunk_next + rank;
                     idx = P.todo_list ? P.todo_list[entry] : queue_slot(P, entry, n_front);
-                    const float oo[3] = {(float)__ldg(P.in.f[F_OX] + idx), (float)__ldg(P.in.f[F_OY] + idx), (float)__ldg(P.in.f[F_OZ] + idx)};
-                    const float dd[3] = {(float)__ldg(P.in.f[F_DX] + idx), (float)__ldg(P.in.f[F_DY] + idx), (float)__ldg(P.in.f[F_DZ] + idx)};
-                    float inv[3], noi[3], ainv[3], E[3];
-#pragma unroll
-                    for (int a = 0; a < 3; a++) {          // the constants of traverse(): same error bound
-                        if (!(fabsf(dd[a]) >= 1e-20f)) {
-                            inv[a] = 0.f; noi[a] = 0.f; ainv[a] = 0.f; E[a] = CUDART_INF_F;
-                        } else {
-                            float r;
-                            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(dd[a]));
-                            inv[a] = r;
-                            noi[a] = -(oo[a] * r);
-                            ainv[a] = fabsf(r);
-                            E[a] = 9.5367431640625e-07f * ((P.scene_abs[a] + fabsf(oo[a])) * ainv[a]) + 1e-30f;
-                        }
+                    q_setup(P, mk3(__ldg(P.in.f[F_OX] + idx), __ldg(P.in.f[F_OY] + idx), __ldg(P.in.f[F_OZ] + idx)),
+                            mk3(__ldg(P.in.f[F_DX] + idx), __ldg(P.in.f[F_DY] + idx), __ldg(P.in.f[F_DZ] + idx)), Q);
+                    {
+                        float a0, a1, a2, b0, b1, b2, dup;
+                        upk2(Q.a[0], a0, dup); upk2(Q.a[1], a1, dup); upk2(Q.a[2], a2, dup);
+                        upk2(Q.b[0], b0, dup); upk2(Q.b[1], b1, dup); upk2(Q.b[2], b2, dup);
+                        s_const[0][threadIdx.x] = make_uint4(__float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(b0));
+                        s_const[1][threadIdx.x] = make_uint4(__float_as_uint(b1), __float_as_uint(b2), Q.sn[0], Q.sn[1]);
+                        s_const[2][threadIdx.x] = make_uint4(Q.sn[2], Q.sf[0], Q.sf[1], Q.sf[2]);
                     }
-                    inv_xy = pk2(inv[0], inv[1]); noi_xy = pk2(noi[0], noi[1]); ainv_xy = pk2(ainv[0], ainv[1]); e_xy = pk2(E[0], E[1]);
-                    inv_zz = pk2(inv[2], inv[2]); noi_zz = pk2(noi[2], noi[2]); ainv_zz = pk2(ainv[2], ainv[2]); e_zz = pk2(E[2], E[2]);
-                    s_const[0][threadIdx.x] = make_ulonglong2(inv_xy, noi_xy);
-                    s_const[1][threadIdx.x] = make_ulonglong2(ainv_xy, e_xy);
-                    s_const[2][threadIdx.x] = make_ulonglong2(inv_zz, noi_zz);
-                    s_const[3][threadIdx.x] = make_ulonglong2(ainv_zz, e_zz);
                     best_t = RT_DEFAULT_MAX_F; best_pad = CUDART_INF_F; best_pos = -1; best_id = 0xffffffffu;
                     sp = 0; cur = P.root_ref;
                     have = true;
@@ -125,20 +118,10 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_TRAV_MIN_BLOCKS) k_travers
         // descend until this lane stands on a leaf or has nothing left (the "while-while" loop of traverse())
         while ((unsigned)cur < (unsigned)SENT) {
             if (COUNT) n_nodes++;
-            const ulonglong2 *np = reinterpret_cast<const ulonglong2 *>(P.nodes + cur);
-            const ulonglong2 q0 = __ldg(np), q1 = __ldg(np + 1), q2 = __ldg(np + 2);
-            const int2 refs = __ldg(reinterpret_cast<const int2 *>(np + 3));
-            const u64 T0 = fma2(q0.x, inv_xy, noi_xy), H0 = fma2(q0.y, ainv_xy, e_xy);
-            const u64 T1 = fma2(q1.x, inv_xy, noi_xy), H1 = fma2(q1.y, ainv_xy, e_xy);
-            const u64 Tz = fma2(q2.x, inv_zz, noi_zz), Hz = fma2(q2.y, ainv_zz, e_zz);
-            float n0x, n0y, f0x, f0y, n1x, n1y, f1x, f1y, nz0, nz1, fz0, fz1;
-            upk2(sub2(T0, H0), n0x, n0y); upk2(add2(T0, H0), f0x, f0y);
-            upk2(sub2(T1, H1), n1x, n1y); upk2(add2(T1, H1), f1x, f1y);
-            upk2(sub2(Tz, Hz), nz0, nz1); upk2(add2(Tz, Hz), fz0, fz1);
-            const float tn0 = fmaxf(fmaxf(n0x, n0y), nz0), tf0 = fminf(fminf(f0x, f0y), fz0);
-            const float tn1 = fmaxf(fmaxf(n1x, n1y), nz1), tf1 = fminf(fminf(f1x, f1y), fz1);
-            const bool h0 = fmaxf(tn0, 0.f) <= fminf(tf0, best_pad);
-            const bool h1 = fmaxf(tn1, 0.f) <= fminf(tf1, best_pad);
+            bool h0, h1;
+            float tn0, tn1;
+            int2 refs;
+            q_visit(P.qnodes, cur, Q, best_pad, h0, h1, tn0, tn1, refs);
             if (h0 & h1) {
                 const bool swap = tn1 < tn0;
                 if (sp < RTS_STACK_DEPTH) stack[sp++] = swap ? refs.x : refs.y;
@@ -185,11 +168,15 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_TRAV_MIN_BLOCKS) k_travers
             {
                 // back to the node loop: the slab constants come back from shared memory (also on the path of a finished
                 // ray, so that on no path the old values have to survive the triangle code above)
-                const unsigned a0 = (unsigned)__cvta_generic_to_shared(&s_const[0][threadIdx.x]);
-                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(inv_xy), "=l"(noi_xy) : "r"(a0));
-                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(ainv_xy), "=l"(e_xy) : "r"(a0 + (unsigned)sizeof(ulonglong2) * RTS_WAVE_BLOCK));
-                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(inv_zz), "=l"(noi_zz) : "r"(a0 + 2u * (unsigned)sizeof(ulonglong2) * RTS_WAVE_BLOCK));
-                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(ainv_zz), "=l"(e_zz) : "r"(a0 + 3u * (unsigned)sizeof(ulonglong2) * RTS_WAVE_BLOCK));
+                const unsigned sa = (unsigned)__cvta_generic_to_shared(&s_const[0][threadIdx.x]);
+                uint4 c0, c1, c2;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c0.x), "=r"(c0.y), "=r"(c0.z), "=r"(c0.w) : "r"(sa));
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c1.x), "=r"(c1.y), "=r"(c1.z), "=r"(c1.w) : "r"(sa + (unsigned)sizeof(uint4) * RTS_WAVE_BLOCK));
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c2.x), "=r"(c2.y), "=r"(c2.z), "=r"(c2.w) : "r"(sa + 2u * (unsigned)sizeof(uint4) * RTS_WAVE_BLOCK));
+                Q.a[0] = pk2(__uint_as_float(c0.x), __uint_as_float(c0.x)); Q.a[1] = pk2(__uint_as_float(c0.y), __uint_as_float(c0.y));
+                Q.a[2] = pk2(__uint_as_float(c0.z), __uint_as_float(c0.z)); Q.b[0] = pk2(__uint_as_float(c0.w), __uint_as_float(c0.w));
+                Q.b[1] = pk2(__uint_as_float(c1.x), __uint_as_float(c1.x)); Q.b[2] = pk2(__uint_as_float(c1.y), __uint_as_float(c1.y));
+                Q.sn[0] = c1.z; Q.sn[1] = c1.w; Q.sn[2] = c2.x; Q.sf[0] = c2.y; Q.sf[1] = c2.z; Q.sf[2] = c2.w;
             }
         }
     }

@@ -291,6 +291,126 @@ __device__ __forceinline__ void traverse(const WaveParams &P, const d3 &o, const
     }
 }
 
+// ---- the same traversal over the quantised 32-byte nodes (engine.h: QNode), for rays that start inside the scene ----
+// A plane of a child box is x(q) = lo + q * ext / 32768 on the frame (lo, ext) of the scene (fp32 values, exact reals
+// here); k_pack rounds every box outward to such planes and widens it by one more cell.  Per axis, per ray:
+//     inv = rcp.approx(fl32(d))                               relative error <= 1.5 * 2^-23
+//     A   = fl32(ext * inv)                                   B = fl32((lo - o) * inv - A)       ((lo - o) * inv - A in fp64)
+//     t   = fma(val, A, B),  val = 1 + q / 32768              (exact: one PRMT of the node's half word with 0x3F800000)
+// B is formed from the rounded A, so val * A + B = (q / 32768) * A + (lo - o) * inv: A's rounding only touches the
+// first term.  With r = |lo - o| / ext and cell = ext / 32768, in units of cell * |inv|:
+//     inv:  1.5 * 2^-23 * |t| <= 1.5 * 2^-8 (r + 1)     A: 2^-9     B: 2^-9 (r + 1)     fma: 2^-9 (r + 1)
+// together < 0.0098 (r + 1) + 0.002 cells — 0.02 cells for an origin inside the frame (every ray of a later wave: it starts
+// on a triangle), under one cell for r <= 64; beyond that (and for |d| < 1e-20) the axis is ignored: near = -inf, far =
+// 3e38.  The one-cell widening of the boxes therefore makes the test conservative with respect to the exact slab
+// interval of the fp64 ray, like traverse()'s.  The sign of inv picks which half word is the near plane (PRMT selector).
+#ifndef RTS_QNODES
+#define RTS_QNODES 1           // 0: later waves walk the 64-byte fp32 nodes too (tuning builds)
+#endif
+struct QRay {
+    u64 a[3], b[3];            // (A, A), (B, B): lanes = child 0, child 1
+    uint32_t sn[3], sf[3];     // PRMT selectors of the near / far plane
+};
+constexpr uint32_t Q_MAGIC = 0x3F800000u;
+
+__device__ __forceinline__ void q_setup(const WaveParams &P, const d3 &o, const d3 &dir, QRay &Q)
+{
+    const double oo[3] = {o.x, o.y, o.z};
+    const float dd[3] = {(float)dir.x, (float)dir.y, (float)dir.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const float flo = __ldg(&P.qframe->lo[k]), ext = __ldg(&P.qframe->ext[k]);
+        const double rel = (double)flo - oo[k];
+        float A = 3.0e38f, B = 0.f;
+        uint32_t sn = 0xE654u, sf = 0x7654u;          // -inf and 1.0 from the magic word alone
+        if ((fabsf(dd[k]) >= 1e-20f) && (fabs(rel) <= 64.0 * (double)ext)) {
+            float inv;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(dd[k]));
+            A = ext * inv;
+            B = (float)(rel * (double)inv - (double)A);
+            sn = inv >= 0.f ? 0x7104u : 0x7324u;
+            sf = inv >= 0.f ? 0x7324u : 0x7104u;
+        }
+        Q.a[k] = pk2(A, A); Q.b[k] = pk2(B, B);
+        Q.sn[k] = sn; Q.sf[k] = sf;
+    }
+}
+
+// both child boxes of node `cur`: overlap of [tn, tf] with [0, best_pad] per child, entry distances, child references
+__device__ __forceinline__ void q_visit(const QNode *__restrict__ qnodes, int cur, const QRay &Q, float best_pad, bool &h0, bool &h1,
+                                        float &tn0, float &tn1, int2 &refs)
+{
+    const uint4 *np = reinterpret_cast<const uint4 *>(qnodes + cur);
+    const uint4 q0 = __ldg(np), q1 = __ldg(np + 1);      // (c0x, c0y, c0z, c1x) (c1y, c1z, ref0, ref1)
+    refs = make_int2((int)q1.z, (int)q1.w);
+#define QV(w, sel) __uint_as_float(__byte_perm((w), Q_MAGIC, (sel)))
+    const u64 Nx = fma2(pk2(QV(q0.x, Q.sn[0]), QV(q0.w, Q.sn[0])), Q.a[0], Q.b[0]);
+    const u64 Fx = fma2(pk2(QV(q0.x, Q.sf[0]), QV(q0.w, Q.sf[0])), Q.a[0], Q.b[0]);
+    const u64 Ny = fma2(pk2(QV(q0.y, Q.sn[1]), QV(q1.x, Q.sn[1])), Q.a[1], Q.b[1]);
+    const u64 Fy = fma2(pk2(QV(q0.y, Q.sf[1]), QV(q1.x, Q.sf[1])), Q.a[1], Q.b[1]);
+    const u64 Nz = fma2(pk2(QV(q0.z, Q.sn[2]), QV(q1.y, Q.sn[2])), Q.a[2], Q.b[2]);
+    const u64 Fz = fma2(pk2(QV(q0.z, Q.sf[2]), QV(q1.y, Q.sf[2])), Q.a[2], Q.b[2]);
+#undef QV
+    float n0x, n1x, n0y, n1y, n0z, n1z, f0x, f1x, f0y, f1y, f0z, f1z;
+    upk2(Nx, n0x, n1x); upk2(Ny, n0y, n1y); upk2(Nz, n0z, n1z);
+    upk2(Fx, f0x, f1x); upk2(Fy, f0y, f1y); upk2(Fz, f0z, f1z);
+    tn0 = fmaxf(fmaxf(n0x, n0y), n0z); tn1 = fmaxf(fmaxf(n1x, n1y), n1z);
+    const float tf0 = fminf(fminf(f0x, f0y), f0z), tf1 = fminf(fminf(f1x, f1y), f1z);
+    h0 = fmaxf(tn0, 0.f) <= fminf(tf0, best_pad);
+    h1 = fmaxf(tn1, 0.f) <= fminf(tf1, best_pad);
+}
+
+template <bool COUNT, bool STATIC_ONLY = false>
+__device__ __forceinline__ void traverse_q(const WaveParams &P, const d3 &o, const d3 &dir, float tmin_f, HitRec &best,
+                                           unsigned &n_nodes, unsigned &n_tris, unsigned &stack_ovf)
+{
+    best.pos = -1; best.t = RT_DEFAULT_MAX_F; best.id = 0xffffffffu;
+    if (P.n_tris == 0) return;
+    QRay Q;
+    q_setup(P, o, dir, Q);
+    const double tmin_d = (double)tmin_f, tmax_d = (double)RT_DEFAULT_MAX_F;
+    float best_pad = CUDART_INF_F;
+    constexpr int SENT = 0x7fffffff;
+    int stack[RTS_STACK_DEPTH];
+    int sp = 0;
+    int cur = P.root_ref;
+    while (cur != SENT) {
+        while ((unsigned)cur < (unsigned)SENT) {
+            if (COUNT) n_nodes++;
+            bool h0, h1;
+            float tn0, tn1;
+            int2 refs;
+            q_visit(P.qnodes, cur, Q, best_pad, h0, h1, tn0, tn1, refs);
+            if (h0 & h1) {
+                const bool swap = tn1 < tn0;
+                if (sp < RTS_STACK_DEPTH) stack[sp++] = swap ? refs.x : refs.y;
+                else stack_ovf++;
+                cur = swap ? refs.y : refs.x;
+            } else if (h0) cur = refs.x;
+            else if (h1) cur = refs.y;
+            else cur = sp ? stack[--sp] : SENT;
+        }
+        if (cur < 0) {
+            const int code = ~cur;
+            const int first = code >> 3, cnt = (code & 7) + 1;
+            for (int k = 0; k < cnt; k++) {
+                if (COUNT) n_tris++;
+                const Tri T = load_tri(P.trirec, first + k);
+                if (STATIC_ONLY && P.moving_flags[T.target]) continue;
+                double t;
+                if (tri_accept(T, o, dir, tmin_d, tmax_d, t)) {
+                    const float tf = (float)t;
+                    if (tf > tmin_f && (tf < best.t || (tf == best.t && T.id < best.id))) {
+                        best.t = tf; best.pos = first + k; best.id = T.id;
+                        best_pad = tf * 1.000001f;
+                    }
+                }
+            }
+            cur = sp ? stack[--sp] : SENT;
+        }
+    }
+}
+
 // Chain end: the record the reference writes back for this result slot
 // (ray_tracer.cu:246-253 for slot 0, normal_shader.cu:272-279 for refracted slots).
 template <bool RECORDS>
@@ -736,7 +856,10 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
         for (bool first = true;; first = false) {
             HitRec h;
             unsigned nn = 0, nt = 0;
-            traverse<COUNT>(P, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz), SCENE_EPS, h, nn, nt, L.overflow); // SCENE_EPS == SCENE_EPS_R (ray_tracer.h:9-10)
+            // SCENE_EPS == SCENE_EPS_R (ray_tracer.h:9-10).  Later waves start on a triangle, i.e. inside the frame of the
+            // quantised nodes; a primary ray starts at the transmitter, wherever that is: fp32 nodes
+            if (PRIMARY || !RTS_QNODES) traverse<COUNT>(P, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz), SCENE_EPS, h, nn, nt, L.overflow);
+            else traverse_q<COUNT>(P, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz), SCENE_EPS, h, nn, nt, L.overflow);
             if (COUNT) { L.nodes += nn; L.tris += nt; }
             if (PRIMARY) {
                 r.len = 0; r.pw = 0; r.dop = 0; r.fx = 0; r.fy = 0; r.fz = 0; r.n0 = 1; r.n1 = 1;

@@ -126,10 +126,10 @@ def test_sparse_table_overflow_is_reported(eng):
     eng.trace(spec, L.RTS_OUT_BINS)            # a handful of bins: fits
     few = len(eng.bins())
     assert 0 < few <= 16
-    ms = scenes.terrain_scene(n=256, cells_x=100, cells_y=50, movers=12, n_rx=3)
-    eng.set_targets(ms.world_targets(3))
+    targets, spec = _many_targets()            # 23 distinct (receiver, path) bins
+    eng.set_targets(targets)
     with pytest.raises(L.RtsError, match="dropped|overflow|capacity"):
-        eng.trace(ms.spec_for(3), L.RTS_OUT_BINS)
+        eng.trace(spec, L.RTS_OUT_BINS)
     eng.set_option("hash_log2", 22)
-    eng.trace(ms.spec_for(3), L.RTS_OUT_BINS)
+    eng.trace(spec, L.RTS_OUT_BINS)
     assert len(eng.bins()) > 16
