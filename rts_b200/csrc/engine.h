@@ -220,7 +220,7 @@ struct DirsKey {
 // Tuning / test switches: read from the environment once in rts_create, changed afterwards only through rts_set_option.
 struct Knobs {
     int no_chain = 0, no_raster = 0, no_tiles = 0, one_ended_queue = 0, debug_raster = 0, no_static_hits = 0,
-        no_kept_reflections = 0, no_split = 0, no_graph = 0;
+        no_kept_reflections = 0, no_split = 1, no_graph = 0, no_follow = 0;
     long long batch = 0;           // 0 = default 2^24 primaries per batch
     int hash_bins = 0;             // 1: sparse (hashed) bins also where a dense table would fit
     uint32_t hash_log2 = 22;       // slots of the sparse bin table
@@ -236,6 +236,8 @@ struct rts_engine {
     cudaEvent_t wave_ev[34] = {};
     cudaEvent_t split_ev[3] = {};      // around k_traverse and k_shade_wave of the second wave
     bool split_timed = false;
+    bool followed = false;             // this pulse's primary shading pass traced the first reflections in place (follow.cuh)
+    int follow_grid = 0;
     float split_ms[2] = {};
     unsigned long long *d_wave_segs = nullptr;
     float wave_ms[32] = {};

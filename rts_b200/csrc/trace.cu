@@ -305,7 +305,7 @@ __device__ __forceinline__ void traverse(const WaveParams &P, const d3 &o, const
 // 3e38.  The one-cell widening of the boxes therefore makes the test conservative with respect to the exact slab
 // interval of the fp64 ray, like traverse()'s.  The sign of inv picks which half word is the near plane (PRMT selector).
 #ifndef RTS_QNODES
-#define RTS_QNODES 1           // 0: later waves walk the 64-byte fp32 nodes too (tuning builds)
+#define RTS_QNODES 0           // 1: later waves walk the quantised 32-byte nodes (measured slower: 1.61 vs 1.37 ms; kept as a tuning build)
 #endif
 struct QRay {
     u64 a[3], b[3];            // (A, A), (B, B): lanes = child 0, child 1
@@ -795,6 +795,7 @@ __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r
 #include "raster.cuh"
 #include "coherent.cuh"
 #include "split.cuh"
+#include "follow.cuh"
 
 template <bool PRIMARY, bool RECORDS, bool COUNT, bool CHAIN>
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_PRIMARY : RTS_WAVE_MIN_BLOCKS) k_wave(const __grid_constant__ WaveParams P)
@@ -943,7 +944,7 @@ int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool rec
     const int grid = primary ? e->wave_grid_primary : e->wave_grid;   // persistent: resident CTAs per SM x SMs
     const bool count = (p.flags & RTS_COUNT_NODES) != 0;
     if (primary) launch_variant<true, false>(grid, e->stream, p, records, count);
-    else if (p.wave_index >= 2 && p.chain_below) launch_variant<false, true>(grid, e->stream, p, records, count);
+    else if (p.wave_index >= (e->followed ? 1u : 2u) && p.chain_below) launch_variant<false, true>(grid, e->stream, p, records, count);
     else launch_variant<false, false>(grid, e->stream, p, records, count);
     RTS_CUDA(cudaGetLastError());
     e->launches++;
@@ -1096,7 +1097,18 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     // shading pass looks the leaf position up itself
     p.hits_resolved = e->coh_on ? 1u : 0u;
     if (e->coh_on) { k_raster_resolve<<<e->num_sms * 16, 256, 0, st>>>(p); e->launches++; }
-    if (records) k_primary_shade<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
+    // Without kept first-reflection hits the shading pass follows each reflection in place (follow.cuh): the second wave's
+    // queue round trip (88 bytes written and read back per lit pixel) disappears, and the next launch is a thin one.
+    e->followed = !e->coh_on && !e->knobs.no_follow && p.dMax >= 2;
+    if (e->followed) {
+        if (!e->follow_grid) {
+            int occ = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_primary_follow<false>, RTS_WAVE_BLOCK, 0);
+            e->follow_grid = e->num_sms * (occ > 0 ? occ : 1);
+        }
+        if (records) k_primary_follow<true><<<e->follow_grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        else k_primary_follow<false><<<e->follow_grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+    } else if (records) k_primary_shade<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     else k_primary_shade<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     RTS_CUDA(cudaGetLastError());
     e->launches += 1;

@@ -6,5 +6,5 @@ python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pyte
 run fusedQ RTS_NO_SPLIT=1
 run splitQ
 run fused_noq RTS_NO_SPLIT=1 RTS_B200_LIB=rts_b200/variants/librts_b200_noq.so
-for v in w5 w7 w8; do run fusedQ_$v RTS_NO_SPLIT=1 RTS_B200_LIB=rts_b200/variants/librts_b200_$v.so; done
-for v in t6 t7 t9 t8f16; do run splitQ_$v RTS_B200_LIB=rts_b200/variants/librts_b200_$v.so; done
+run split_noq RTS_B200_LIB=rts_b200/variants/librts_b200_noq.so
+for v in w7 w8; do run fusedQ_$v RTS_NO_SPLIT=1 RTS_B200_LIB=rts_b200/variants/librts_b200_$v.so; done
