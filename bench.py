@@ -16,7 +16,8 @@ value  : K steps timed without reading the bins back (inputs resident, CUDA even
          traced from scratch (RTS_NO_REUSE); the figure with the library's between-pulse reuse on is in `temporal_reuse`
 e2e    : the same steps through the C-ABI with host buffers, plus the device->host read of the bins
 sustained: the `value` loop again for at least --sustain seconds (the K-step legs last only tens of milliseconds)
-roofline: the longest single kernel of a step.  `bound` names what binds it; `achieved`/`frac`/`traffic` are its measured
+roofline: the longest single kernel of a step (k_primary_follow: the projected primary wave's shading pass with every first
+         reflection traced in place).  `bound` names what binds it; `achieved`/`frac`/`traffic` are its measured
          DRAM bytes (ncu counters of one launch, taken by a child run of this very script at the end, or failing that
          the committed capture under profiles/) against the measured HBM peak; `algorithmic` keeps SURVEY.md §8(d)'s byte
          model; `issue` is the kernel's instruction issue rate against the SMs' peak.
@@ -234,12 +235,13 @@ def run_ours(args):
         launches0 = eng.kernel_launches()
         t0 = time.perf_counter()
         e0.record(stream)
-        waves, split, segs, caps, d2h = [], [], 0, 0, 0
+        waves, split, follow, segs, caps, d2h = [], [], [], 0, 0, 0
         for i in range(k):
             st, bins = step(k0 + i, read_back, reuse)
             if st is not None:
                 waves.append(eng.wave_profile())
                 split.append(eng.split_profile())
+                follow.append(eng.follow_profile())
                 segs += st["segments"]
                 caps += st["captured"]
                 # device -> pinned host per step: the emitted-bin block (256 x sizeof(rts_bin)), its count, the
@@ -252,7 +254,7 @@ def run_ours(args):
         t = torch.tensor([ms_dev, wall * 1e3], dtype=torch.float64, device=dev)
         if world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        return dict(ms=float(t[0]), wall_ms=float(t[1]), waves=waves, split=split, segments=segs, captured=caps, d2h=d2h,
+        return dict(ms=float(t[0]), wall_ms=float(t[1]), waves=waves, split=split, follow=follow, segments=segs, captured=caps, d2h=d2h,
                     launches=eng.kernel_launches() - launches0)
 
     clocks = ClockSampler(local)
@@ -284,21 +286,31 @@ def run_ours(args):
     value = rays_per_step_total * args.steps / (r_dev["ms"] * 1e-3) / 1e6
     e2e = rays_per_step_total * args.steps / (r_e2e["ms"] * 1e-3) / 1e6
 
-    # The dominant kernel, rank 0's launches, timed live with the CUDA events the engine records on its stream: wave 0
-    # is a group of kernels (projected primary wave: directions, footprints, shading); the second wave (first reflections,
-    # ~13.5M rays) holds the longest single kernel of a step — k_traverse (split.cuh), or the fused k_wave when split is off.
+    # The dominant kernel, rank 0's launches, timed live with the CUDA events the engine records on its stream.  Wave 0 is a
+    # group of kernels (projected primary wave: directions, footprints, then k_primary_follow = shading of the primary hits
+    # with every first reflection traced in place, follow.cuh) — k_primary_follow is the longest single kernel of a step and
+    # has its own pair of events.  When it did not run (option no_follow), the second wave holds the longest kernel:
+    # k_traverse (split.cuh) or the fused k_wave.
     n_w = max((len(w) for w in r_e2e["waves"]), default=0)
     nst = max(1, len(r_e2e["waves"]))
     per_wave_ms = [sum(w[i][0] for w in r_e2e["waves"] if len(w) > i) / nst for i in range(n_w)]
     per_wave_seg = [sum(w[i][1] for w in r_e2e["waves"] if len(w) > i) / nst for i in range(n_w)]
-    dom = max(range(1, n_w), key=lambda i: per_wave_ms[i]) if n_w > 1 else 0
     trav_ms = sum(s[0] for s in r_e2e["split"]) / nst
     shade_ms = sum(s[1] for s in r_e2e["split"]) / nst
-    split_on = dom == 1 and trav_ms > 0
-    kernel_name = "k_traverse<COUNT=false> (second wave, split.cuh)" if split_on else \
-        (f"k_wave<PRIMARY=false,RECORDS=false,COUNT=false,CHAIN=false> (wave {dom})" if dom else "primary wave")
-    avg_ms = trav_ms if split_on else per_wave_ms[dom]
-    avg_seg = per_wave_seg[dom]
+    follow_ms = sum(r_e2e["follow"]) / nst
+    followed = follow_ms > 0
+    dom = 0 if followed else (max(range(1, n_w), key=lambda i: per_wave_ms[i]) if n_w > 1 else 0)
+    split_on = not followed and dom == 1 and trav_ms > 0
+    if followed:
+        kernel_name, ncu_regex = "k_primary_follow<RECORDS=false> (primary shading pass + first reflections in place, follow.cuh)", "k_primary_follow"
+        avg_ms = follow_ms
+        # segments of that launch that walk the BVH: the first reflections (wave 0 counts primaries + followed segments)
+        avg_seg = per_wave_seg[0] - n_mine
+    elif split_on:
+        kernel_name, ncu_regex, avg_ms, avg_seg = "k_traverse<COUNT=false> (second wave, split.cuh)", "k_traverse", trav_ms, per_wave_seg[dom]
+    else:
+        kernel_name = f"k_wave<PRIMARY=false,RECORDS=false,COUNT=false,CHAIN=false> (wave {dom})" if dom else "primary wave"
+        ncu_regex, avg_ms, avg_seg = "k_wave<\\(bool\\)0", per_wave_ms[dom], per_wave_seg[dom]
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -306,7 +318,9 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-    alg_bytes = avg_seg * B_SEG_1M
+    # 1632 B per segment that walks the tree; the fused kernel also streams 32 B per primary ray (hit word +
+    # direction) and gathers an 80-byte triangle record per primary hit (= per followed segment)
+    alg_bytes = avg_seg * B_SEG_1M + (n_mine * 32.0 + avg_seg * 80.0 if followed else 0.0)
     alg_gbs = alg_bytes / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     roof = {"bound": "issue/latency", "kernel": kernel_name, "achieved": None, "peak": peak, "unit": "GB/s", "frac": None, "traffic": None,
             "peak_source": peak_src, "ms_per_launch": round(avg_ms, 4), "segments_per_launch": int(avg_seg),
@@ -317,12 +331,13 @@ def run_ours(args):
                                     "neighbouring rays share nodes through L1/L2, so this is not a DRAM rate and may exceed 1"},
             "waves_ms_per_step": [round(x, 4) for x in per_wave_ms],
             "second_wave_kernels_ms": {"k_traverse": round(trav_ms, 4), "k_shade_wave": round(shade_ms, 4)},
+            "k_primary_follow_ms": round(follow_ms, 4),
             "all_waves_ms_per_step": round(sum(sum(x[0] for x in w) for w in r_e2e["waves"]) / nst, 4)}
     if rank == 0 and world == 1:
         counters, source = (None, "skipped (--quick / --no-ncu)")
         if not (args.quick or args.no_ncu):
             # the engine must let go of the GPU's profiler-visible state? no: ncu profiles the child process only
-            counters, source = ncu_counters("k_traverse" if split_on else "k_wave<\\(bool\\)0", 3 if split_on else 3)
+            counters, source = ncu_counters(ncu_regex, 2 if followed else 3)
             if counters is None:
                 log(f"[bench] {source}")
         if counters is None:
@@ -378,7 +393,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD + scaling_note,
                        "triangles": int(sum(len(t.tris) for t in ms.base)), "rays_per_step": int(rays_per_step_total),
                        "segments_per_ray": round(seg_per_ray, 4), "captured_per_step": int(r_e2e["captured"] / args.steps),
-                       "l2_policy": "per-step working set (BVH 64 MB + triangle records 81 MB + 2.4 GB of ray queues written and re-read) exceeds the 126 MB L2; no flush needed",
+                       "l2_policy": "per-step working set (BVH 64 MB + triangle records 81 MB + 0.4 GB of ray directions and 0.13 GB of hit words written and re-read) exceeds the 126 MB L2; no flush needed",
                        "parallelism": f"{'pulse' if mode == 'pulse' else 'ray'}-shard x{world}", "sharding": mode},
             "e2e": {"value": round(e2e, 2), "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(r_e2e["d2h"] / args.steps),
                     "ms_per_step": round(r_e2e["ms"] / args.steps, 4)},

@@ -135,6 +135,10 @@ int rts_get_wave_profile(rts_engine *e, uint32_t cap, float *ms, uint64_t *segme
  * queries of every first reflection), ms[1] = k_shade_wave (closest_hit / miss / bins of the survivors); both 0 when
  * that wave ran as the fused kernel.  The wave-level figure of rts_get_wave_profile also holds kernels that returned at once. */
 int rts_get_split_profile(rts_engine *e, float ms[2]);
+/* Device milliseconds of k_primary_follow in the last pulse (follow.cuh: the projected primary wave's shading pass with
+ * every first reflection traced in place — the longest single kernel of a from-scratch pulse); 0 when the pulse did not
+ * run it (kept first-reflection hits in use, BVH primary wave, max_refl == 0, option no_follow, several batches). */
+int rts_get_follow_profile(rts_engine *e, float *ms);
 /* Cumulative number of CUDA kernels this engine has launched (every <<<>>> of the library). */
 int rts_kernel_launches(rts_engine *e, uint64_t *out);
 /* Measurement aid (bench.py roofline): read bandwidth in GB/s of a `bytes`-sized device buffer streamed

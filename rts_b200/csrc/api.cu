@@ -124,6 +124,7 @@ extern "C" int rts_create(int device, rts_engine **out)
     for (auto &ev : e->ev) cudaEventCreate(&ev);
     for (auto &ev : e->wave_ev) cudaEventCreate(&ev);
     for (auto &ev : e->split_ev) cudaEventCreate(&ev);
+    for (auto &ev : e->follow_ev) cudaEventCreate(&ev);
     for (auto &s : e->stage) cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->sah_ev, cudaEventDisableTiming);
     if (cudaMallocHost((void **)&e->h_rb, sizeof(Readback)) != cudaSuccess) {
@@ -167,6 +168,7 @@ extern "C" void rts_destroy(rts_engine *e)
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->wave_ev) if (ev) cudaEventDestroy(ev);
     for (auto &ev : e->split_ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : e->follow_ev) if (ev) cudaEventDestroy(ev);
     for (auto &s : e->stage) { if (s.done) cudaEventDestroy(s.done); if (s.host) cudaFreeHost(s.host); }
     if (e->sah_ev) cudaEventDestroy(e->sah_ev);
     if (e->h_rb) cudaFreeHost(e->h_rb);
@@ -596,6 +598,8 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     RTS_CUDA(cudaMemsetAsync(e->d_counters, 0, sizeof(Counters), st));
 
     e->split_timed = false;
+    e->follow_timed = false;
+    e->followed = false;
     cudaEventRecord(e->ev[0], st);
     if (records) {
         int rc = agg_fill_records(e, sz.ray_total, sz.depth_total, sz.tri_cols);
@@ -703,6 +707,8 @@ int pulse_collect(rts_engine *e)
         cudaEventElapsedTime(&e->split_ms[0], e->split_ev[0], e->split_ev[1]);
         cudaEventElapsedTime(&e->split_ms[1], e->split_ev[1], e->split_ev[2]);
     }
+    e->follow_ms = 0.f;
+    if (e->follow_timed) cudaEventElapsedTime(&e->follow_ms, e->follow_ev[0], e->follow_ev[1]);
     collect_refit_time(e);
     rts_stats &s = e->stats;
     memset(&s, 0, sizeof(s));
@@ -754,6 +760,15 @@ extern "C" int rts_get_split_profile(rts_engine *e, float ms[2])
     if (!e->have_pulse) return rts_fail(RTS_ERR_STATE, "no pulse traced yet");
     pulse_collect(e);
     ms[0] = e->split_ms[0]; ms[1] = e->split_ms[1];
+    return RTS_OK;
+}
+
+extern "C" int rts_get_follow_profile(rts_engine *e, float *ms)
+{
+    if (!e || !ms) return rts_fail(RTS_ERR_ARG, "NULL argument");
+    if (!e->have_pulse) return rts_fail(RTS_ERR_STATE, "no pulse traced yet");
+    pulse_collect(e);
+    *ms = e->follow_ms;
     return RTS_OK;
 }
 

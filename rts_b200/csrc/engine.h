@@ -235,6 +235,9 @@ struct rts_engine {
     cudaEvent_t ev[6] = {};
     cudaEvent_t wave_ev[34] = {};
     cudaEvent_t split_ev[3] = {};      // around k_traverse and k_shade_wave of the second wave
+    cudaEvent_t follow_ev[2] = {};     // around k_primary_follow
+    bool follow_timed = false;
+    float follow_ms = 0.f;
     bool split_timed = false;
     bool followed = false;             // this pulse's primary shading pass traced the first reflections in place (follow.cuh)
     int follow_grid = 0;

@@ -1106,8 +1106,11 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_primary_follow<false>, RTS_WAVE_BLOCK, 0);
             e->follow_grid = e->num_sms * (occ > 0 ? occ : 1);
         }
+        const bool timed = single_batch && e->follow_ev[0];   // this kernel alone, apart from the directions / footprint passes of the wave (rts_get_follow_profile)
+        if (timed) cudaEventRecord(e->follow_ev[0], st);
         if (records) k_primary_follow<true><<<e->follow_grid, RTS_WAVE_BLOCK, 0, st>>>(p);
         else k_primary_follow<false><<<e->follow_grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        if (timed) { cudaEventRecord(e->follow_ev[1], st); e->follow_timed = true; }
     } else if (records) k_primary_shade<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     else k_primary_shade<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     RTS_CUDA(cudaGetLastError());

@@ -51,7 +51,7 @@ EXPORTS = [
     "rts_rx_sphere_from_desc", "rts_result_sizes", "rts_rect_mesh", "rts_sphere_mesh", "rts_file_mesh",
     "rts_rotation_matrix", "rts_scene_set_targets", "rts_scene_set_poses", "rts_scene_rebuild", "rts_scene_bvh_info",
     "rts_scene_get_world_vertices", "rts_scene_get_tri_bounds", "rts_scene_check_bvh", "rts_trace_pulse",
-    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_get_split_profile", "rts_kernel_launches", "rts_probe_read_bandwidth", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_get_records_shard", "rts_get_received", "rts_bins_device", "rts_bins_compact_device", "rts_bins_load_compact", "rts_finalise_bins", "rts_aggregate",
+    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_get_split_profile", "rts_get_follow_profile", "rts_kernel_launches", "rts_probe_read_bandwidth", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_get_records_shard", "rts_get_received", "rts_bins_device", "rts_bins_compact_device", "rts_bins_load_compact", "rts_finalise_bins", "rts_aggregate",
 ]
 
 _lib = None
@@ -96,6 +96,7 @@ def load() -> C.CDLL:
     lib.rts_get_stats.argtypes = [vp, P(RtsStats)]
     lib.rts_get_wave_profile.argtypes = [vp, u32, P(C.c_float), P(u64), P(u32)]
     lib.rts_get_split_profile.argtypes = [vp, P(C.c_float)]
+    lib.rts_get_follow_profile.argtypes = [vp, P(C.c_float)]
     lib.rts_kernel_launches.argtypes = [vp, P(u64)]
     lib.rts_probe_read_bandwidth.argtypes = [vp, u64, u32, P(dbl)]
     lib.rts_get_bins.argtypes = [vp, P(RtsBin), u32, P(u32)]
@@ -267,6 +268,12 @@ class Engine:
         ms = (C.c_float * 2)()
         _check(self._lib.rts_get_split_profile(self._h, ms))
         return float(ms[0]), float(ms[1])
+
+    def follow_profile(self) -> float:
+        """ms of k_primary_follow (primary shading + first reflections in place) in the last pulse; 0 when it did not run."""
+        ms = C.c_float()
+        _check(self._lib.rts_get_follow_profile(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def kernel_launches(self) -> int:
         v = C.c_uint64()

@@ -3,4 +3,4 @@
 run() { tag=$1; shift; env "$@" python bench.py --steps 32 --warmup 4 --quick 2>gpurun_out/ab_$tag.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); r=d['roofline']
-print('$tag', 'value', d['value'], 'ms/step', d['ms_per_step'], 'waves', r['waves_ms_per_step'], 'split', r['second_wave_kernels_ms'], 'e2e', d['e2e']['value'], flush=True)" || tail -3 gpurun_out/ab_$tag.err; }
+print('$tag', 'value', d['value'], 'ms/step', d['ms_per_step'], 'waves', r['waves_ms_per_step'], 'follow', r.get('k_primary_follow_ms'), 'split', r['second_wave_kernels_ms'], 'e2e', d['e2e']['value'], flush=True)" || tail -3 gpurun_out/ab_$tag.err; }

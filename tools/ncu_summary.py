@@ -55,19 +55,22 @@ for d in summ[:2]:
 def gb(s):
     v, u = s.split()
     return float(v) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[u]
-prim = [d for d in summ if "k_wave<1, 0" in d["Kernel Name"]]
-later = [d for d in summ if "k_wave<0, 0, 0, 0" in d["Kernel Name"]]
+# the dominant kernel's counters in the form bench.py's roofline falls back to when its own ncu child cannot run
+dom = [d for d in summ if "k_primary_follow" in d["Kernel Name"]] or [d for d in summ if "k_wave<0, 0, 0, 0" in d["Kernel Name"]]
 out = {"source": f"profiles/{tag}_k_wave_ncu_full.json (ncu --set full, one launch each)"}
-if prim:
-    out["k_wave_primary_dram_bytes_per_launch"] = gb(prim[0]["dram__bytes_read.sum"]) + gb(prim[0]["dram__bytes_write.sum"])
-if later:
-    out["k_wave_later_dram_bytes_per_launch"] = gb(later[0]["dram__bytes_read.sum"]) + gb(later[0]["dram__bytes_write.sum"])
-json.dump(out, open(os.path.join(out_dir, "r01_traffic.json"), "w"))
+if dom:
+    d0 = dom[0]
+    out.update({"kernel": d0["Kernel Name"], "dram__bytes_read.sum": gb(d0["dram__bytes_read.sum"]), "dram__bytes_write.sum": gb(d0["dram__bytes_write.sum"]),
+                "sm__inst_executed.sum": float(d0["smsp__inst_executed.sum"].split()[0]),
+                "smsp__issue_active.avg.pct_of_peak_sustained_active": float(d0["smsp__issue_active.avg.pct_of_peak_sustained_active"].split()[0]),
+                "sm__warps_active.avg.pct_of_peak_sustained_active": float(d0["sm__warps_active.avg.pct_of_peak_sustained_active"].split()[0]),
+                "smsp__thread_inst_executed_per_inst_executed.ratio": float(d0["smsp__thread_inst_executed_per_inst_executed.ratio"].split()[0])})
+json.dump(out, open(os.path.join(out_dir, f"{tag}_traffic.json"), "w"))
 print(out)
 # ---- one from-scratch step, kernel by kernel (the nine launches of the full capture are the traced part of one step):
 # the share of the step the roofline kernel takes, to set beside bench.py's roofline.kernel_share_of_step
 step = [(d["Kernel Name"], float(d["gpu__time_duration.sum"].split()[0]) * {"ms": 1.0, "us": 1e-3, "s": 1e3}[d["gpu__time_duration.sum"].split()[1]]) for d in summ]
 tot_step = sum(t for _, t in step)
-json.dump({"source": "the nine consecutive launches of the ncu --set full capture = every wave / projection kernel of one from-scratch step (pose update, refit and bin emission, ~0.15 ms, not captured)",
+json.dump({"source": "the consecutive launches of the ncu --set full capture = every wave / projection kernel of one from-scratch step (pose update, refit and bin emission, ~0.15 ms, not captured)",
            "total_ms": round(tot_step, 4), "kernels": [{"kernel": k, "ms": round(t, 4), "share_pct": round(100 * t / tot_step, 2)} for k, t in step]},
           open(os.path.join(out_dir, f"{tag}_step_breakdown.json"), "w"), indent=1)
