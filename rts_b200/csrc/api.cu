@@ -980,15 +980,24 @@ void kernel_wrapper(PerRayData *h_rx_results_arr, int *h_rx_intersects_arr, unsi
                     double *h_phase_arr, int *h_pathMatch)
 {
     (void)MaxThreads; (void)MaxBlocks;
-    static thread_local rts_engine *eng = nullptr;
-    if (!eng) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (rts_create(dev, &eng) != RTS_OK) {
+    // one engine per calling thread and device, created on first use and released when the thread ends
+    struct Holder {
+        rts_engine *eng = nullptr;
+        int dev = -1;
+        ~Holder() { if (eng) rts_destroy(eng); }
+    };
+    static thread_local Holder h;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!h.eng || h.dev != dev) {
+        if (h.eng) { rts_destroy(h.eng); h.eng = nullptr; }
+        if (rts_create(dev, &h.eng) != RTS_OK) {
             fprintf(stderr, "Fatal error: rs::kernel_wrapper: %s\n*** FAILED - ABORTING\n\n", rts_last_error());
             exit(1);
         }
+        h.dev = dev;
     }
+    rts_engine *eng = h.eng;
     if (rts_aggregate(eng, reinterpret_cast<rts_ray_record *>(h_rx_results_arr), h_rx_intersects_arr, receivedRays, depthTotal,
                       cspeed, carrier, h_npath_arr, h_power_arr, h_doppler_arr, h_delay_arr, h_phase_arr, h_pathMatch) != RTS_OK) {
         fprintf(stderr, "Fatal error: rs::kernel_wrapper: %s\n*** FAILED - ABORTING\n\n", rts_last_error());

@@ -19,6 +19,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_LIB = os.path.join(ORACLE_DIR, "liboracle.so")
 REF_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_rts.so")
 REF_AGG_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_aggregation.so")
+REF_MESH_LIB = os.path.join(ORACLE_DIR, "_ref", "libref_mesh.so")   # the reference's own mesh helpers (oracle/Makefile: ref)
 
 EDGE_TRI, EDGE_TIE, EDGE_WINDOW, EDGE_TMIN = 1, 2, 4, 8
 
@@ -259,6 +260,43 @@ def sphere_mesh(subdivs, radius, yaw=0.0, pitch=0.0, roll=0.0):
 
 def file_mesh(v_file, n_file, yaw=0.0, pitch=0.0, roll=0.0):
     return _mesh(oracle().orc_file_mesh, str(v_file).encode(), str(n_file).encode(), C.c_float(yaw), C.c_float(pitch), C.c_float(roll))
+
+
+_ref_mesh = None
+
+
+def ref_mesh():
+    """oracle/_ref/libref_mesh.so: ray_tracer.cpp's rect_mesh / sphere_mesh / file_mesh / vertex_rotation compiled unmodified."""
+    global _ref_mesh
+    if _ref_mesh is None:
+        lib = C.CDLL(REF_MESH_LIB)
+        P, u32, dbl = C.POINTER, C.c_uint32, C.c_double
+        tail = [P(dbl), P(u32), P(u32), P(u32), P(dbl), P(u32)]
+        lib.refm_rect_mesh.argtypes = [C.c_float] * 6 + tail
+        lib.refm_sphere_mesh.argtypes = [u32] + [C.c_float] * 4 + tail
+        lib.refm_file_mesh.argtypes = [C.c_char_p, C.c_char_p] + [C.c_float] * 3 + tail
+        lib.refm_vertex_rotation.argtypes = [P(dbl), u32, C.c_float, C.c_float, C.c_float]
+        lib.refm_vertex_rotation.restype = None
+        _ref_mesh = lib
+    return _ref_mesh
+
+
+def ref_rect_mesh(w, h, d, yaw=0.0, pitch=0.0, roll=0.0):
+    return _mesh(ref_mesh().refm_rect_mesh, C.c_float(w), C.c_float(h), C.c_float(d), C.c_float(yaw), C.c_float(pitch), C.c_float(roll))
+
+
+def ref_sphere_mesh(subdivs, radius, yaw=0.0, pitch=0.0, roll=0.0):
+    return _mesh(ref_mesh().refm_sphere_mesh, C.c_uint32(subdivs), C.c_float(radius), C.c_float(yaw), C.c_float(pitch), C.c_float(roll))
+
+
+def ref_file_mesh(v_file, n_file, yaw=0.0, pitch=0.0, roll=0.0):
+    return _mesh(ref_mesh().refm_file_mesh, str(v_file).encode(), str(n_file).encode(), C.c_float(yaw), C.c_float(pitch), C.c_float(roll))
+
+
+def ref_rotation_matrix(yaw, pitch, roll) -> np.ndarray:
+    e = np.eye(3)
+    ref_mesh().refm_vertex_rotation(e.ctypes.data_as(C.POINTER(C.c_double)), 3, C.c_float(yaw), C.c_float(pitch), C.c_float(roll))
+    return np.ascontiguousarray(e.T)
 
 
 def rotation_matrix(yaw, pitch, roll) -> np.ndarray:

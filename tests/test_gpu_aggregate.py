@@ -112,6 +112,49 @@ def test_aggregate_matches_reference_aggregation_cu(engine, seed):
     assert np.array_equal(b["path_match"], pm) and np.allclose(b["delay"], acc["delay"], rtol=1e-12)
 
 
+def test_kernel_wrapper_by_its_reference_symbol(engine):
+    """rs::kernel_wrapper called the way a host linked against the reference calls it — through the C++ symbol with the
+    reference's signature (aggregation.cuh:18-23), host arrays in and out, no engine handle — from two threads (each gets
+    its own engine, released when the thread ends) and compared with rts_aggregate and the literal oracle."""
+    import threading
+    from rts_b200 import lib as L
+    lib = L.load()
+    fn = getattr(lib, "_ZN2rs14kernel_wrapperEP10PerRayDataPijjjjddPdS3_S3_S3_S3_S2_")
+    fn.restype = None
+    fn.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_double, C.c_double] + \
+        [C.POINTER(C.c_double)] * 5 + [C.POINTER(C.c_int)]
+    spec = PulseSpec(grid=(1, 1, 1), max_refl=2, max_refr=2)
+    dp = lambda x: x.ctypes.data_as(C.POINTER(C.c_double))
+    out = {}
+
+    def call(seed):
+        res, rows = _random_case(seed, R=2500)
+        R, D = len(res), rows.shape[1]
+        r2 = res.copy()
+        acc = {k: np.zeros(R) for k in ("npath", "power", "doppler", "delay", "phase")}
+        pm = np.full(R, R + 1, dtype=np.int32)                     # ray_tracer.cpp:1271
+        for _ in range(2):                                         # the second call reuses the thread's engine
+            r2[:] = res
+            fn(r2.ctypes.data_as(C.c_void_p), rows.ctypes.data_as(C.POINTER(C.c_int)), R, D, 256, 1024, spec.cspeed, spec.carrier,
+               dp(acc["npath"]), dp(acc["power"]), dp(acc["doppler"]), dp(acc["delay"]), dp(acc["phase"]), pm.ctypes.data_as(C.POINTER(C.c_int)))
+        out[seed] = (res, rows, r2, acc, pm)
+
+    threads = [threading.Thread(target=call, args=(s,)) for s in (21, 22)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for seed in (21, 22):
+        res, rows, r2, acc, pm = out[seed]
+        a = engine.aggregate(res, rows, spec.cspeed, spec.carrier, ray_total=len(res))
+        b = O.aggregate(res, rows, spec, literal=True, ray_total=len(res))
+        for want in (a, b):
+            assert np.array_equal(want["path_match"], pm)
+            assert np.allclose(want["delay"], acc["delay"], rtol=1e-5) and np.allclose(want["phase"], acc["phase"], rtol=1e-5)
+            assert np.allclose(want["results"]["power"], r2["power"], rtol=1e-5, atol=1e-300)
+            assert np.allclose(want["results"]["doppler"], r2["doppler"], rtol=1e-5, atol=1e-9)
+
+
 @pytest.mark.parametrize("scene", ["slab", "direct+", "direct-"])
 def test_fused_rcs_gains_and_responses(engine, scene):
     """RTS_OUT_BINS with per-target RCS and Gt/Gr (the SOARS callbacks of ray_tracer.cpp:1219-1247 as scalars) and

@@ -97,3 +97,35 @@ def test_random_helper_parameters_match_the_oracle(seed):
     pos = tuple(float(x) for x in rng.normal(0, 5000.0, 3))
     args = (pos, float(rng.uniform(-7, 7)), float(rng.uniform(-1.5, 1.5)), float(10.0 ** rng.uniform(-1, 3)), float(rng.uniform(0.01, 6.0)), float(rng.uniform(0.01, 3.0)))
     assert bytes(lib.rx_sphere_from_desc(*args)) == bytes(O.rx_sphere_from_desc(*args))
+
+
+# ---- pinned to the reference's own code: oracle/_ref/libref_mesh.so is ray_tracer.cpp's helper functions compiled unmodified
+needs_ref_mesh = pytest.mark.skipif(not os.path.exists(O.REF_MESH_LIB), reason="oracle/_ref/libref_mesh.so not built (make -C oracle ref)")
+
+
+def _same(a, b):
+    return all(x.shape == y.shape and x.tobytes() == y.tobytes() for x, y in zip(a, b))
+
+
+@needs_ref_mesh
+@pytest.mark.parametrize("seed", range(16))
+def test_helpers_match_the_reference_functions(seed, tmp_path):
+    """rts_rect_mesh / rts_sphere_mesh / rts_file_mesh / rts_rotation_matrix and the oracle's restatement, bit for bit
+    against rect_mesh / sphere_mesh / file_mesh / vertex_rotation of /root/reference/ray_tracer.cpp itself."""
+    rng = np.random.default_rng(900 + seed)
+    w, h, d = (float(x) for x in 10.0 ** rng.uniform(-3, 3, 3))
+    ypr = tuple(float(x) for x in rng.uniform(-8.0, 8.0, 3)) if seed else (0.0, 0.0, 0.0)
+    want = O.ref_rect_mesh(w, h, d, *ypr)
+    assert _same(lib.rect_mesh(w, h, d, *ypr), want) and _same(O.rect_mesh(w, h, d, *ypr), want)
+    sub, rad = int(rng.integers(0, 4)), float(rng.choice([-1.0, 1.0]) * 10.0 ** rng.uniform(-2, 2))
+    want = O.ref_sphere_mesh(sub, rad, *ypr)
+    assert _same(lib.sphere_mesh(sub, rad, *ypr), want) and _same(O.sphere_mesh(sub, rad, *ypr), want)
+    want = O.ref_rotation_matrix(*ypr)
+    assert np.array_equal(lib.rotation_matrix(*ypr), want) and np.array_equal(O.rotation_matrix(*ypr), want)
+    n = int(rng.integers(1, 9))
+    fmt = lambda row: "%.17g %.17g %.17g, %.17g %.17g %.17g, %.17g %.17g %.17g,\n" % tuple(row)
+    vf, nf = tmp_path / "v.txt", tmp_path / "n.txt"
+    vf.write_text("".join(fmt(r) for r in rng.normal(size=(n, 9)) * 10.0 ** rng.uniform(-2, 3)))
+    nf.write_text("".join(fmt(r) for r in rng.normal(size=(n, 9))))
+    want = O.ref_file_mesh(vf, nf, *ypr)
+    assert _same(lib.file_mesh(vf, nf, *ypr), want) and _same(O.file_mesh(vf, nf, *ypr), want)
