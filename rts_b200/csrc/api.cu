@@ -220,6 +220,7 @@ template <class T> static int upload(T **dst, const std::vector<T> &src)
 
 extern "C" int rts_scene_set_targets(rts_engine *e, const rts_target_mesh *targets, uint32_t n_targets)
 {
+    NvtxRange nvtx_range("rts:scene_set_targets (upload + BVH build)");
     if (!e || (!targets && n_targets)) return rts_fail(RTS_ERR_ARG, "NULL argument");
     RTS_CUDA(cudaSetDevice(e->device));
     RTS_CUDA(cudaStreamSynchronize(e->stream));
@@ -298,6 +299,7 @@ static bool same_pose(const rts_pose &a, const rts_pose &b)
 
 extern "C" int rts_scene_set_poses(rts_engine *e, const rts_pose *poses, uint32_t n_targets)
 {
+    NvtxRange nvtx_range("rts:scene_set_poses (transform + refit)");
     if (!e || !poses) return rts_fail(RTS_ERR_ARG, "NULL argument");
     if (!e->scene_ready) return rts_fail(RTS_ERR_STATE, "no scene committed");
     if (n_targets != e->n_targets) return rts_fail(RTS_ERR_ARG, "%u poses for %u targets", n_targets, e->n_targets);
@@ -444,6 +446,7 @@ static int ensure_records(rts_engine *e, const rts_sizes &sz)
 
 extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags)
 {
+    NvtxRange nvtx_range("rts:trace_pulse");
     if (!e || !p) return rts_fail(RTS_ERR_ARG, "NULL argument");
     if (!e->scene_ready) return rts_fail(RTS_ERR_STATE, "no scene committed (rts_scene_set_targets)");
     if (!(flags & (RTS_OUT_BINS | RTS_OUT_RECORDS))) return rts_fail(RTS_ERR_ARG, "flags must request RTS_OUT_BINS and/or RTS_OUT_RECORDS");
@@ -639,6 +642,9 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
             Q.work_counter = e->d_counts + 32 + w;
             Q.wave_index = w;
             if (single_batch) cudaEventRecord(e->wave_ev[w], st);
+            char wave_name[24];
+            snprintf(wave_name, sizeof(wave_name), "rts:wave %u", w);
+            NvtxRange wave_range(wave_name);
             if (w == 0 && use_raster) {   // projected primary wave; the BVH one behind it runs only if the guard trips
                 int rr = trace_launch_raster(e, Q, records, single_batch);
                 if (rr) return rr;
@@ -692,6 +698,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
 // Wait for the pulse in flight and fold its read-back into e->stats / the wave profile.
 int pulse_collect(rts_engine *e)
 {
+    NvtxRange nvtx_range("rts:pulse_collect (wait)");
     if (!e->pulse_pending) return RTS_OK;
     RTS_CUDA(cudaStreamSynchronize(e->stream));
     e->pulse_pending = false;
@@ -830,6 +837,7 @@ extern "C" int rts_probe_read_bandwidth(rts_engine *e, uint64_t bytes, uint32_t 
 
 extern "C" int rts_get_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
 {
+    NvtxRange nvtx_range("rts:get_bins");
     if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
     if (!e->have_pulse || !(e->last_flags & RTS_OUT_BINS)) return rts_fail(RTS_ERR_STATE, "last pulse did not produce bins");
     RTS_CUDA(cudaSetDevice(e->device));
@@ -958,6 +966,7 @@ extern "C" int rts_aggregate(rts_engine *e, rts_ray_record *rx_results, const in
                              uint32_t depth_total, double cspeed, double carrier, double *npath, double *power,
                              double *doppler, double *delay, double *phase, int32_t *path_match)
 {
+    NvtxRange nvtx_range("rts:aggregate (kernel_wrapper)");
     if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
     if (received && (!rx_results || !npath || !power || !doppler || !delay || !phase || !path_match || (depth_total && !rx_intersects)))
         return rts_fail(RTS_ERR_ARG, "NULL array");

@@ -370,6 +370,16 @@ struct rts_engine {
 
 // error plumbing (api.cu)
 int rts_fail(int code, const char *fmt, ...);
+// NVTX ranges around the host-side stages (tracing hooks); without a profiler attached a range is one
+// function-pointer test.  Kernels of a stage show up under its range on the nsys / ncu timeline.
+#include <nvtx3/nvToolsExt.h>
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+
 #define RTS_CUDA(call)                                                                                  \
     do {                                                                                                \
         cudaError_t _e = (call);                                                                        \
