@@ -205,7 +205,32 @@ def run_ours(args):
     else:
         begin, count, stride = rank, 0, world
     n_mine = (ms.spec.rays - begin + stride - 1) // stride
-    reduce_bins = world > 1 and mode != "pulse"
+    reduce_bins = (world > 1 and mode != "pulse") or args.force_exchange
+    # the bins' exchange: two kernels over peer memory (comm.cu; handles swapped through torch.distributed once), or the
+    # pair of NCCL all-reduces (--exchange nccl, and the fallback where CUDA IPC is not available)
+    px = None
+    exchange = "none"
+    if reduce_bins and world == 1:      # measurement aid: the exchange path on one GPU (its own block only)
+        class _Solo:
+            def allreduce_bins(self):
+                eng.comm_allreduce_bins()
+
+            def close(self):
+                eng.comm_destroy()
+        eng.comm_create(0, 1, 1 << 16)
+        px, exchange = _Solo(), "peer (world 1)"
+    elif reduce_bins:
+        exchange = "nccl"
+        if args.exchange == "peer":
+            try:
+                px = rdist.PeerExchange(eng, dev, max_bins=1 << 16)
+                exchange = "peer"
+            except Exception as ex:  # noqa: BLE001
+                log(f"[bench] rank {rank}: peer-memory exchange unavailable ({ex}); using NCCL all-reduces")
+            ok = torch.tensor([1 if px is not None else 0], device=dev)
+            torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN)
+            if int(ok) == 0 and px is not None:
+                px.close(); px = None; exchange = "nccl"
 
     def step(pulse, read_back, reuse=False):
         # everything below is enqueued on one stream; nothing waits on the host unless the bins are read back.
@@ -217,7 +242,9 @@ def run_ours(args):
         spec = ms.spec_for(pulse)
         spec.ray_begin, spec.ray_count, spec.ray_stride = begin, count, stride
         eng.trace(spec, L.RTS_OUT_BINS | L.RTS_ASYNC | (0 if reuse else L.RTS_NO_REUSE) | (L.RTS_NO_FINALISE if reduce_bins else 0))
-        if reduce_bins:
+        if px is not None:
+            px.allreduce_bins()
+        elif reduce_bins:
             rdist.allreduce_bins(eng, dev)
         if read_back:
             bins = eng.bins()                                # D2H (waits for the pulse)
@@ -254,7 +281,7 @@ def run_ours(args):
         t = torch.tensor([ms_dev, wall * 1e3], dtype=torch.float64, device=dev)
         if world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        return dict(ms=float(t[0]), wall_ms=float(t[1]), waves=waves, split=split, follow=follow, segments=segs, captured=caps, d2h=d2h,
+        return dict(ms=float(t[0]), own_ms=ms_dev, wall_ms=float(t[1]), waves=waves, split=split, follow=follow, segments=segs, captured=caps, d2h=d2h,
                     launches=eng.kernel_launches() - launches0)
 
     clocks = ClockSampler(local)
@@ -263,8 +290,23 @@ def run_ours(args):
     for w in range(args.warmup):
         step(w, True)
     k0 = args.warmup
+    def comm_mark(tag, prev=[None]):
+        # peer exchange: mean wait for the slowest rank / kernel time per exchange since the last mark (stderr, every rank)
+        if px is None:
+            return
+        c = eng.comm_stats()
+        if prev[0] is not None and c["exchanges"] > prev[0]["exchanges"]:
+            n = c["exchanges"] - prev[0]["exchanges"]
+            w = (c["wait_us"] * c["exchanges"] - prev[0]["wait_us"] * prev[0]["exchanges"]) / n
+            k = (c["kernel_us"] * c["exchanges"] - prev[0]["kernel_us"] * prev[0]["exchanges"]) / n
+            log(f"[bench] rank {rank}: {tag}: {n} exchanges, waited {w:.1f} us for the slowest rank, reduce kernel {k:.1f} us on average")
+        prev[0] = c
+
+    comm_mark("warm-up")
     r_dev = timed(k0, args.steps, read_back=False)
+    comm_mark("value leg")
     r_e2e = timed(k0, args.steps, read_back=True)
+    comm_mark("e2e leg")
     # the sustained leg: the same loop for at least --sustain seconds (same K on every rank)
     r_sus = None
     if args.sustain > 0 and not args.quick:
@@ -295,6 +337,8 @@ def run_ours(args):
     nst = max(1, len(r_e2e["waves"]))
     per_wave_ms = [sum(w[i][0] for w in r_e2e["waves"] if len(w) > i) / nst for i in range(n_w)]
     per_wave_seg = [sum(w[i][1] for w in r_e2e["waves"] if len(w) > i) / nst for i in range(n_w)]
+    if world > 1:
+        log(f"[bench] rank {rank}: waves ms/step {[round(x, 4) for x in per_wave_ms]}, own value-leg device time {r_dev['own_ms'] / args.steps:.4f} ms/step")
     trav_ms = sum(s[0] for s in r_e2e["split"]) / nst
     shade_ms = sum(s[1] for s in r_e2e["split"]) / nst
     follow_ms = sum(r_e2e["follow"]) / nst
@@ -383,8 +427,8 @@ def run_ours(args):
     if rank == 0:
         seg_per_ray = r_e2e["segments"] / (n_mine * args.steps)
         h2d = len(ms.base) * 112 + len(ms.base) * 24 + 64   # poses + target velocities + receiver
-        scaling_note = {"weak": f", launch grid (1,{N_GRID * world},{N_GRID}) ray-sharded round-robin, NCCL all-reduce of bins",
-                        "strong": f", the (1,{N_GRID},{N_GRID}) launch ray-sharded round-robin over {world} GPUs, NCCL all-reduce of bins",
+        scaling_note = {"weak": f", launch grid (1,{N_GRID * world},{N_GRID}) ray-sharded round-robin, bins reduced across the GPUs every pulse",
+                        "strong": f", the (1,{N_GRID},{N_GRID}) launch ray-sharded round-robin over {world} GPUs, bins reduced across the GPUs every pulse",
                         "pulse": f", pulse-sharded: rank r traces pulses p = r mod {world} in full, no exchange; a step = {world} pulses"}[mode] if world > 1 else ""
         out = {
             "metric": "Mrays/s (3-bounce, 1M-tri scene)", "value": round(value, 2), "unit": "Mrays/s", "n_gpus": world,
@@ -394,7 +438,7 @@ def run_ours(args):
                        "triangles": int(sum(len(t.tris) for t in ms.base)), "rays_per_step": int(rays_per_step_total),
                        "segments_per_ray": round(seg_per_ray, 4), "captured_per_step": int(r_e2e["captured"] / args.steps),
                        "l2_policy": "per-step working set (BVH 64 MB + triangle records 81 MB + 0.4 GB of ray directions and 0.13 GB of hit words written and re-read) exceeds the 126 MB L2; no flush needed",
-                       "parallelism": f"{'pulse' if mode == 'pulse' else 'ray'}-shard x{world}", "sharding": mode},
+                       "parallelism": f"{'pulse' if mode == 'pulse' else 'ray'}-shard x{world}", "sharding": mode, "bin_exchange": exchange},
             "e2e": {"value": round(e2e, 2), "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(r_e2e["d2h"] / args.steps),
                     "ms_per_step": round(r_e2e["ms"] / args.steps, 4)},
             "gpu_launches": int(r_dev["launches"]),
@@ -418,6 +462,9 @@ def run_ours(args):
         if cpu is not None:
             out["cpu_baseline"] = cpu
         print(json.dumps(out), flush=True)
+    if px is not None:
+        barrier()              # nobody unmaps a block a peer may still be reading
+        px.close()
     if world > 1:
         torch.distributed.destroy_process_group()
     eng.close()
@@ -497,11 +544,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong", "pulse"], help="how N > 1 GPUs share the work (see the module docstring)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: bins reduced by the library's peer-memory kernels or by NCCL all-reduces")
     ap.add_argument("--sustain", type=float, default=2.0, help="seconds of the sustained leg (0 = off)")
     ap.add_argument("--cpu-stride", type=int, default=0, help="oracle sample: every n-th primary ray (0 = 1 for cpu_baseline; for --impl reference 0 = chosen so that the run takes about 100 s)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ncu", action="store_true", help="do not spawn the ncu child for the roofline counters")
     ap.add_argument("--quick", action="store_true", help="A/B runs: only the value and e2e legs")
+    ap.add_argument("--force-exchange", action="store_true", help="N = 1: run the peer-memory exchange path on the one GPU (measures its fixed cost)")
     ap.add_argument("--ncu-child", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.ncu_child:

@@ -6,8 +6,9 @@
 //
 //   one host thread per GPU  ->  rts_create(g) · rts_scene_set_targets · own cudaStream (rts_set_stream)
 //   per pulse                ->  rts_scene_set_poses · rts_trace_pulse(BINS | NO_FINALISE | ASYNC) on rays g, g+N, ...
-//                                ncclAllReduce(SUM, double) over bins[n][5], ncclAllReduce(MIN, uint64) over the slots
-//                                rts_finalise_bins · rts_get_bins
+//                                rts_comm_allreduce_bins: the library's own exchange over peer memory (default), or
+//                                (--exchange nccl) ncclAllReduce(SUM, double) over bins[n][5] + ncclAllReduce(MIN, uint64)
+//                                over the slots, then rts_finalise_bins; rts_get_bins
 //   check                    ->  a second engine on GPU 0 traces the whole launch un-sharded; the reduced bins must
 //                                have the same keys, counts and representative slots, and sums within 1e-9
 //
@@ -125,9 +126,11 @@ struct Scene {
 int main(int argc, char **argv)
 {
     int n_gpus = 0, grid = 2048, pulses = 8, cells = 256, n_rx = 4, movers = 8;
+    bool peer = true;      // bins reduced by the library's peer-memory kernels (rts_comm_*); --exchange nccl: two NCCL all-reduces
     for (int i = 1; i + 1 < argc; i += 2) {
         const std::string a = argv[i];
         const int v = std::atoi(argv[i + 1]);
+        if (a == "--exchange") { peer = std::string(argv[i + 1]) != "nccl"; continue; }
         if (a == "--gpus") n_gpus = v; else if (a == "--grid") grid = v; else if (a == "--pulses") pulses = v;
         else if (a == "--cells") cells = v; else if (a == "--rx") n_rx = v; else if (a == "--movers") movers = v;
         else { std::fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
@@ -180,6 +183,7 @@ int main(int argc, char **argv)
     for (int g = 0; g < n_gpus; g++) devs[g] = g;
     CHECK_NCCL(ncclCommInitAll(comms.data(), n_gpus, devs.data()));
     Barrier bar(n_gpus);
+    std::vector<void *> xchg(n_gpus, nullptr);             // every rank's exchange block (peer-memory exchange)
     std::vector<std::vector<rts_bin>> reduced(pulses);     // rank 0's view of every pulse
     std::vector<float> ms_pulse(pulses, 0.f);
     uint64_t launches = 0;
@@ -194,6 +198,20 @@ int main(int argc, char **argv)
         CHECK_RTS(rts_scene_set_targets(e, S.views.data(), (uint32_t)K));
         cudaEvent_t e0, e1;
         CHECK_CUDA(cudaEventCreate(&e0)); CHECK_CUDA(cudaEventCreate(&e1));
+        if (peer) {
+            // one exchange block per GPU, mapped by every other GPU of this process: peer access + raw pointers
+            CHECK_RTS(rts_comm_create(e, (uint32_t)g, (uint32_t)n_gpus, 1u << 16));
+            CHECK_RTS(rts_comm_local_ptr(e, &xchg[g]));
+            for (int q = 0; q < n_gpus; q++)
+                if (q != g) {
+                    cudaError_t pe = cudaDeviceEnablePeerAccess(q, 0);
+                    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) { std::fprintf(stderr, "GPU %d cannot map GPU %d: %s\n", g, q, cudaGetErrorString(pe)); std::exit(2); }
+                    cudaGetLastError();
+                }
+            bar.wait();
+            CHECK_RTS(rts_comm_connect_ptrs(e, xchg.data()));
+            bar.wait();
+        }
         rts_pulse mine = S.pulse;
         mine.ray_begin = (uint64_t)g; mine.ray_count = 0; mine.ray_stride = (uint64_t)n_gpus;   // rays g, g+N, g+2N, ...
         for (int p = -1; p < pulses; p++) {                 // p = -1: warm-up
@@ -203,14 +221,18 @@ int main(int argc, char **argv)
             CHECK_CUDA(cudaEventRecord(e0, st));
             CHECK_RTS(rts_scene_set_poses(e, poses.data(), (uint32_t)K));
             CHECK_RTS(rts_trace_pulse(e, &mine, RTS_OUT_BINS | RTS_NO_FINALISE | RTS_ASYNC | RTS_NO_REUSE));
-            void *sums = nullptr, *mins = nullptr;
-            uint64_t n_sums = 0, n_mins = 0;
-            CHECK_RTS(rts_bins_device(e, &sums, &n_sums, &mins, &n_mins));
-            CHECK_NCCL(ncclGroupStart());
-            CHECK_NCCL(ncclAllReduce(sums, sums, n_sums, ncclDouble, ncclSum, comms[g], st));
-            CHECK_NCCL(ncclAllReduce(mins, mins, n_mins, ncclUint64, ncclMin, comms[g], st));
-            CHECK_NCCL(ncclGroupEnd());
-            CHECK_RTS(rts_finalise_bins(e));
+            if (peer) {
+                CHECK_RTS(rts_comm_allreduce_bins(e));         // publish, wait for the peers, reduce in rank order, finalise
+            } else {
+                void *sums = nullptr, *mins = nullptr;
+                uint64_t n_sums = 0, n_mins = 0;
+                CHECK_RTS(rts_bins_device(e, &sums, &n_sums, &mins, &n_mins));
+                CHECK_NCCL(ncclGroupStart());
+                CHECK_NCCL(ncclAllReduce(sums, sums, n_sums, ncclDouble, ncclSum, comms[g], st));
+                CHECK_NCCL(ncclAllReduce(mins, mins, n_mins, ncclUint64, ncclMin, comms[g], st));
+                CHECK_NCCL(ncclGroupEnd());
+                CHECK_RTS(rts_finalise_bins(e));
+            }
             CHECK_CUDA(cudaEventRecord(e1, st));
             uint32_t n = 0;
             std::vector<rts_bin> bins(4096);
@@ -223,6 +245,7 @@ int main(int argc, char **argv)
             }
         }
         if (g == 0) CHECK_RTS(rts_kernel_launches(e, &launches));
+        bar.wait();                                         // nobody frees a block a peer may still be reading
         rts_destroy(e);
         cudaStreamDestroy(st);
     };
@@ -272,8 +295,8 @@ int main(int argc, char **argv)
     const double rays = (double)grid * grid;
     size_t tris = 0;
     for (const Mesh &m : S.meshes) tris += m.tris.size() / 3;
-    std::printf("{\"gpus\": %d, \"pulses\": %d, \"rays_per_pulse\": %.0f, \"triangles\": %zu, \"receivers\": %d, \"bins\": %zu, "
+    std::printf("{\"gpus\": %d, \"exchange\": \"%s\", \"pulses\": %d, \"rays_per_pulse\": %.0f, \"triangles\": %zu, \"receivers\": %d, \"bins\": %zu, "
                 "\"ms_per_pulse\": %.4f, \"Mrays_per_s\": %.1f, \"kernel_launches_rank0\": %llu, \"max_rel_vs_single_gpu\": %.3e, \"ok\": %s}\n",
-                n_gpus, pulses, rays, tris, n_rx, n_bins, ms, rays / (ms * 1e-3) / 1e6, (unsigned long long)launches, max_rel, ok ? "true" : "false");
+                n_gpus, peer ? "peer" : "nccl", pulses, rays, tris, n_rx, n_bins, ms, rays / (ms * 1e-3) / 1e6, (unsigned long long)launches, max_rel, ok ? "true" : "false");
     return ok ? 0 : 1;
 }

@@ -191,6 +191,24 @@ int rts_bins_load_compact(rts_engine *e, const void *keys_device, const void *su
 /* Marks the (externally reduced) bins final and enqueues their emission on the engine's stream: call it after the
  * reduction has been enqueued on that same stream (rts_set_stream) or has completed. */
 int rts_finalise_bins(rts_engine *e);
+/* ---- Peer-memory exchange of the receiver bins (one engine per GPU of one NVLink/NVSwitch node; comm.cu) -----------
+ * Replaces the pair of NCCL all-reduces behind a ray- or pulse-sharded launch (the reference has no multi-GPU path; the
+ * exchanged quantity is the commutative aggregation of aggregation.cu:56-69).  Every rank creates an exchange block,
+ * the ranks swap its handle (rts_comm_ipc_handle between processes — any transport, e.g. an all-gather of 64 bytes —
+ * or rts_comm_local_ptr between the threads of one process after cudaDeviceEnablePeerAccess) and connect; from then on
+ * rts_comm_allreduce_bins, called by every rank once per pulse traced with RTS_OUT_BINS | RTS_NO_FINALISE, enqueues on
+ * the engine's stream: publish this rank's accumulators, wait for the peers', reduce all of them in rank order (the same
+ * bits on every GPU) and finalise (as rts_finalise_bins).  Dense bin tables only; max_bins bounds their size.
+ * A rank that never arrives makes the others give up after ~2 s: RTS_ERR_STATE at the next collection, no hang. */
+int rts_comm_create(rts_engine *e, uint32_t rank, uint32_t world, uint64_t max_bins);
+int rts_comm_ipc_handle(rts_engine *e, void *handle_64_bytes);
+int rts_comm_local_ptr(rts_engine *e, void **device_ptr);
+int rts_comm_connect_ipc(rts_engine *e, const void *handles /* world x 64 bytes, rank order */);
+int rts_comm_connect_ptrs(rts_engine *e, void *const *device_ptrs /* world, rank order */);
+int rts_comm_allreduce_bins(rts_engine *e);
+/* out = {exchanges so far, mean ns the reduce kernel waited for the slowest rank's flag, mean ns it ran}; waits for the stream. */
+int rts_comm_stats(rts_engine *e, double out[3]);
+int rts_comm_destroy(rts_engine *e);
 
 /* ---- aggregation of caller-supplied received rays: the C form of rs::kernel_wrapper
  *      (aggregation.cuh:18-23, aggregation.cu:103-184).  Same array contract: accumulators

@@ -160,9 +160,10 @@ extern "C" void rts_destroy(rts_engine *e)
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
+    rts_comm_destroy(e);
     free_scene(e);
     for (int k = 0; k < 2; k++) if (e->q_slab[k]) cudaFree(e->q_slab[k]);
-    void *ptrs[] = {e->d_ckeys, e->d_csums, e->d_cmins, e->d_hash_keys, e->d_hash_used, e->d_hash_count, e->d_trav_hits, e->d_todo, e->d_w1_static, e->d_target_box, e->d_mover_nodes, e->d_dirs, e->d_hits, e->d_hits_static, e->d_raster_ctl, e->d_raster_ctl_static, e->d_raster_items, e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count, e->d_rx_sums, e->d_rx_mins,
+    void *ptrs[] = {e->d_ckeys, e->d_csums, e->d_cmins, e->d_hash_keys, e->d_hash_used, e->d_hash_count, e->d_trav_hits, e->d_todo, e->d_coop_stacks, e->d_w1_static, e->d_target_box, e->d_mover_nodes, e->d_dirs, e->d_hits, e->d_hits_static, e->d_raster_ctl, e->d_raster_ctl_static, e->d_raster_items, e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count, e->d_rx_sums, e->d_rx_mins,
                     e->d_results, e->d_targ_intersect, e->d_tri_path, e->d_rcs_angle};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -728,6 +729,10 @@ int pulse_collect(rts_engine *e)
     if (e->knobs.debug_raster && e->pulse_raster)
         fprintf(stderr, "[raster] candidates %llu (+ %llu kept from the static pass), %u row chunks, projected %u\n", e->h_rb->raster.area, e->h_rb->raster_static.area, e->h_rb->raster.n_items, s.primary_projected);
     if (c.overflow) return rts_fail(RTS_ERR_CAPACITY, "%llu ray states dropped (queue/stack overflow)", (unsigned long long)c.overflow);
+    if (e->comm.check_timeout) {
+        e->comm.check_timeout = false;
+        if (e->h_rb->comm_timed_out) return rts_fail(RTS_ERR_STATE, "peer-memory bin exchange: a rank did not publish its bins within 2 s (every rank must call rts_comm_allreduce_bins once per pulse)");
+    }
     return RTS_OK;
 }
 

@@ -17,6 +17,8 @@
 #define RTS_WAVE_MIN_BLOCKS_PRIMARY 8   // same, primary wave (its state is smaller)
 #endif
 #define RTS_MAX_RX 64
+#define RTS_COOP_STACK 4096u     // entries of a warp's shared stack in the cooperative traversal of a straggler ray (follow.cuh)
+#define RTS_MAX_WORLD 16          // GPUs of one node that can share a peer-memory bin exchange (comm.cu)
 #define RTS_EAGER_BINS 256u      // bins brought to pinned host memory right behind a pulse
 #define RTS_REBUILD_RATIO 1.2   // refit falls back to a rebuild when SAH cost exceeds this x the as-built cost
 
@@ -189,6 +191,9 @@ struct WaveParams {
     // kernel (which returns at once for the others when split_on is set).
     unsigned long long *trav_hits;
     uint32_t split_on, split_below, split_keep_all;
+    // follow.cuh: per-warp scratch stacks of the warp-cooperative traversal that finishes straggler rays
+    // (RTS_COOP_STACK entries per resident warp of k_primary_follow)
+    int *coop_stacks;
 };
 
 // ---- engine ---------------------------------------------------------------------------------
@@ -199,6 +204,7 @@ struct Readback {
     double sah;
     RasterCtl raster, raster_static;
     uint32_t bins_count;
+    unsigned long long comm_timed_out;   // peer-memory exchange: a rank never arrived (comm.cu)
 };
 
 // One slot of the pinned staging ring for small per-pulse host arrays (poses, receivers, velocities, RCS).
@@ -215,6 +221,18 @@ struct DirsKey {
     int single;
     uint64_t begin, stride, base, n;
     double c[30];   // origin, beamStart, slope, Rot, Rot1, boresight
+};
+
+// Peer-memory exchange of the receiver bins (comm.cu): this rank's exchange block and the mapped blocks of its peers.
+struct Comm {
+    char *block = nullptr;
+    uint64_t bytes = 0, max_bins = 0, half_words = 0;
+    uint32_t rank = 0, world = 0;
+    char *peer[RTS_MAX_WORLD] = {};
+    bool ipc_opened[RTS_MAX_WORLD] = {};
+    bool connected = false, check_timeout = false;
+    unsigned long long seq = 0;
+    int clock_khz = 1965000;
 };
 
 // Tuning / test switches: read from the environment once in rts_create, changed afterwards only through rts_set_option.
@@ -322,6 +340,7 @@ struct rts_engine {
     unsigned *d_target_box = nullptr;
     BvhNode *d_mover_nodes = nullptr;
     uint32_t *d_todo = nullptr;
+    int *d_coop_stacks = nullptr;      // follow.cuh: RTS_COOP_STACK ints per resident warp of k_primary_follow
     uint64_t todo_alloc = 0;
     unsigned long long *d_trav_hits = nullptr;   // split.cuh: one hit word per queue slot
     uint64_t trav_alloc = 0;
@@ -358,6 +377,8 @@ struct rts_engine {
     bool pulse_pending = false;        // a pulse was enqueued and its read-back not yet folded into `stats`
     bool pulse_single_batch = false, pulse_raster = false;
     uint64_t pulse_primary = 0, pulse_waves = 0;
+
+    Comm comm;
 
     // last pulse
     bool have_pulse = false, bins_finalised = false;

@@ -204,12 +204,19 @@ __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0,
 // fp32 pairs, matching the BvhNode word order: 12 packed instructions test both child boxes.
 // Closest hit = smallest fp32 t in (tmin, inf), ties to the lowest global triangle id
 // (rtPotentialIntersection semantics with a defined tie rule).
-template <bool COUNT, bool STATIC_ONLY = false>
-__device__ __forceinline__ void traverse(const WaveParams &P, const d3 &o, const d3 &dir, float tmin_f, HitRec &best,
+// BUDGET (k_primary_follow): a ray whose walk needs more than RTS_FOLLOW_BUDGET leaf visits / stack pops is given up
+// (the return value says so; best is then meaningless) so that the caller can queue it for the next, thin launch instead
+// of holding 31 finished lanes and, at the end of the launch, the whole GPU (see follow.cuh).
+#ifndef RTS_FOLLOW_BUDGET
+#define RTS_FOLLOW_BUDGET 48u
+#endif
+template <bool COUNT, bool STATIC_ONLY = false, bool BUDGET = false>
+__device__ __forceinline__ bool traverse(const WaveParams &P, const d3 &o, const d3 &dir, float tmin_f, HitRec &best,
                                          unsigned &n_nodes, unsigned &n_tris, unsigned &stack_ovf)
 {
     best.pos = -1; best.t = RT_DEFAULT_MAX_F; best.id = 0xffffffffu;
-    if (P.n_tris == 0) return;
+    if (P.n_tris == 0) return true;
+    unsigned rounds = 0;
     u64 inv_xy, noi_xy, ainv_xy, e_xy, inv_zz, noi_zz, ainv_zz, e_zz;
     {
         const float oo[3] = {(float)o.x, (float)o.y, (float)o.z}, dd[3] = {(float)dir.x, (float)dir.y, (float)dir.z};
@@ -240,6 +247,7 @@ __device__ __forceinline__ void traverse(const WaveParams &P, const d3 &o, const
     int sp = 0;
     int cur = P.root_ref;
     while (cur != SENT) {
+        if (BUDGET && ++rounds > RTS_FOLLOW_BUDGET) return false;
         while ((unsigned)cur < (unsigned)SENT) {
             if (COUNT) n_nodes++;
             const ulonglong2 *np = reinterpret_cast<const ulonglong2 *>(P.nodes + cur);
@@ -289,6 +297,7 @@ __device__ __forceinline__ void traverse(const WaveParams &P, const d3 &o, const
             cur = sp ? stack[--sp] : SENT;
         }
     }
+    return true;
 }
 
 // ---- the same traversal over the quantised 32-byte nodes (engine.h: QNode), for rays that start inside the scene ----
@@ -1106,6 +1115,8 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_primary_follow<false>, RTS_WAVE_BLOCK, 0);
             e->follow_grid = e->num_sms * (occ > 0 ? occ : 1);
         }
+        if (!e->d_coop_stacks) RTS_CUDA(cudaMalloc(&e->d_coop_stacks, COOP_WARP_BYTES * (size_t)e->follow_grid * (RTS_WAVE_BLOCK / 32)));
+        p.coop_stacks = e->d_coop_stacks;
         const bool timed = single_batch && e->follow_ev[0];   // this kernel alone, apart from the directions / footprint passes of the wave (rts_get_follow_profile)
         if (timed) cudaEventRecord(e->follow_ev[0], st);
         if (records) k_primary_follow<true><<<e->follow_grid, RTS_WAVE_BLOCK, 0, st>>>(p);

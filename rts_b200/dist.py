@@ -80,6 +80,36 @@ def allreduce_bins(engine, device, group=None):
     engine.finalise_bins()
 
 
+class PeerExchange:
+    """The bins' exchange over peer memory instead of NCCL (include/rts_b200.h: rts_comm_*; csrc/comm.cu): every rank's
+    exchange block is mapped into every other rank's address space through CUDA IPC — the 64-byte handles travel over
+    torch.distributed once — and from then on a pulse's exchange is two small kernels on the engine's stream that
+    publish this rank's accumulators, wait for the peers' and reduce all of them in rank order over NVLink.
+
+        px = PeerExchange(engine, device, max_bins)      # collective: every rank of the group
+        engine.trace(spec, RTS_OUT_BINS | RTS_NO_FINALISE | RTS_ASYNC); px.allreduce_bins()   # every rank, every pulse
+    """
+
+    def __init__(self, engine, device, max_bins: int, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.engine = engine
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        engine.comm_create(rank, world, max_bins)
+        mine = torch.frombuffer(bytearray(engine.comm_ipc_handle()), dtype=torch.uint8).to(device)
+        handles = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(handles, mine, group=group)
+        engine.comm_connect_ipc(b"".join(bytes(h.cpu().numpy().tobytes()) for h in handles))
+        dist.barrier(group=group)          # nobody publishes before everyone has mapped everyone
+
+    def allreduce_bins(self):
+        self.engine.comm_allreduce_bins()
+
+    def close(self):
+        self.engine.comm_destroy()
+
+
 def exchange_sparse(keys, sums, mins, group=None):
     """The exchange step for sparse bins ("hash -> sorted key table + all-gather of keys"): every rank
     holds its occupied bins as compact arrays keys int64[n_r] (distinct), sums float64[n_r,5], mins int64[n_r].

@@ -51,7 +51,7 @@ EXPORTS = [
     "rts_rx_sphere_from_desc", "rts_result_sizes", "rts_rect_mesh", "rts_sphere_mesh", "rts_file_mesh",
     "rts_rotation_matrix", "rts_scene_set_targets", "rts_scene_set_poses", "rts_scene_rebuild", "rts_scene_bvh_info",
     "rts_scene_get_world_vertices", "rts_scene_get_tri_bounds", "rts_scene_check_bvh", "rts_trace_pulse",
-    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_get_split_profile", "rts_get_follow_profile", "rts_kernel_launches", "rts_probe_read_bandwidth", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_get_records_shard", "rts_get_received", "rts_bins_device", "rts_bins_compact_device", "rts_bins_load_compact", "rts_finalise_bins", "rts_aggregate",
+    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_get_split_profile", "rts_get_follow_profile", "rts_kernel_launches", "rts_probe_read_bandwidth", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_get_records_shard", "rts_get_received", "rts_bins_device", "rts_bins_compact_device", "rts_bins_load_compact", "rts_finalise_bins", "rts_aggregate", "rts_comm_create", "rts_comm_ipc_handle", "rts_comm_local_ptr", "rts_comm_connect_ipc", "rts_comm_connect_ptrs", "rts_comm_allreduce_bins", "rts_comm_stats", "rts_comm_destroy",
 ]
 
 _lib = None
@@ -97,6 +97,14 @@ def load() -> C.CDLL:
     lib.rts_get_wave_profile.argtypes = [vp, u32, P(C.c_float), P(u64), P(u32)]
     lib.rts_get_split_profile.argtypes = [vp, P(C.c_float)]
     lib.rts_get_follow_profile.argtypes = [vp, P(C.c_float)]
+    lib.rts_comm_create.argtypes = [vp, u32, u32, u64]
+    lib.rts_comm_ipc_handle.argtypes = [vp, vp]
+    lib.rts_comm_local_ptr.argtypes = [vp, P(vp)]
+    lib.rts_comm_connect_ipc.argtypes = [vp, vp]
+    lib.rts_comm_connect_ptrs.argtypes = [vp, P(vp)]
+    lib.rts_comm_allreduce_bins.argtypes = [vp]
+    lib.rts_comm_destroy.argtypes = [vp]
+    lib.rts_comm_stats.argtypes = [vp, P(dbl)]
     lib.rts_kernel_launches.argtypes = [vp, P(u64)]
     lib.rts_probe_read_bandwidth.argtypes = [vp, u64, u32, P(dbl)]
     lib.rts_get_bins.argtypes = [vp, P(RtsBin), u32, P(u32)]
@@ -369,6 +377,39 @@ class Engine:
 
     def finalise_bins(self):
         _check(self._lib.rts_finalise_bins(self._h))
+
+    # ---- peer-memory bin exchange (include/rts_b200.h: rts_comm_*) ----
+    def comm_create(self, rank: int, world: int, max_bins: int):
+        _check(self._lib.rts_comm_create(self._h, int(rank), int(world), int(max_bins)))
+
+    def comm_ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(self._lib.rts_comm_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def comm_local_ptr(self) -> int:
+        p = C.c_void_p()
+        _check(self._lib.rts_comm_local_ptr(self._h, C.byref(p)))
+        return int(p.value)
+
+    def comm_connect_ipc(self, handles: bytes):
+        buf = C.create_string_buffer(bytes(handles), len(handles))
+        _check(self._lib.rts_comm_connect_ipc(self._h, buf))
+
+    def comm_connect_ptrs(self, ptrs):
+        arr = (C.c_void_p * len(ptrs))(*[C.c_void_p(int(p)) for p in ptrs])
+        _check(self._lib.rts_comm_connect_ptrs(self._h, arr))
+
+    def comm_allreduce_bins(self):
+        _check(self._lib.rts_comm_allreduce_bins(self._h))
+
+    def comm_stats(self) -> dict:
+        out = (C.c_double * 3)()
+        _check(self._lib.rts_comm_stats(self._h, out))
+        return {"exchanges": int(out[0]), "wait_us": out[1] * 1e-3, "kernel_us": out[2] * 1e-3}
+
+    def comm_destroy(self):
+        _check(self._lib.rts_comm_destroy(self._h))
 
     def set_option(self, name: str, value: int):
         """Tuning / test switch (include/rts_b200.h: rts_set_option); RTS_<NAME> in the environment sets the initial value."""

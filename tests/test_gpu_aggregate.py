@@ -130,11 +130,10 @@ def test_kernel_wrapper_by_its_reference_symbol(engine):
     def call(seed):
         res, rows = _random_case(seed, R=2500)
         R, D = len(res), rows.shape[1]
-        r2 = res.copy()
-        acc = {k: np.zeros(R) for k in ("npath", "power", "doppler", "delay", "phase")}
-        pm = np.full(R, R + 1, dtype=np.int32)                     # ray_tracer.cpp:1271
         for _ in range(2):                                         # the second call reuses the thread's engine
-            r2[:] = res
+            r2 = res.copy()                                        # fresh arrays per call, as the reference's host loop has them
+            acc = {k: np.zeros(R) for k in ("npath", "power", "doppler", "delay", "phase")}
+            pm = np.full(R, R + 1, dtype=np.int32)                 # ray_tracer.cpp:1271
             fn(r2.ctypes.data_as(C.c_void_p), rows.ctypes.data_as(C.POINTER(C.c_int)), R, D, 256, 1024, spec.cspeed, spec.carrier,
                dp(acc["npath"]), dp(acc["power"]), dp(acc["doppler"]), dp(acc["delay"]), dp(acc["phase"]), pm.ctypes.data_as(C.POINTER(C.c_int)))
         out[seed] = (res, rows, r2, acc, pm)

@@ -30,9 +30,12 @@ def test_cpp_host_builds_against_the_c_abi():
 
 @needs_nccl
 @pytest.mark.gpu
-def test_cpp_host_reduced_bins_equal_single_engine():
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_cpp_host_reduced_bins_equal_single_engine(exchange):
+    """All visible GPUs (one thread each); bins reduced by the library's peer-memory kernels (rts_comm_*) or by NCCL."""
     _build()
-    r = subprocess.run([BIN, "--grid", "768", "--pulses", "3", "--cells", "96"], capture_output=True, text=True, timeout=300)
+    r = subprocess.run([BIN, "--grid", "768", "--pulses", "3", "--cells", "96", "--exchange", exchange], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["exchange"] == exchange
     assert d["ok"] is True and d["bins"] >= 2 and d["max_rel_vs_single_gpu"] <= 1e-9 and d["kernel_launches_rank0"] > 0, d

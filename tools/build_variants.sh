@@ -14,7 +14,7 @@ for v in "$@"; do
 done
 wait
 for v in "$@"; do
-  nvcc $ARCH -shared -ccbin /usr/bin/g++ -o ../variants/librts_b200_$v.so api.o bvh.o ../variants/trace_$v.o aggregate.o host_mesh.o -cudart static -ldl
+  nvcc $ARCH -shared -ccbin /usr/bin/g++ -o ../variants/librts_b200_$v.so api.o bvh.o ../variants/trace_$v.o aggregate.o comm.o host_mesh.o -cudart static -ldl
   rm -f ../variants/trace_$v.o
 done
 ls -la ../variants
