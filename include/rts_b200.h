@@ -33,6 +33,8 @@ extern "C" {
 #define RTS_NO_FINALISE   8u  /* leave bins un-finalised (caller reduces across GPUs, then rts_finalise_bins) */
 #define RTS_NO_RCS_ANGLES 16u /* records mode: skip the four atan2 per bounce, leave rcs_angle at -1e6 */
 #define RTS_ASYNC         32u /* return once the pulse is enqueued on the engine's stream; rts_sync / any getter waits */
+#define RTS_TABLES        128u /* fused bins: per-hop RCS from the tables of rts_set_rcs_tables and gains from the antennas of
+                                 rts_set_antennas (angle-dependent Target::GetRCS / GetGain evaluated on the device) */
 #define RTS_NO_REUSE      64u /* trace this pulse from scratch: use nothing kept from earlier pulses (ray directions, static
                                  primary hits, static first-reflection hits — raster.cuh, coherent.cuh)                 */
 
@@ -125,6 +127,17 @@ int rts_scene_check_bvh(rts_engine *e, uint64_t *violations);
 
 /* ---- one pulse (replaces rtContextLaunch3D + the result hand-off, ray_tracer.cpp:1165-1258) ---- */
 int rts_trace_pulse(rts_engine *e, const rts_pulse *pulse, uint32_t flags);
+/* Angle-dependent callbacks as data (ray_tracer.cpp:1219-1247 without the per-ray host loop).
+ * rts_set_rcs_tables: one table per target, sampled by the caller from Target::GetRCS(az, el, Wl) over the summed
+ * in/out angles the reference stores in dbuf_rcs_angle (normal_shader.cu:259-265, 320-326: az in [-2pi, 2pi], el in
+ * [-pi, pi]); a target whose table has n_az == 0 keeps its scalar rts_pulse.targ_rcs (or 1).  The factor of a hop is
+ * folded into the ray's power where the reference writes that hop's angles.  Pulses without refraction only
+ * (max_refr == 0): the reference's pre-filled path rows of refracted chains are not reproduced by the fused form.
+ * rts_set_antennas: transmitter and per-receiver gain patterns + boresights + positions (rts_antenna); NULL keeps the
+ * scalar rts_pulse.gain_tx / gain_rx.  The tables are copied to the device; n_targets == 0 / NULL clears.
+ * A pulse uses them when traced with RTS_OUT_BINS | RTS_TABLES. */
+int rts_set_rcs_tables(rts_engine *e, const rts_table2d *tables, uint32_t n_targets);
+int rts_set_antennas(rts_engine *e, const rts_antenna *tx, const rts_antenna *rx, uint32_t n_rx);
 /* Wait for everything enqueued on the engine's stream (RTS_ASYNC pulses, pose updates) and report a deferred error. */
 int rts_sync(rts_engine *e);
 int rts_get_stats(rts_engine *e, rts_stats *out);

@@ -107,6 +107,26 @@ typedef struct rts_pulse {
     double   gain_tx, gain_rx;    /* Gt, Gr (:1233-1235); 0 is read as 1                              */
 } rts_pulse;
 
+/* Tabulated callbacks for the fused post-process (ray_tracer.cpp:1219-1247 on the device): a function of two angles sampled
+ * on a regular grid, values[i * n_el + j] = f(az0 + i * az_step, el0 + j * el_step), evaluated by bilinear interpolation
+ * with the arguments clamped to the grid (no wrap-around).  n_az == 0: no table (the scalar stand-in applies). */
+typedef struct rts_table2d {
+    uint32_t n_az, n_el;
+    double az0, az_step, el0, el_step;
+    const double *values;
+} rts_table2d;
+
+/* One antenna for the fused gains (Transmitter::GetGain / Receiver::GetGain, ray_tracer.cpp:1233-1235): the gain as a
+ * table over (azimuth, elevation) of the look direction MINUS the boresight, both in the simulator's spherical
+ * convention SVec3(Vec3): azimuth = atan2(y, x), elevation = asin(z / length).  The boresight of a receiver is taken at
+ * the ray's arrival time: bore + rate * delay (GetRotation(delay + time_t) of an antenna that turns at a constant rate).
+ * position: Transmitter/Receiver::GetPosition — for a receiver NOT the capture sphere's centre (ray_tracer.cpp:1201). */
+typedef struct rts_antenna {
+    rts_table2d gain;
+    double bore_az, bore_el, rate_az, rate_el;
+    double position[3];
+} rts_antenna;
+
 /* One (receiver, target-path) group — the unit the reference's aggregation produces
  * (aggregation.cu:32-97) and from which one Response is emitted (ray_tracer.cpp:1289-1321). */
 typedef struct rts_bin {

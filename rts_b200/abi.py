@@ -82,6 +82,66 @@ class RtsResponse(C.Structure):
                 ("doppler", C.c_double), ("phase", C.c_double)]
 
 
+class RtsTable2d(C.Structure):
+    """include/rts_types.h: rts_table2d."""
+    _fields_ = [("n_az", C.c_uint32), ("n_el", C.c_uint32), ("az0", C.c_double), ("az_step", C.c_double), ("el0", C.c_double),
+                ("el_step", C.c_double), ("values", C.POINTER(C.c_double))]
+
+
+class RtsAntenna(C.Structure):
+    """include/rts_types.h: rts_antenna."""
+    _fields_ = [("gain", RtsTable2d), ("bore_az", C.c_double), ("bore_el", C.c_double), ("rate_az", C.c_double), ("rate_el", C.c_double),
+                ("position", C.c_double * 3)]
+
+
+@dataclass
+class Table2d:
+    """A callback of two angles sampled on a regular grid (values[i, j] = f(az0 + i az_step, el0 + j el_step))."""
+    az0: float
+    az_step: float
+    el0: float
+    el_step: float
+    values: np.ndarray
+
+    def c(self) -> "RtsTable2d":
+        self.values = np.ascontiguousarray(self.values, dtype=np.float64)
+        t = RtsTable2d()
+        t.n_az, t.n_el = self.values.shape
+        t.az0, t.az_step, t.el0, t.el_step = float(self.az0), float(self.az_step), float(self.el0), float(self.el_step)
+        t.values = self.values.ctypes.data_as(C.POINTER(C.c_double))
+        return t
+
+    def __call__(self, az, el):
+        """The library's bilinear interpolation, in numpy (the host callback of the two-phase path in the tests)."""
+        n_az, n_el = self.values.shape
+        u = np.clip((np.asarray(az, dtype=np.float64) - self.az0) / self.az_step, 0.0, n_az - 1.0)
+        v = np.clip((np.asarray(el, dtype=np.float64) - self.el0) / self.el_step, 0.0, n_el - 1.0)
+        i0 = np.minimum(u.astype(np.int64), n_az - 1); j0 = np.minimum(v.astype(np.int64), n_el - 1)
+        i1 = np.minimum(i0 + 1, n_az - 1); j1 = np.minimum(j0 + 1, n_el - 1)
+        f, g = u - i0, v - j0
+        V = self.values
+        return (V[i0, j0] * (1 - f) + V[i1, j0] * f) * (1 - g) + (V[i0, j1] * (1 - f) + V[i1, j1] * f) * g
+
+
+@dataclass
+class Antenna:
+    """include/rts_types.h: rts_antenna (gain None: the scalar gain of the pulse applies)."""
+    position: tuple
+    bore_az: float = 0.0
+    bore_el: float = 0.0
+    rate_az: float = 0.0
+    rate_el: float = 0.0
+    gain: Optional[Table2d] = None
+
+    def c(self) -> "RtsAntenna":
+        a = RtsAntenna()
+        if self.gain is not None:
+            a.gain = self.gain.c()
+        a.bore_az, a.bore_el, a.rate_az, a.rate_el = float(self.bore_az), float(self.bore_el), float(self.rate_az), float(self.rate_el)
+        a.position = (C.c_double * 3)(*[float(x) for x in self.position])
+        return a
+
+
 RESPONSE_DTYPE = np.dtype([("rx", "<i4"), ("_pad", "<i4"), ("slot", "<u8"), ("power", "<f8"), ("delay", "<f8"), ("doppler", "<f8"), ("phase", "<f8")])
 
 

@@ -161,6 +161,7 @@ extern "C" void rts_destroy(rts_engine *e)
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     rts_comm_destroy(e);
+    for (void *p : {(void *)e->d_rcs_tab, (void *)e->d_rcs_values, (void *)e->d_ant_tx, (void *)e->d_ant_rx, (void *)e->d_ant_values}) if (p) cudaFree(p);
     free_scene(e);
     for (int k = 0; k < 2; k++) if (e->q_slab[k]) cudaFree(e->q_slab[k]);
     void *ptrs[] = {e->d_ckeys, e->d_csums, e->d_cmins, e->d_hash_keys, e->d_hash_used, e->d_hash_count, e->d_trav_hits, e->d_todo, e->d_coop_stacks, e->d_w1_static, e->d_target_box, e->d_mover_nodes, e->d_dirs, e->d_hits, e->d_hits_static, e->d_raster_ctl, e->d_raster_ctl_static, e->d_raster_items, e->d_counts, e->d_counters, e->d_rx, e->d_bin_sums, e->d_bin_mins, e->d_bins_out, e->d_bins_out_count, e->d_rx_sums, e->d_rx_mins,
@@ -493,6 +494,25 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
         P.wl2gain = (Wl * Wl * Gt * Gr);                          // ray_tracer.cpp:1247
     }
     P.t_rcs = p->targ_rcs ? e->d_t_rcs : nullptr;
+    if (flags & RTS_TABLES) {   // tabulated Target::GetRCS / GetGain on the device (rts_set_rcs_tables / rts_set_antennas)
+        if (!(flags & RTS_OUT_BINS) || (flags & RTS_OUT_RECORDS))
+            return rts_fail(RTS_ERR_ARG, "RTS_TABLES applies to the fused bins: trace with RTS_OUT_BINS and without RTS_OUT_RECORDS");
+        if (!e->d_rcs_tab && !e->d_ant_rx) return rts_fail(RTS_ERR_STATE, "RTS_TABLES without tables: rts_set_rcs_tables / rts_set_antennas first");
+        if (e->d_rcs_tab) {
+            if (rMax) return rts_fail(RTS_ERR_ARG, "tabulated RCS is not available with refraction (max_refr > 0): use the two-phase path (rts_get_received + rts_aggregate)");
+            if (e->n_rcs_tab != e->n_targets) return rts_fail(RTS_ERR_ARG, "%u RCS tables for %u targets", e->n_rcs_tab, e->n_targets);
+            P.rcs_tab = e->d_rcs_tab;
+        }
+        if (e->d_ant_rx) {
+            if (e->n_ant_rx != p->n_rx) return rts_fail(RTS_ERR_ARG, "%u receiver antennas for %u receivers", e->n_ant_rx, p->n_rx);
+            P.ant_tx = e->d_ant_tx; P.ant_rx = e->d_ant_rx;
+            P.keep_first = 1;
+            const double Wl = p->cspeed / p->carrier;
+            P.wl2 = Wl * Wl;
+            P.gain_tx_scalar = p->gain_tx != 0 ? p->gain_tx : 1.0;
+            P.gain_rx_scalar = p->gain_rx != 0 ? p->gain_rx : 1.0;
+        }
+    }
     P.B = (uint64_t)e->n_targets + 1;
     // path key: digits base B = n_targets + 1 (digit 0 <=> -1)
     const uint64_t B = (uint64_t)e->n_targets + 1;
@@ -658,7 +678,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
                 int rr = trace_launch_kept(e, Q, records);
                 if (rr) return rr;
             }
-            if (w >= 1 && !e->knobs.no_split) {   // the two-kernel form for waves that are large (split.cuh); decided on the device
+            if (w >= 1 && !e->knobs.no_split && !(Q.rcs_tab || Q.ant_rx)) {   // (the split form has no RTS_TABLES instantiation)   // the two-kernel form for waves that are large (split.cuh); decided on the device
                 Q.split_below = e->knobs.split_below;
                 int rr = trace_launch_split(e, Q, records);
                 if (rr) return rr;
@@ -733,6 +753,100 @@ int pulse_collect(rts_engine *e)
         e->comm.check_timeout = false;
         if (e->h_rb->comm_timed_out) return rts_fail(RTS_ERR_STATE, "peer-memory bin exchange: a rank did not publish its bins within 2 s (every rank must call rts_comm_allreduce_bins once per pulse)");
     }
+    return RTS_OK;
+}
+
+// ---- tabulated callbacks ------------------------------------------------------------------------
+static int check_table(const rts_table2d &t, const char *what, uint32_t k)
+{
+    if (t.n_az == 0) return RTS_OK;
+    if (!t.values || t.n_el == 0 || !(t.az_step > 0) || !(t.el_step > 0) || (uint64_t)t.n_az * t.n_el > (1ull << 26))
+        return rts_fail(RTS_ERR_ARG, "%s table %u: needs values, n_el > 0, positive steps and at most 2^26 samples", what, k);
+    return RTS_OK;
+}
+static DevTable dev_table(const rts_table2d &t, const double *values)
+{
+    DevTable d;
+    memset(&d, 0, sizeof(d));
+    d.n_az = t.n_az; d.n_el = t.n_az ? t.n_el : 0;
+    d.az0 = t.az0; d.az_step = t.az_step; d.el0 = t.el0; d.el_step = t.el_step;
+    d.values = t.n_az ? values : nullptr;
+    return d;
+}
+
+extern "C" int rts_set_rcs_tables(rts_engine *e, const rts_table2d *tables, uint32_t n_targets)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    RTS_CUDA(cudaSetDevice(e->device));
+    RTS_CUDA(cudaStreamSynchronize(e->stream));      // a pulse in flight may still read the old tables
+    if (e->d_rcs_tab) { cudaFree(e->d_rcs_tab); e->d_rcs_tab = nullptr; }
+    if (e->d_rcs_values) { cudaFree(e->d_rcs_values); e->d_rcs_values = nullptr; }
+    e->n_rcs_tab = 0;
+    if (!tables || !n_targets) return RTS_OK;
+    size_t total = 0;
+    for (uint32_t k = 0; k < n_targets; k++) {
+        int rc = check_table(tables[k], "RCS", k);
+        if (rc) return rc;
+        total += (size_t)tables[k].n_az * tables[k].n_el;
+    }
+    RTS_CUDA(cudaMalloc(&e->d_rcs_values, sizeof(double) * std::max<size_t>(total, 1)));
+    RTS_CUDA(cudaMalloc(&e->d_rcs_tab, sizeof(DevTable) * n_targets));
+    std::vector<DevTable> dev(n_targets);
+    size_t at = 0;
+    for (uint32_t k = 0; k < n_targets; k++) {
+        const size_t n = (size_t)tables[k].n_az * tables[k].n_el;
+        dev[k] = dev_table(tables[k], e->d_rcs_values + at);
+        if (n) RTS_CUDA(cudaMemcpy(e->d_rcs_values + at, tables[k].values, sizeof(double) * n, cudaMemcpyHostToDevice));
+        at += n;
+    }
+    RTS_CUDA(cudaMemcpy(e->d_rcs_tab, dev.data(), sizeof(DevTable) * n_targets, cudaMemcpyHostToDevice));
+    e->n_rcs_tab = n_targets;
+    return RTS_OK;
+}
+
+extern "C" int rts_set_antennas(rts_engine *e, const rts_antenna *tx, const rts_antenna *rx, uint32_t n_rx)
+{
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    RTS_CUDA(cudaSetDevice(e->device));
+    RTS_CUDA(cudaStreamSynchronize(e->stream));
+    for (void *p : {(void *)e->d_ant_tx, (void *)e->d_ant_rx, (void *)e->d_ant_values}) if (p) cudaFree(p);
+    e->d_ant_tx = nullptr; e->d_ant_rx = nullptr; e->d_ant_values = nullptr; e->n_ant_rx = 0;
+    if (!rx || !n_rx) {
+        if (tx) return rts_fail(RTS_ERR_ARG, "a transmitter antenna needs the receivers' antennas too (their positions orient the direct ray, ray_tracer.cpp:1206)");
+        return RTS_OK;
+    }
+    if (n_rx > RTS_MAX_RX) return rts_fail(RTS_ERR_CAPACITY, "%u receivers > %u", n_rx, RTS_MAX_RX);
+    size_t total = 0;
+    if (tx) { int rc = check_table(tx->gain, "transmitter gain", 0); if (rc) return rc; total += (size_t)tx->gain.n_az * tx->gain.n_el; }
+    for (uint32_t j = 0; j < n_rx; j++) {
+        int rc = check_table(rx[j].gain, "receiver gain", j);
+        if (rc) return rc;
+        total += (size_t)rx[j].gain.n_az * rx[j].gain.n_el;
+    }
+    RTS_CUDA(cudaMalloc(&e->d_ant_values, sizeof(double) * std::max<size_t>(total, 1)));
+    size_t at = 0;
+    auto make = [&](const rts_antenna &a, DevAntenna &d) -> int {
+        const size_t n = (size_t)a.gain.n_az * a.gain.n_el;
+        memset(&d, 0, sizeof(d));
+        d.gain = dev_table(a.gain, e->d_ant_values + at);
+        d.bore_az = a.bore_az; d.bore_el = a.bore_el; d.rate_az = a.rate_az; d.rate_el = a.rate_el;
+        memcpy(d.pos, a.position, sizeof(d.pos));
+        if (n) RTS_CUDA(cudaMemcpy(e->d_ant_values + at, a.gain.values, sizeof(double) * n, cudaMemcpyHostToDevice));
+        at += n;
+        return RTS_OK;
+    };
+    if (tx) {
+        DevAntenna d;
+        int rc = make(*tx, d);
+        if (rc) return rc;
+        RTS_CUDA(cudaMalloc(&e->d_ant_tx, sizeof(DevAntenna)));
+        RTS_CUDA(cudaMemcpy(e->d_ant_tx, &d, sizeof(d), cudaMemcpyHostToDevice));
+    }
+    std::vector<DevAntenna> dev(n_rx);
+    for (uint32_t j = 0; j < n_rx; j++) { int rc = make(rx[j], dev[j]); if (rc) return rc; }
+    RTS_CUDA(cudaMalloc(&e->d_ant_rx, sizeof(DevAntenna) * n_rx));
+    RTS_CUDA(cudaMemcpy(e->d_ant_rx, dev.data(), sizeof(DevAntenna) * n_rx, cudaMemcpyHostToDevice));
+    e->n_ant_rx = n_rx;
     return RTS_OK;
 }
 

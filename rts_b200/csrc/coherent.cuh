@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_WAVE_MIN_BLOCKS) k_wave1_f
 }
 
 // Every pulse: the flagged rays, served from the kept hits unless a moving target is near.
-template <bool RECORDS>
+template <bool RECORDS, bool TABLES = false>
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_wave1_kept(const __grid_constant__ WaveParams P)
 {
     const unsigned lane = threadIdx.x & 31u;
@@ -192,19 +192,19 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_wave1_
             P.todo_list[at + g.thread_rank()] = idx;
             continue;
         }
-        load_ray_rest(P.in, idx, r, RECORDS, P.rMax != 0);
+        load_ray_rest(P.in, idx, r, RECORDS || P.keep_first != 0, P.rMax != 0);
         r.meta &= ~M_COH;
         served++;
         if (kept != ~0ull) {
             HitRec h;
             h.pos = (int)(uint32_t)kept; h.t = __uint_as_float((unsigned)(kept >> 32)); h.id = 0;
             L.a += C_HIT;
-            shade<RECORDS>(P, r, h, L, false);
+            shade<RECORDS, TABLES>(P, r, h, L, false);
         } else {
             const int received = miss<RECORDS>(P, r, L);
             if (received >= 0) {
                 L.a += C_CAPTURED;
-                if (P.flags & RTS_OUT_BINS) accumulate_bin(P, r, received);
+                if (P.flags & RTS_OUT_BINS) accumulate_bin<TABLES>(P, r, received);
             }
         }
     }

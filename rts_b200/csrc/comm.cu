@@ -106,15 +106,23 @@ __global__ void __launch_bounds__(256) k_xchg_reduce(double *__restrict__ sums, 
     const unsigned long long half = (seq & 1ull) * half_words;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_sum + n_bins;
          i += (unsigned long long)gridDim.x * blockDim.x) {
+        // all ranks' words first — independent loads, in flight together over NVLink (summing as they arrive would
+        // serialise eight ~1.5 us round trips) — then the reduction in rank order: identical bits on every GPU
+        unsigned long long v[RTS_MAX_WORLD];
+#pragma unroll
+        for (uint32_t q = 0; q < RTS_MAX_WORLD; q++)
+            if (q < world) v[q] = ld_relaxed_sys(reinterpret_cast<const unsigned long long *>(peers.block[q] + XCHG_HEADER_BYTES) + half + i);
         if (i < n_sum) {
             double acc = 0.0;
-            for (uint32_t q = 0; q < world; q++)   // rank order on every GPU: identical bits everywhere
-                acc += __longlong_as_double((long long)ld_relaxed_sys(reinterpret_cast<const unsigned long long *>(peers.block[q] + XCHG_HEADER_BYTES) + half + i));
+#pragma unroll
+            for (uint32_t q = 0; q < RTS_MAX_WORLD; q++)
+                if (q < world) acc += __longlong_as_double((long long)v[q]);
             sums[i] = acc;
         } else {
             unsigned long long m = ~0ull;
-            for (uint32_t q = 0; q < world; q++)
-                m = min(m, ld_relaxed_sys(reinterpret_cast<const unsigned long long *>(peers.block[q] + XCHG_HEADER_BYTES) + half + i));
+#pragma unroll
+            for (uint32_t q = 0; q < RTS_MAX_WORLD; q++)
+                if (q < world) m = min(m, v[q]);
             mins[i - n_sum] = m;
         }
     }

@@ -84,6 +84,10 @@ struct Counters {              // device-side, accumulated with atomics
 struct RxDev { double cx, cy, cz, radius, min_theta, max_theta, min_phi, max_phi; };
 
 // Everything a bounce-wave kernel needs, passed by value.
+// device mirrors of rts_table2d / rts_antenna (values: device pointer)
+struct DevTable { uint32_t n_az, n_el; double az0, az_step, el0, el_step; const double *values; };
+struct DevAntenna { DevTable gain; double bore_az, bore_el, rate_az, rate_el; double pos[3]; };
+
 struct WaveParams {
     // scene
     const BvhNode *nodes;
@@ -191,6 +195,12 @@ struct WaveParams {
     // kernel (which returns at once for the others when split_on is set).
     unsigned long long *trav_hits;
     uint32_t split_on, split_below, split_keep_all;
+    // tabulated callbacks (RTS_TABLES): per-target RCS tables (nullptr: scalar t_rcs at capture), antennas (nullptr: scalar
+    // gains inside wl2gain); keep_first: the first hit point travels with the ray state (gains need it, like records mode)
+    const DevTable *rcs_tab;
+    const DevAntenna *ant_tx, *ant_rx;
+    uint32_t keep_first;
+    double wl2, gain_tx_scalar, gain_rx_scalar;   // Wl^2 (ray_tracer.cpp:1247) and the scalar gains, apart, when antennas are in use
     // follow.cuh: per-warp scratch stacks of the warp-cooperative traversal that finishes straggler rays
     // (RTS_COOP_STACK entries per resident warp of k_primary_follow)
     int *coop_stacks;
@@ -340,7 +350,8 @@ struct rts_engine {
     unsigned *d_target_box = nullptr;
     BvhNode *d_mover_nodes = nullptr;
     uint32_t *d_todo = nullptr;
-    int *d_coop_stacks = nullptr;      // follow.cuh: RTS_COOP_STACK ints per resident warp of k_primary_follow
+    char *d_coop_stacks = nullptr;     // follow.cuh: COOP_WARP_BYTES of scratch per resident warp of the wave kernels
+    int coop_ctas = 0;
     uint64_t todo_alloc = 0;
     unsigned long long *d_trav_hits = nullptr;   // split.cuh: one hit word per queue slot
     uint64_t trav_alloc = 0;
@@ -379,6 +390,13 @@ struct rts_engine {
     uint64_t pulse_primary = 0, pulse_waves = 0;
 
     Comm comm;
+    // tabulated callbacks (rts_set_rcs_tables / rts_set_antennas)
+    DevTable *d_rcs_tab = nullptr;
+    double *d_rcs_values = nullptr;
+    uint32_t n_rcs_tab = 0;
+    DevAntenna *d_ant_tx = nullptr, *d_ant_rx = nullptr;
+    double *d_ant_values = nullptr;
+    uint32_t n_ant_rx = 0;
 
     // last pulse
     bool have_pulse = false, bins_finalised = false;

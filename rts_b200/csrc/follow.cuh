@@ -123,7 +123,7 @@ constexpr size_t COOP_WARP_BYTES = sizeof(int) * RTS_COOP_STACK + sizeof(Ray) * 
 // The rays of this warp that traverse() gave up on, parked in `slots` by their lanes: walked by the whole warp one after
 // the other, then shaded by their own lane.  Called with the warp converged.  Out of line: it runs for a few rays per
 // launch and must not cost the loop around it any registers.
-template <bool RECORDS>
+template <bool RECORDS, bool TABLES>
 __device__ __noinline__ void finish_stragglers(const WaveParams &P, int *stk, const Ray *slots, bool pending, Local &L, unsigned &followed)
 {
     constexpr unsigned FULL = 0xffffffffu;
@@ -137,12 +137,12 @@ __device__ __noinline__ void finish_stragglers(const WaveParams &P, int *stk, co
             followed++;
             if (h.pos >= 0) {
                 L.a += C_HIT;
-                shade<RECORDS>(P, r, h, L, false);
+                shade<RECORDS, TABLES>(P, r, h, L, false);
             } else {
                 const int received = miss<RECORDS>(P, r, L);
                 if (received >= 0) {
                     L.a += C_CAPTURED;
-                    if (P.flags & RTS_OUT_BINS) accumulate_bin(P, r, received);
+                    if (P.flags & RTS_OUT_BINS) accumulate_bin<TABLES>(P, r, received);
                 }
             }
         }
@@ -150,7 +150,7 @@ __device__ __noinline__ void finish_stragglers(const WaveParams &P, int *stk, co
     }
 }
 
-template <bool RECORDS>
+template <bool RECORDS, bool TABLES = false>
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_WAVE_MIN_BLOCKS) k_primary_follow(const __grid_constant__ WaveParams P)
 {
     if (!raster_on(P)) return;
@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_WAVE_MIN_BLOCKS) k_primary
         // the warp is converged here: stragglers of the last round first
         if (__any_sync(FULL, pending)) {
             char *scratch = reinterpret_cast<char *>(P.coop_stacks) + COOP_WARP_BYTES * ((size_t)blockIdx.x * (RTS_WAVE_BLOCK / 32) + (threadIdx.x >> 5));
-            finish_stragglers<RECORDS>(P, reinterpret_cast<int *>(scratch), reinterpret_cast<const Ray *>(scratch + sizeof(int) * RTS_COOP_STACK), pending, L, followed);
+            finish_stragglers<RECORDS, TABLES>(P, reinterpret_cast<int *>(scratch), reinterpret_cast<const Ray *>(scratch + sizeof(int) * RTS_COOP_STACK), pending, L, followed);
             pending = false;
         }
         unsigned base = 0;
@@ -191,12 +191,12 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_WAVE_MIN_BLOCKS) k_primary
             h.pos = P.hits_resolved ? (int)((uint32_t)hit & 0x7fffffffu) : (int)__ldg(P.leaf_of_tri + (uint32_t)hit);
             h.t = __uint_as_float((unsigned)(hit >> 32)); h.id = 0;   // shade() takes the id from the record
             L.a += C_HIT;
-            follow = shade<RECORDS>(P, r, h, L, true);
+            follow = shade<RECORDS, TABLES>(P, r, h, L, true);
         } else {
             const int received = miss<RECORDS>(P, r, L);
             if (received >= 0) {
                 L.a += C_CAPTURED;
-                if (P.flags & RTS_OUT_BINS) accumulate_bin(P, r, received);
+                if (P.flags & RTS_OUT_BINS) accumulate_bin<TABLES>(P, r, received);
             }
         }
         if (!follow) continue;
@@ -213,12 +213,12 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_WAVE_MIN_BLOCKS) k_primary
         followed++;
         if (h.pos >= 0) {
             L.a += C_HIT;
-            shade<RECORDS>(P, r, h, L, false);
+            shade<RECORDS, TABLES>(P, r, h, L, false);
         } else {
             const int received = miss<RECORDS>(P, r, L);
             if (received >= 0) {
                 L.a += C_CAPTURED;
-                if (P.flags & RTS_OUT_BINS) accumulate_bin(P, r, received);
+                if (P.flags & RTS_OUT_BINS) accumulate_bin<TABLES>(P, r, received);
             }
         }
     }

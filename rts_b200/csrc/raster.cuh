@@ -313,7 +313,7 @@ __global__ void k_raster_resolve(const __grid_constant__ WaveParams P)
 }
 
 // Pass 3b: the primary wave without traversal — the closest hit comes from the hit buffer.
-template <bool RECORDS>
+template <bool RECORDS, bool TABLES = false>
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_primary_shade(const __grid_constant__ WaveParams P)
 {
     if (!raster_on(P)) return;
@@ -349,12 +349,12 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_primar
             h.pos = P.hits_resolved ? (int)((uint32_t)hit & 0x7fffffffu) : (int)P.leaf_of_tri[(uint32_t)hit];
             h.t = __uint_as_float((unsigned)(hit >> 32)); h.id = 0;   // shade() takes the id from the record
             L.a += C_HIT;
-            shade<RECORDS>(P, r, h, L, false, (P.hits_resolved && ((uint32_t)hit & 0x80000000u)) ? M_COH : 0u);
+            shade<RECORDS, TABLES>(P, r, h, L, false, (P.hits_resolved && ((uint32_t)hit & 0x80000000u)) ? M_COH : 0u);
         } else {
             const int received = miss<RECORDS>(P, r, L);
             if (received >= 0) {
                 L.a += C_CAPTURED;
-                if (P.flags & RTS_OUT_BINS) accumulate_bin(P, r, received);
+                if (P.flags & RTS_OUT_BINS) accumulate_bin<TABLES>(P, r, received);
             }
         }
         rel = nrel;

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_shade_
         Ray r;
         load_ray_geom(P.in, idx, r);
         r.meta &= ~M_COH;
-        load_ray_rest(P.in, idx, r, RECORDS, P.rMax != 0);
+        load_ray_rest(P.in, idx, r, RECORDS || P.keep_first != 0, P.rMax != 0);
         if (word != TRAV_MISS) {
             HitRec h;
             h.pos = (int)(uint32_t)word; h.t = __uint_as_float((unsigned)(word >> 32)); h.id = 0;

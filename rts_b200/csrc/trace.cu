@@ -87,7 +87,7 @@ __device__ __forceinline__ void push_ray(const WaveParams &P, const Ray &r, unsi
     if (g.thread_rank() == 0) base = atomicAdd(P.out_count, (unsigned long long)g.size());
     base = g.shfl(base, 0);
     const unsigned long long i = base + g.thread_rank();
-    if (i < P.out_capacity) store_ray(P.out, i, r, (P.flags & RTS_OUT_RECORDS) != 0, P.rMax != 0);
+    if (i < P.out_capacity) store_ray(P.out, i, r, (P.flags & RTS_OUT_RECORDS) != 0 || P.keep_first != 0, P.rMax != 0);
     else overflow++;
 }
 
@@ -99,7 +99,7 @@ __device__ __forceinline__ void push_ray_back(const WaveParams &P, const Ray &r,
     if (g.thread_rank() == 0) base = atomicAdd(P.out_back, (unsigned long long)g.size());
     base = g.shfl(base, 0);
     const unsigned long long i = base + g.thread_rank();
-    if (i < P.out_capacity) store_ray(P.out, P.out_capacity - 1ull - i, r, (P.flags & RTS_OUT_RECORDS) != 0, P.rMax != 0);
+    if (i < P.out_capacity) store_ray(P.out, P.out_capacity - 1ull - i, r, (P.flags & RTS_OUT_RECORDS) != 0 || P.keep_first != 0, P.rMax != 0);
     else overflow++;
 }
 // Slot of entry i of the incoming wave (see WaveParams::in_back).
@@ -456,10 +456,43 @@ struct Local {
 constexpr unsigned long long C_HIT = 1ull, C_SHADED = 1ull << 21, C_CAPTURED = 1ull << 42;
 constexpr unsigned long long C_MULTI = 1ull, C_EDGE = 1ull << 21, C_REFRACTED = 1ull << 42;
 
+// Bilinear sample of a tabulated callback (rts_table2d), arguments clamped to the grid.
+__device__ __forceinline__ double table_lookup(const DevTable &t, double az, double el)
+{
+    double u = (az - t.az0) / t.az_step, v = (el - t.el0) / t.el_step;
+    u = fmin(fmax(u, 0.0), (double)(t.n_az - 1u));
+    v = fmin(fmax(v, 0.0), (double)(t.n_el - 1u));
+    const uint32_t i0 = min((uint32_t)u, t.n_az - 1u), j0 = min((uint32_t)v, t.n_el - 1u);
+    const uint32_t i1 = min(i0 + 1u, t.n_az - 1u), j1 = min(j0 + 1u, t.n_el - 1u);
+    const double f = u - (double)i0, g = v - (double)j0;
+    const double v00 = t.values[(size_t)i0 * t.n_el + j0], v01 = t.values[(size_t)i0 * t.n_el + j1];
+    const double v10 = t.values[(size_t)i1 * t.n_el + j0], v11 = t.values[(size_t)i1 * t.n_el + j1];
+    return (v00 * (1 - f) + v10 * f) * (1 - g) + (v01 * (1 - f) + v11 * f) * g;
+}
+// SVec3(Vec3) of the host simulator: azimuth = atan2(y, x), elevation = asin(z / length); a zero vector keeps (0, 0)
+__device__ __forceinline__ void svec3_angles(double x, double y, double z, double &az, double &el)
+{
+    const double len = sqrt(x * x + y * y + z * z);
+    az = 0; el = 0;
+    if (len != 0) { el = asin(z / len); az = atan2(y, x); }
+}
+
+// Tabulated Target::GetRCS for one hop (RTS_TABLES): the summed in/out angles of normal_shader.cu:320-326, then the
+// target's table (or its scalar).  Out of line: pulses without tables must not pay registers for it.
+__device__ __noinline__ double rcs_hop_factor(const WaveParams &P, uint32_t targ, const d3 k0, const d3 k1)
+{
+    const DevTable tab = P.rcs_tab[targ];
+    if (!tab.n_az) return P.t_rcs ? P.t_rcs[targ] : 1.0;
+    double a0, e0, a1, e1;
+    cart_to_sph(k0, a0, e0);
+    cart_to_sph(mk3(-k1.x, -k1.y, -k1.z), a1, e1);
+    return table_lookup(tab, a0 + a1, e0 + e1);
+}
+
 // normal_shader.cu:128-340
 // Returns true when `chain` is set and the reflected ray is to be followed at once by the caller (r holds it)
 // instead of being queued for the next wave.
-template <bool RECORDS>
+template <bool RECORDS, bool TABLES = false>
 __device__ __forceinline__ bool shade(const WaveParams &P, Ray &r, const HitRec &h, Local &L, bool chain, uint32_t coh = 0)
 {
     const uint32_t dMax = P.dMax, rMax = P.rMax;
@@ -550,7 +583,10 @@ __device__ __forceinline__ bool shade(const WaveParams &P, Ray &r, const HitRec 
     // and the RCS angles.  For a target at rest V.(k1-k0) is exactly +0 and doppler += 0 leaves the value
     // unchanged, so the two fp64 normalisations are skipped unless the angles are wanted.
     const bool want_rcs = RECORDS && !(P.flags & RTS_NO_RCS_ANGLES);
-    const bool need_k = want_rcs || (V.x != 0.0) || (V.y != 0.0) || (V.z != 0.0);
+    // tabulated Target::GetRCS (RTS_TABLES, fused bins): the factor of this hop is folded into the power where the reference
+    // writes the hop's angles (:320-326) — the host loop of ray_tracer.cpp:1221-1231 multiplies the very same factors later
+    const bool fold_rcs = TABLES && !RECORDS && P.rcs_tab != nullptr;   // TABLES: separate instantiations, so that pulses without tables pay nothing
+    const bool need_k = want_rcs || fold_rcs || (V.x != 0.0) || (V.y != 0.0) || (V.z != 0.0);
 
     // :191-194
     const double pr_n0 = r.n1; // prd_refr.refrIndex.x = prd_refr.refrIndex.y
@@ -627,6 +663,7 @@ __device__ __forceinline__ bool shade(const WaveParams &P, Ray &r, const HitRec 
                 P.rcs_angle[(row * P.D + x) * 2 + 1] = e0 + e1;
             }
         }
+        if (fold_rcs && ((reflDepth - 1) + refrDepth) < P.D) r.pw *= rcs_hop_factor(P, targ, k0, k1);
         }
         r.meta = m_make(reflDepth, refrDepth, slot, end, false, col + 1) | coh;
         if (chain) return true;
@@ -741,14 +778,38 @@ __device__ __forceinline__ int miss(const WaveParams &P, Ray &r, Local &L)
     return received;
 }
 
+// Wl^2 * Gt * Gr of a captured ray with tabulated antenna patterns (RTS_TABLES):
+// Gt = trans->GetGain(transvec, GetRotation(time_t)), Gr = recv->GetGain(recvvec, GetRotation(delay + time_t))
+// (ray_tracer.cpp:1201-1235, 1247); an antenna without a table keeps its scalar gain.  Out of line like rcs_hop_factor.
+__device__ __noinline__ double antenna_factor(const WaveParams &P, const Ray &r, int received)
+{
+    double Gt = P.gain_tx_scalar, Gr = P.gain_rx_scalar;
+    const bool direct = (m_refl(r.meta) == 0) && (m_refr(r.meta) == 0);
+    const DevAntenna rxa = P.ant_rx[received];
+    double az, el;
+    if (P.ant_tx && P.ant_tx->gain.n_az) {
+        if (direct) svec3_angles(P.origin[0] - rxa.pos[0], P.origin[1] - rxa.pos[1], P.origin[2] - rxa.pos[2], az, el);   // :1206
+        else svec3_angles(r.fx - P.origin[0], r.fy - P.origin[1], r.fz - P.origin[2], az, el);                              // :1210
+        Gt = table_lookup(P.ant_tx->gain, az - P.ant_tx->bore_az, el - P.ant_tx->bore_el);
+    }
+    if (rxa.gain.n_az) {
+        if (direct) svec3_angles(rxa.pos[0] - P.origin[0], rxa.pos[1] - P.origin[1], rxa.pos[2] - P.origin[2], az, el);   // :1207
+        else svec3_angles(r.ox - rxa.pos[0], r.oy - rxa.pos[1], r.oz - rxa.pos[2], az, el);                                 // :1211
+        const double d = r.len / P.cspeed;                                                                                  // :1218
+        Gr = table_lookup(rxa.gain, az - (rxa.bore_az + rxa.rate_az * d), el - (rxa.bore_el + rxa.rate_el * d));
+    }
+    return P.wl2 * Gt * Gr;
+}
+
 // Fused host post-process (per-target scalar RCS, constant Gt/Gr; ray_tracer.cpp:1219-1253) and the per-ray terms of
 // myKernel1 (aggregation.cu:59-69), summed into the (receiver, path) bin.  Lanes of a converged
 // group that hit the same bin are reduced with shuffles first, so one group issues one set of
 // fp64 atomics per distinct bin.
+template <bool TABLES = false>
 __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r, int received)
 {
     double pw = r.pw;
-    if (P.t_rcs) { // ray_tracer.cpp:1219-1230: one factor per path-row entry >= 0, in column order
+    if (P.t_rcs && !(TABLES && P.rcs_tab)) { // ray_tracer.cpp:1219-1230: one factor per path-row entry >= 0, in column order
         unsigned long long k = r.key;
         for (uint32_t c = 0; c < P.D; c++) {
             const uint32_t digit = (uint32_t)(k % P.B);
@@ -756,7 +817,7 @@ __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r
             if (digit) pw *= P.t_rcs[digit - 1];
         }
     }
-    pw *= P.wl2gain;
+    pw *= (TABLES && P.ant_rx) ? antenna_factor(P, r, received) : P.wl2gain;
     const double Vr = r.dop / 2;
     const double dopHz = P.carrier * (((1 + Vr / P.cspeed) / (1 - Vr / P.cspeed)) - 1);
     const double delay = (r.len) / P.cspeed;
@@ -806,7 +867,7 @@ __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r
 #include "split.cuh"
 #include "follow.cuh"
 
-template <bool PRIMARY, bool RECORDS, bool COUNT, bool CHAIN>
+template <bool PRIMARY, bool RECORDS, bool COUNT, bool CHAIN, bool TABLES = false>
 __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_PRIMARY : RTS_WAVE_MIN_BLOCKS) k_wave(const __grid_constant__ WaveParams P)
 {
     if (PRIMARY && P.raster_ctl && raster_on(P)) return;   // the projected primary wave (raster.cuh) did this batch
@@ -868,6 +929,8 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
             unsigned nn = 0, nt = 0;
             // SCENE_EPS == SCENE_EPS_R (ray_tracer.h:9-10).  Later waves start on a triangle, i.e. inside the frame of the
             // quantised nodes; a primary ray starts at the transmitter, wherever that is: fp32 nodes
+            // (the cooperative finish of straggler rays, follow.cuh, was tried here too: on the ship scene a large share of
+            // the rays inside the closed dielectric hull exceeds any small budget, and walking them one per warp cost 23 %)
             if (PRIMARY || !RTS_QNODES) traverse<COUNT>(P, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz), SCENE_EPS, h, nn, nt, L.overflow);
             else traverse_q<COUNT>(P, mk3(r.ox, r.oy, r.oz), mk3(r.dx, r.dy, r.dz), SCENE_EPS, h, nn, nt, L.overflow);
             if (COUNT) { L.nodes += nn; L.tris += nt; }
@@ -875,17 +938,17 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
                 r.len = 0; r.pw = 0; r.dop = 0; r.fx = 0; r.fy = 0; r.fz = 0; r.n0 = 1; r.n1 = 1;
                 r.key = 0; r.ray = (uint32_t)rayIndex;
             } else if (first) {
-                load_ray_rest(P.in, idx, r, RECORDS, P.rMax != 0);
+                load_ray_rest(P.in, idx, r, RECORDS || P.keep_first != 0, P.rMax != 0);
             }
             bool follow = false;
             if (h.pos >= 0) {
                 L.a += C_HIT;
-                follow = shade<RECORDS>(P, r, h, L, chain);
+                follow = shade<RECORDS, TABLES>(P, r, h, L, chain);
             } else {
                 const int received = miss<RECORDS>(P, r, L);
                 if (received >= 0) {
                     L.a += C_CAPTURED;
-                    if (P.flags & RTS_OUT_BINS) accumulate_bin(P, r, received);
+                    if (P.flags & RTS_OUT_BINS) accumulate_bin<TABLES>(P, r, received);
                 }
             }
             if (PRIMARY || !CHAIN || !follow) break;
@@ -938,6 +1001,10 @@ int trace_wave_grid(rts_engine *e)
 template <bool PRIMARY, bool CHAIN>
 static void launch_variant(int grid, cudaStream_t st, const WaveParams &p, bool records, bool count)
 {
+    if (p.rcs_tab || p.ant_rx) {   // RTS_TABLES pulses (fused bins, no records, no node counting): their own instantiation
+        k_wave<PRIMARY, false, false, CHAIN, true><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        return;
+    }
     if (records) {
         if (count) k_wave<PRIMARY, true, true, CHAIN><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
         else k_wave<PRIMARY, true, false, CHAIN><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
@@ -947,10 +1014,21 @@ static void launch_variant(int grid, cudaStream_t st, const WaveParams &p, bool 
     }
 }
 
-int trace_launch_wave(rts_engine *e, const WaveParams &p, bool primary, bool records)
+// per-warp scratch of the cooperative straggler traversal, for kernels of up to `ctas` CTAs
+static int ensure_coop(rts_engine *e, int ctas)
+{
+    if (e->coop_ctas >= ctas) return RTS_OK;
+    if (e->d_coop_stacks) { cudaFree(e->d_coop_stacks); e->d_coop_stacks = nullptr; e->coop_ctas = 0; }
+    RTS_CUDA(cudaMalloc(&e->d_coop_stacks, COOP_WARP_BYTES * (size_t)ctas * (RTS_WAVE_BLOCK / 32)));
+    e->coop_ctas = ctas;
+    return RTS_OK;
+}
+
+int trace_launch_wave(rts_engine *e, const WaveParams &p_in, bool primary, bool records)
 {
     trace_wave_grid(e);
     const int grid = primary ? e->wave_grid_primary : e->wave_grid;   // persistent: resident CTAs per SM x SMs
+    const WaveParams &p = p_in;
     const bool count = (p.flags & RTS_COUNT_NODES) != 0;
     if (primary) launch_variant<true, false>(grid, e->stream, p, records, count);
     else if (p.wave_index >= (e->followed ? 1u : 2u) && p.chain_below) launch_variant<false, true>(grid, e->stream, p, records, count);
@@ -1115,14 +1193,20 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_primary_follow<false>, RTS_WAVE_BLOCK, 0);
             e->follow_grid = e->num_sms * (occ > 0 ? occ : 1);
         }
-        if (!e->d_coop_stacks) RTS_CUDA(cudaMalloc(&e->d_coop_stacks, COOP_WARP_BYTES * (size_t)e->follow_grid * (RTS_WAVE_BLOCK / 32)));
-        p.coop_stacks = e->d_coop_stacks;
+        trace_wave_grid(e);
+        {
+            int rc = ensure_coop(e, std::max(e->wave_grid, e->follow_grid));
+            if (rc) return rc;
+        }
+        p.coop_stacks = reinterpret_cast<int *>(e->d_coop_stacks);
         const bool timed = single_batch && e->follow_ev[0];   // this kernel alone, apart from the directions / footprint passes of the wave (rts_get_follow_profile)
         if (timed) cudaEventRecord(e->follow_ev[0], st);
-        if (records) k_primary_follow<true><<<e->follow_grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        if (p.rcs_tab || p.ant_rx) k_primary_follow<false, true><<<e->follow_grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        else if (records) k_primary_follow<true><<<e->follow_grid, RTS_WAVE_BLOCK, 0, st>>>(p);
         else k_primary_follow<false><<<e->follow_grid, RTS_WAVE_BLOCK, 0, st>>>(p);
         if (timed) { cudaEventRecord(e->follow_ev[1], st); e->follow_timed = true; }
-    } else if (records) k_primary_shade<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
+    } else if (p.rcs_tab || p.ant_rx) k_primary_shade<false, true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
+    else if (records) k_primary_shade<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     else k_primary_shade<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     RTS_CUDA(cudaGetLastError());
     e->launches += 1;
@@ -1163,7 +1247,8 @@ int trace_launch_kept(rts_engine *e, WaveParams &p, bool records)
         k_wave1_fill<<<e->wave_grid, RTS_WAVE_BLOCK, 0, st>>>(p);
         e->launches++;
     }
-    if (records) k_wave1_kept<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
+    if (p.rcs_tab || p.ant_rx) k_wave1_kept<false, true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
+    else if (records) k_wave1_kept<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     else k_wave1_kept<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
     e->launches++;
     RTS_CUDA(cudaGetLastError());

@@ -11,7 +11,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from .abi import (BIN_DTYPE, RAY_RECORD, RESPONSE_DTYPE, CPulse, CScene, PulseSpec, RtsBin, RtsPulse, RtsResponse, RtsRxDesc,
+from .abi import (Antenna, RtsAntenna, RtsTable2d, Table2d, BIN_DTYPE, RAY_RECORD, RESPONSE_DTYPE, CPulse, CScene, PulseSpec, RtsBin, RtsPulse, RtsResponse, RtsRxDesc,
                   RtsRxSphere, RtsStats, RtsTargetMesh, Target)
 
 RTS_OUT_BINS = 1
@@ -21,6 +21,7 @@ RTS_NO_FINALISE = 8
 RTS_NO_RCS_ANGLES = 16
 RTS_ASYNC = 32
 RTS_NO_REUSE = 64
+RTS_TABLES = 128
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RTS_B200_LIB", os.path.join(_HERE, "librts_b200.so"))   # override: tuning builds only
@@ -51,7 +52,7 @@ EXPORTS = [
     "rts_rx_sphere_from_desc", "rts_result_sizes", "rts_rect_mesh", "rts_sphere_mesh", "rts_file_mesh",
     "rts_rotation_matrix", "rts_scene_set_targets", "rts_scene_set_poses", "rts_scene_rebuild", "rts_scene_bvh_info",
     "rts_scene_get_world_vertices", "rts_scene_get_tri_bounds", "rts_scene_check_bvh", "rts_trace_pulse",
-    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_get_split_profile", "rts_get_follow_profile", "rts_kernel_launches", "rts_probe_read_bandwidth", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_get_records_shard", "rts_get_received", "rts_bins_device", "rts_bins_compact_device", "rts_bins_load_compact", "rts_finalise_bins", "rts_aggregate", "rts_comm_create", "rts_comm_ipc_handle", "rts_comm_local_ptr", "rts_comm_connect_ipc", "rts_comm_connect_ptrs", "rts_comm_allreduce_bins", "rts_comm_stats", "rts_comm_destroy",
+    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_get_split_profile", "rts_get_follow_profile", "rts_kernel_launches", "rts_probe_read_bandwidth", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_get_records_shard", "rts_get_received", "rts_bins_device", "rts_bins_compact_device", "rts_bins_load_compact", "rts_finalise_bins", "rts_aggregate", "rts_set_rcs_tables", "rts_set_antennas", "rts_comm_create", "rts_comm_ipc_handle", "rts_comm_local_ptr", "rts_comm_connect_ipc", "rts_comm_connect_ptrs", "rts_comm_allreduce_bins", "rts_comm_stats", "rts_comm_destroy",
 ]
 
 _lib = None
@@ -98,6 +99,8 @@ def load() -> C.CDLL:
     lib.rts_get_split_profile.argtypes = [vp, P(C.c_float)]
     lib.rts_get_follow_profile.argtypes = [vp, P(C.c_float)]
     lib.rts_comm_create.argtypes = [vp, u32, u32, u64]
+    lib.rts_set_rcs_tables.argtypes = [vp, P(RtsTable2d), u32]
+    lib.rts_set_antennas.argtypes = [vp, P(RtsAntenna), P(RtsAntenna), u32]
     lib.rts_comm_ipc_handle.argtypes = [vp, vp]
     lib.rts_comm_local_ptr.argtypes = [vp, P(vp)]
     lib.rts_comm_connect_ipc.argtypes = [vp, vp]
@@ -377,6 +380,25 @@ class Engine:
 
     def finalise_bins(self):
         _check(self._lib.rts_finalise_bins(self._h))
+
+    # ---- tabulated callbacks (include/rts_b200.h: rts_set_rcs_tables / rts_set_antennas; used by pulses traced with RTS_TABLES)
+    def set_rcs_tables(self, tables):
+        """tables: one Table2d (or None: scalar RCS) per target; None / [] clears."""
+        if not tables:
+            _check(self._lib.rts_set_rcs_tables(self._h, None, 0))
+            return
+        arr = (RtsTable2d * len(tables))(*[t.c() if t is not None else RtsTable2d() for t in tables])
+        _check(self._lib.rts_set_rcs_tables(self._h, arr, len(tables)))
+
+    def set_antennas(self, tx, rx):
+        """tx: Antenna or None; rx: list of Antenna (one per receiver) or None / [] to clear."""
+        if not rx:
+            txc = tx.c() if tx is not None else None      # a transmitter antenna alone is refused by the library
+            _check(self._lib.rts_set_antennas(self._h, C.byref(txc) if txc is not None else None, None, 0))
+            return
+        arr = (RtsAntenna * len(rx))(*[a.c() for a in rx])
+        txc = tx.c() if tx is not None else None
+        _check(self._lib.rts_set_antennas(self._h, C.byref(txc) if txc is not None else None, arr, len(rx)))
 
     # ---- peer-memory bin exchange (include/rts_b200.h: rts_comm_*) ----
     def comm_create(self, rank: int, world: int, max_bins: int):
