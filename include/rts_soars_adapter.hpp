@@ -21,6 +21,12 @@
 //   fused            Options::fused: RCS and gains are sampled once per pulse as scalars and folded on the device
 //                    (rts_pulse.targ_rcs / gain_tx / gain_rx); responses come from rts_get_responses.  Exact only
 //                    when the callbacks do not depend on the angles.
+//   tabulated        Options::tabulated: Target::GetRCS and the GetGain patterns are sampled on regular grids
+//                    (Options::table_az x table_el) — once per pulse, a few hundred thousand callback calls instead of one
+//                    set per received ray — and evaluated on the device by bilinear interpolation per hop / per captured
+//                    ray (rts_set_rcs_tables / rts_set_antennas, RTS_TABLES): no per-ray data crosses to the host.  Exact
+//                    for callbacks that are themselves tables on that grid; otherwise within the interpolation error
+//                    (h^2/8 * |f''|: 1e-5 for smooth patterns at the default resolution).  Reflection-only pulses.
 #ifndef RTS_SOARS_ADAPTER_HPP
 #define RTS_SOARS_ADAPTER_HPP
 
@@ -38,6 +44,8 @@ namespace rts_b200 {
 struct Options {
     int device = 0;
     bool fused = false;     // fold scalar RCS / gains on the device instead of calling the callbacks per ray
+    bool tabulated = false; // sample the callbacks on grids and evaluate them on the device (angle-dependent, no per-ray D2H)
+    unsigned table_az = 1441, table_el = 721;   // samples over [-2pi, 2pi] x [-pi, pi]
     bool verbose = false;   // the reference's progress prints (ray_tracer.cpp:521, 1260, 1362)
 };
 
@@ -196,6 +204,62 @@ void RTS(typename S::World *world, unsigned int MaxThreads, unsigned int MaxBloc
             pl.n_rx = rxsize; pl.rx = rx.data();
             pl.n_targets = targsize; pl.targ_vel = vel.data();
             const double h_rayOrigin[3] = {trpos.x, trpos.y, trpos.z};
+
+            if (opt.tabulated) {
+                if (h_maxRefrDepth) throw Error("Options::tabulated: pulses with refraction need the exact path");
+                // the callbacks as tables: GetRCS over the summed in/out angles of dbuf_rcs_angle, GetGain over the look
+                // direction minus the boresight; the receiver's boresight drift from two GetRotation samples
+                const double PI = 3.14159265358979323846;
+                const unsigned na = opt.table_az, ne = opt.table_el;
+                const double az0 = -2 * PI, azs = 4 * PI / (na - 1), el0 = -PI, els = 2 * PI / (ne - 1);
+                std::vector<std::vector<double>> rcs_vals(targsize, std::vector<double>((size_t)na * ne));
+                std::vector<rts_table2d> rcs_tab(targsize);
+                for (unsigned i = 0; i < targsize; i++) {
+                    for (unsigned a = 0; a < na; a++)
+                        for (unsigned b = 0; b < ne; b++) rcs_vals[i][(size_t)a * ne + b] = targ_arr[i]->GetRCS(az0 + a * azs, el0 + b * els, Wl);
+                    rcs_tab[i] = rts_table2d{na, ne, az0, azs, el0, els, rcs_vals[i].data()};
+                }
+                detail::check(rts_set_rcs_tables(eng, rcs_tab.data(), targsize), "rts_set_rcs_tables");
+                auto sample_gain = [&](auto *ant, const SVec3 &bore, std::vector<double> &vals) {
+                    vals.resize((size_t)na * ne);
+                    for (unsigned a = 0; a < na; a++)
+                        for (unsigned b = 0; b < ne; b++)
+                            vals[(size_t)a * ne + b] = ant->GetGain(SVec3(1, bore.azimuth + (az0 + a * azs), bore.elevation + (el0 + b * els)), bore, Wl);
+                    return rts_table2d{na, ne, az0, azs, el0, els, vals.data()};
+                };
+                std::vector<double> tx_vals;
+                std::vector<std::vector<double>> rx_vals(rxsize);
+                rts_antenna txa = {};
+                const SVec3 tx_bore = trans->GetRotation(time_t);
+                txa.gain = sample_gain(trans, tx_bore, tx_vals);
+                txa.bore_az = tx_bore.azimuth; txa.bore_el = tx_bore.elevation;
+                txa.position[0] = trpos.x; txa.position[1] = trpos.y; txa.position[2] = trpos.z;
+                std::vector<rts_antenna> rxa(rxsize);
+                for (unsigned j = 0; j < rxsize; j++) {
+                    const SVec3 b0 = recv_arr[j]->GetRotation(time_t), b1 = recv_arr[j]->GetRotation(time_t + sample_time);
+                    rxa[j] = rts_antenna{};
+                    rxa[j].gain = sample_gain(recv_arr[j], b0, rx_vals[j]);
+                    rxa[j].bore_az = b0.azimuth; rxa[j].bore_el = b0.elevation;
+                    rxa[j].rate_az = (b1.azimuth - b0.azimuth) / sample_time; rxa[j].rate_el = (b1.elevation - b0.elevation) / sample_time;
+                    const Vec3 rp = recv_arr[j]->GetPosition(0);
+                    rxa[j].position[0] = rp.x; rxa[j].position[1] = rp.y; rxa[j].position[2] = rp.z;
+                }
+                detail::check(rts_set_antennas(eng, &txa, rxa.data(), rxsize), "rts_set_antennas");
+                detail::check(rts_trace_pulse(eng, &pl, RTS_OUT_BINS | RTS_TABLES), "rts_trace_pulse");
+                uint32_t n = 0;
+                detail::check(rts_get_responses(eng, nullptr, 0, &n), "rts_get_responses");
+                std::vector<rts_response> resp(n ? n : 1);
+                detail::check(rts_get_responses(eng, resp.data(), n, &n), "rts_get_responses");
+                for (uint32_t u = 0; u < n; u++) {                                     // :1301-1320
+                    const rts_response &a = resp[u];
+                    typename S::InterpPoint point(a.power, time_t + a.delay, a.delay, a.doppler, a.phase,
+                                                  recv_arr[a.rx]->GetNoiseTemperature());
+                    auto *response = new typename S::Response(wave, trans);
+                    response->AddInterpPoint(point);
+                    recv_arr[a.rx]->AddResponse(response);
+                }
+                continue;
+            }
 
             if (opt.fused) {
                 // scalar callbacks folded on the device, responses straight from the bins

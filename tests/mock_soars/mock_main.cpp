@@ -1,6 +1,6 @@
 // mock_main.cpp — runs rts_b200::RTS<mock::Soars> on a small world and prints every response as one JSON line.
 // TEST INFRASTRUCTURE (tests/test_soars_adapter.py builds and runs it on the GPU box).
-//   mock_main <exact|fused> <N> <maxRefl> <maxRefr> <pulses>
+//   mock_main <exact|fused|tabulated> <N> <maxRefl> <maxRefr> <pulses>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -30,6 +30,7 @@ int main(int argc, char **argv)
 
     rts_b200::Options opt;
     opt.fused = fused;
+    opt.tabulated = argc > 1 && !strcmp(argv[1], "tabulated");
     try {
         rts_b200::RTS<Soars>(&world, 256, 1024, opt);
     } catch (const std::exception &e) {

@@ -148,3 +148,22 @@ def test_adapter_fused_mode_runs_and_matches_exact_paths_delays():
     for x, y in zip(ga, gb):
         assert x["rx"] == y["rx"] and math.isclose(x["delay"], y["delay"], rel_tol=1e-12) and math.isclose(x["phase"], y["phase"], rel_tol=1e-9)
         assert y["power"] > 0
+
+
+@pytest.mark.gpu
+def test_adapter_tabulated_mode_matches_the_exact_path():
+    """Options::tabulated: the mock's angle-dependent GetRCS / GetGain sampled on 1441 x 721 grids and evaluated on the device
+    (RTS_TABLES) — no per-ray data on the host — against the exact path that calls them per received ray.  The mock's
+    callbacks are smooth cosines, so the difference is the bilinear interpolation error: h^2/8 with h = 4pi/1440 -> 1e-5."""
+    exe = build_mock()
+    a = subprocess.run([exe, "exact", "24", "2", "0", "3"], capture_output=True, text=True, timeout=600)
+    b = subprocess.run([exe, "tabulated", "24", "2", "0", "3"], capture_output=True, text=True, timeout=600)
+    assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
+    ga = [json.loads(l) for l in a.stdout.splitlines() if l.startswith("{")]
+    gb = [json.loads(l) for l in b.stdout.splitlines() if l.startswith("{")]
+    assert len(ga) == len(gb) > 0
+    for x, y in zip(ga, gb):
+        assert x["rx"] == y["rx"] and x["noise"] == y["noise"]
+        assert math.isclose(x["delay"], y["delay"], rel_tol=1e-12) and math.isclose(x["phase"], y["phase"], rel_tol=1e-9)
+        assert math.isclose(x["doppler"], y["doppler"], rel_tol=1e-9, abs_tol=1e-9)
+        assert math.isclose(x["power"], y["power"], rel_tol=5e-5), (x, y)
