@@ -74,6 +74,7 @@ static int set_option(rts_engine *e, const char *name, long long v)
     else if (!strcmp(name, "split_below")) { if (v < 0 || v > (1ll << 30)) return rts_fail(RTS_ERR_ARG, "split_below out of range"); k.split_below = (uint32_t)v; }
     else if (!strcmp(name, "no_graph")) k.no_graph = v != 0;
     else if (!strcmp(name, "no_follow")) k.no_follow = v != 0;
+    else if (!strcmp(name, "no_smem_bins")) k.no_smem_bins = v != 0;
     else if (!strcmp(name, "hash_bins")) k.hash_bins = v != 0;
     else if (!strcmp(name, "hash_log2")) { if (v < 4 || v > 28) return rts_fail(RTS_ERR_ARG, "hash_log2 must be 4..28"); k.hash_log2 = (uint32_t)v; e->hash_ready = false; }
     else if (!strcmp(name, "batch")) { if (v != 0 && (v < 32 || v > (1ll << 24))) return rts_fail(RTS_ERR_ARG, "batch must be 0 or 32..2^24"); k.batch = v; }
@@ -113,7 +114,7 @@ extern "C" int rts_create(int device, rts_engine **out)
     e->stream = e->own_stream;
     // tuning / test switches: the environment is read here, once; afterwards only rts_set_option changes them
     for (const char *name : {"bvh", "leaf_max", "no_chain", "no_raster", "no_tiles", "one_ended_queue", "debug_raster", "no_static_hits",
-                             "no_kept_reflections", "no_split", "split_below", "no_graph", "no_follow", "batch", "hash_bins", "hash_log2"}) {
+                             "no_kept_reflections", "no_split", "split_below", "no_graph", "no_follow", "no_smem_bins", "batch", "hash_bins", "hash_log2"}) {
         std::string env = "RTS_";
         for (const char *c = name; *c; c++) env += (char)toupper(*c);
         if (const char *v = getenv(env.c_str())) {
@@ -582,6 +583,8 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
             RTS_CUDA(cudaMemsetAsync(e->d_bin_mins, 0x7f, sizeof(unsigned long long) * nb, st)); // empty = 0x7f7f…7f: positive as int64, so a signed MIN all-reduce keeps it last
         }
         P.bin_sums = e->d_bin_sums; P.bin_mins = e->d_bin_mins; P.n_bins = e->n_bins_dense;
+        // small dense tables are pre-reduced per CTA in shared memory (trace.cu: bins_smem_*); not in the split form of the waves
+        P.smem_bins = (!e->bins_hashed && e->n_bins_dense <= RTS_SMEM_BINS && e->knobs.no_split && !e->knobs.no_smem_bins) ? (uint32_t)e->n_bins_dense : 0u;
     } else {
         e->n_bins_dense = 0;
     }

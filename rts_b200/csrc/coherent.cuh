@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_wave1_
     const unsigned n_in = n_front + (P.in_back ? (unsigned)min(*P.in_back, P.out_capacity - n_front) : 0u);
     Local L = {0, 0, 0, 0, 0};
     unsigned served = 0;
+    bins_smem_init(P);
     const unsigned stride = gridDim.x * blockDim.x;
     for (unsigned entry = blockIdx.x * blockDim.x + threadIdx.x; entry < n_in; entry += stride) {
         const unsigned idx = queue_slot(P, entry, n_front);
@@ -208,6 +209,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_wave1_
             }
         }
     }
+    bins_smem_flush(P);
     unsigned long long *c = reinterpret_cast<unsigned long long *>(P.counters);
     const unsigned f[7] = {(unsigned)(L.a & 0x1fffff), (unsigned)((L.a >> 21) & 0x1fffff), (unsigned)(L.a >> 42),
                            (unsigned)(L.b & 0x1fffff), (unsigned)((L.b >> 21) & 0x1fffff), (unsigned)(L.b >> 42), L.overflow};

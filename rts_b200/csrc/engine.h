@@ -17,6 +17,7 @@
 #define RTS_WAVE_MIN_BLOCKS_PRIMARY 8   // same, primary wave (its state is smaller)
 #endif
 #define RTS_MAX_RX 64
+#define RTS_SMEM_BINS 256u        // dense bin tables up to this many bins are pre-reduced per CTA in shared memory (12 KB)
 #define RTS_COOP_STACK 4096u     // entries of a warp's shared stack in the cooperative traversal of a straggler ray (follow.cuh)
 #define RTS_MAX_WORLD 16          // GPUs of one node that can share a peer-memory bin exchange (comm.cu)
 #define RTS_EAGER_BINS 256u      // bins brought to pinned host memory right behind a pulse
@@ -195,6 +196,9 @@ struct WaveParams {
     // kernel (which returns at once for the others when split_on is set).
     unsigned long long *trav_hits;
     uint32_t split_on, split_below, split_keep_all;
+    // per-CTA shared-memory copy of a small dense bin table (trace.cu: bins_smem_*): > 0 = the number of bins cached,
+    // i.e. n_bins; the kernels are then launched with n_bins * 48 bytes of dynamic shared memory
+    uint32_t smem_bins;
     // tabulated callbacks (RTS_TABLES): per-target RCS tables (nullptr: scalar t_rcs at capture), antennas (nullptr: scalar
     // gains inside wl2gain); keep_first: the first hit point travels with the ray state (gains need it, like records mode)
     const DevTable *rcs_tab;
@@ -248,7 +252,7 @@ struct Comm {
 // Tuning / test switches: read from the environment once in rts_create, changed afterwards only through rts_set_option.
 struct Knobs {
     int no_chain = 0, no_raster = 0, no_tiles = 0, one_ended_queue = 0, debug_raster = 0, no_static_hits = 0,
-        no_kept_reflections = 0, no_split = 1, no_graph = 0, no_follow = 0;
+        no_kept_reflections = 0, no_split = 1, no_graph = 0, no_follow = 0, no_smem_bins = 0;
     long long batch = 0;           // 0 = default 2^24 primaries per batch
     int hash_bins = 0;             // 1: sparse (hashed) bins also where a dense table would fit
     uint32_t hash_log2 = 22;       // slots of the sparse bin table

@@ -164,6 +164,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_WAVE_MIN_BLOCKS) k_primary
     }
     unsigned *work = reinterpret_cast<unsigned *>(P.work_counter);
     unsigned followed = 0;
+    bins_smem_init(P);
     bool pending = false;            // this lane parked a straggler ray in its slot during the last round
     for (;;) {
         // the warp is converged here: stragglers of the last round first
@@ -222,6 +223,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_WAVE_MIN_BLOCKS) k_primary
             }
         }
     }
+    bins_smem_flush(P);
     {   // segments traced in place belong to this launch
         const unsigned x = __reduce_add_sync(FULL, followed);
         if (lane == 0 && x) {

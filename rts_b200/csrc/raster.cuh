@@ -326,6 +326,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_primar
     }
     // Every ray costs about the same here (no traversal), so the rays are dealt out statically; the next ray's
     // hit word and direction are fetched, and its triangle record prefetched, while the current one is shaded.
+    bins_smem_init(P);
     const unsigned stride = gridDim.x * blockDim.x;
     unsigned rel = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long hit_n = ~0ull;
@@ -359,6 +360,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_SHADE_MIN_BLOCKS) k_primar
         }
         rel = nrel;
     }
+    bins_smem_flush(P);
     unsigned long long *c = reinterpret_cast<unsigned long long *>(P.counters);
     const unsigned f[7] = {(unsigned)(L.a & 0x1fffff), (unsigned)((L.a >> 21) & 0x1fffff), (unsigned)(L.a >> 42),
                            (unsigned)(L.b & 0x1fffff), (unsigned)((L.b >> 21) & 0x1fffff), (unsigned)(L.b >> 42), L.overflow};

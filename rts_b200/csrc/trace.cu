@@ -805,6 +805,35 @@ __device__ __noinline__ double antenna_factor(const WaveParams &P, const Ray &r,
 // myKernel1 (aggregation.cu:59-69), summed into the (receiver, path) bin.  Lanes of a converged
 // group that hit the same bin are reduced with shuffles first, so one group issues one set of
 // fp64 atomics per distinct bin.
+// Shared-memory pre-reduction of the bins (the north star's "shared-memory pre-reduction ... before any global atomics"):
+// when the dense table is small (P.smem_bins = n_bins <= RTS_SMEM_BINS) every CTA accumulates into its own copy — the
+// lanes of a warp are combined with shuffles first (below), the warps of the CTA with shared-memory atomics — and adds
+// the copy to the global table once, when its warps have run out of rays: one set of global atomics per CTA and touched
+// bin instead of one per warp and capture.  Large tables (the benchmark's 5,832 bins) stay with global atomics: a copy
+// per CTA would take L1 away from the BVH nodes.
+extern __shared__ unsigned long long s_bins_raw[];
+__device__ __forceinline__ void bins_smem_init(const WaveParams &P)
+{
+    if (!P.smem_bins) return;
+    const unsigned n = P.smem_bins;
+    for (unsigned i = threadIdx.x; i < n * 6u; i += blockDim.x) s_bins_raw[i] = i < n * 5u ? 0ull : 0x7f7f7f7f7f7f7f7full;
+    __syncthreads();
+}
+__device__ __forceinline__ void bins_smem_flush(const WaveParams &P)
+{
+    if (!P.smem_bins) return;
+    __syncthreads();
+    const unsigned n = P.smem_bins;
+    const double *s_sum = reinterpret_cast<const double *>(s_bins_raw);
+    for (unsigned b = threadIdx.x; b < n; b += blockDim.x) {
+        if (s_sum[b * 5u] != 0.0) {                      // npath > 0: the bin was touched by this CTA
+#pragma unroll
+            for (int k = 0; k < 5; k++) atomicAdd(P.bin_sums + (size_t)b * 5 + k, s_sum[b * 5u + k]);
+            atomicMin(P.bin_mins + b, s_bins_raw[n * 5u + b]);
+        }
+    }
+}
+
 template <bool TABLES = false>
 __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r, int received)
 {
@@ -852,6 +881,16 @@ __device__ __forceinline__ void accumulate_bin(const WaveParams &P, const Ray &r
                 if (++probes > mask) { atomicAdd(&P.counters->overflow, 1ull); return; }   // table full: reported as RTS_ERR_CAPACITY
             }
         }
+        if (P.smem_bins) {          // this CTA's copy (dense table: at == bin < n_bins)
+            double *b = reinterpret_cast<double *>(s_bins_raw) + at * 5;
+            atomicAdd(b + 0, s_n);
+            atomicAdd(b + 1, s_a);
+            atomicAdd(b + 2, s_d);
+            atomicAdd(b + 3, s_p);
+            atomicAdd(b + 4, s_f);
+            atomicMin(s_bins_raw + (size_t)P.smem_bins * 5 + at, s_m);
+            return;
+        }
         double *b = P.bin_sums + at * 5;
         atomicAdd(b + 0, s_n);
         atomicAdd(b + 1, s_a);
@@ -880,6 +919,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
     if (!PRIMARY && P.split_on && n_in >= P.split_below && P.n_tris != 0) return;   // k_traverse + k_shade_wave did this wave (split.cuh)
     unsigned *work = reinterpret_cast<unsigned *>(P.work_counter);
     Local L = {0, 0, 0, 0, 0};
+    bins_smem_init(P);
     // Thin late waves (a few thousand rays whose latency, not throughput, sets the launch time) follow their
     // reflections in place instead of paying one more launch per bounce; refracted children are still queued.
     // A separate instantiation (CHAIN, used from the third wave on) so the bulk waves keep their register budget.
@@ -955,6 +995,7 @@ __global__ void __launch_bounds__(RTS_WAVE_BLOCK, PRIMARY ? RTS_WAVE_MIN_BLOCKS_
             chained++;
         }
     }
+    bins_smem_flush(P);
     if (!PRIMARY && CHAIN) {   // segments traced in place belong to this launch
         const unsigned x = __reduce_add_sync(0xffffffffu, chained);
         if (lane == 0 && x) {
@@ -998,19 +1039,21 @@ int trace_wave_grid(rts_engine *e)
     return e->wave_grid;
 }
 
+static size_t bins_smem_bytes(const WaveParams &p) { return (size_t)p.smem_bins * 48u; }
+
 template <bool PRIMARY, bool CHAIN>
 static void launch_variant(int grid, cudaStream_t st, const WaveParams &p, bool records, bool count)
 {
     if (p.rcs_tab || p.ant_rx) {   // RTS_TABLES pulses (fused bins, no records, no node counting): their own instantiation
-        k_wave<PRIMARY, false, false, CHAIN, true><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        k_wave<PRIMARY, false, false, CHAIN, true><<<grid, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
         return;
     }
     if (records) {
-        if (count) k_wave<PRIMARY, true, true, CHAIN><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
-        else k_wave<PRIMARY, true, false, CHAIN><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        if (count) k_wave<PRIMARY, true, true, CHAIN><<<grid, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
+        else k_wave<PRIMARY, true, false, CHAIN><<<grid, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
     } else {
-        if (count) k_wave<PRIMARY, false, true, CHAIN><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
-        else k_wave<PRIMARY, false, false, CHAIN><<<grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        if (count) k_wave<PRIMARY, false, true, CHAIN><<<grid, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
+        else k_wave<PRIMARY, false, false, CHAIN><<<grid, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
     }
 }
 
@@ -1062,8 +1105,8 @@ int trace_launch_split(rts_engine *e, WaveParams &p, bool records)
     if (p.flags & RTS_COUNT_NODES) k_traverse<true><<<e->trav_grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
     else k_traverse<false><<<e->trav_grid, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
     if (timed) cudaEventRecord(e->split_ev[1], e->stream);
-    if (records) k_shade_wave<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
-    else k_shade_wave<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, e->stream>>>(p);
+    if (records) k_shade_wave<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, bins_smem_bytes(p), e->stream>>>(p);
+    else k_shade_wave<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, bins_smem_bytes(p), e->stream>>>(p);
     if (timed) { cudaEventRecord(e->split_ev[2], e->stream); e->split_timed = true; }
     RTS_CUDA(cudaGetLastError());
     e->launches += 2;
@@ -1201,13 +1244,13 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
         p.coop_stacks = reinterpret_cast<int *>(e->d_coop_stacks);
         const bool timed = single_batch && e->follow_ev[0];   // this kernel alone, apart from the directions / footprint passes of the wave (rts_get_follow_profile)
         if (timed) cudaEventRecord(e->follow_ev[0], st);
-        if (p.rcs_tab || p.ant_rx) k_primary_follow<false, true><<<e->follow_grid, RTS_WAVE_BLOCK, 0, st>>>(p);
-        else if (records) k_primary_follow<true><<<e->follow_grid, RTS_WAVE_BLOCK, 0, st>>>(p);
-        else k_primary_follow<false><<<e->follow_grid, RTS_WAVE_BLOCK, 0, st>>>(p);
+        if (p.rcs_tab || p.ant_rx) k_primary_follow<false, true><<<e->follow_grid, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
+        else if (records) k_primary_follow<true><<<e->follow_grid, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
+        else k_primary_follow<false><<<e->follow_grid, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
         if (timed) { cudaEventRecord(e->follow_ev[1], st); e->follow_timed = true; }
-    } else if (p.rcs_tab || p.ant_rx) k_primary_shade<false, true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
-    else if (records) k_primary_shade<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
-    else k_primary_shade<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
+    } else if (p.rcs_tab || p.ant_rx) k_primary_shade<false, true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
+    else if (records) k_primary_shade<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
+    else k_primary_shade<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
     RTS_CUDA(cudaGetLastError());
     e->launches += 1;
     return RTS_OK;
@@ -1247,9 +1290,9 @@ int trace_launch_kept(rts_engine *e, WaveParams &p, bool records)
         k_wave1_fill<<<e->wave_grid, RTS_WAVE_BLOCK, 0, st>>>(p);
         e->launches++;
     }
-    if (p.rcs_tab || p.ant_rx) k_wave1_kept<false, true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
-    else if (records) k_wave1_kept<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
-    else k_wave1_kept<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, 0, st>>>(p);
+    if (p.rcs_tab || p.ant_rx) k_wave1_kept<false, true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
+    else if (records) k_wave1_kept<true><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
+    else k_wave1_kept<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
     e->launches++;
     RTS_CUDA(cudaGetLastError());
     return RTS_OK;
