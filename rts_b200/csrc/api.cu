@@ -70,7 +70,12 @@ static int set_option(rts_engine *e, const char *name, long long v)
     else if (!strcmp(name, "debug_raster")) k.debug_raster = v != 0;
     else if (!strcmp(name, "no_static_hits")) k.no_static_hits = v != 0;
     else if (!strcmp(name, "no_kept_reflections")) k.no_kept_reflections = v != 0;
-    else if (!strcmp(name, "no_split")) k.no_split = v != 0;
+    else if (!strcmp(name, "no_split")) {
+        const bool was = k.no_split != 0;
+        k.no_split = v != 0;
+        // the split form walks the quantised nodes, which are only maintained while it is enabled (bvh.cu: want_qnodes)
+        if (was && !k.no_split && e->scene_ready) { int rc = bvh_build(e); if (rc) return rc; }
+    }
     else if (!strcmp(name, "split_below")) { if (v < 0 || v > (1ll << 30)) return rts_fail(RTS_ERR_ARG, "split_below out of range"); k.split_below = (uint32_t)v; }
     else if (!strcmp(name, "no_graph")) k.no_graph = v != 0;
     else if (!strcmp(name, "no_follow")) k.no_follow = v != 0;

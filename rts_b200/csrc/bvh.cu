@@ -335,16 +335,16 @@ __global__ void k_pack(const int2 *__restrict__ children, const int2 *__restrict
             const double d = fmax((double)hi - (double)c0, (double)c0 - (double)lo);
             cc[c][a] = c0;
             hh[c][a] = nextafterf(__double2float_ru(d), CUDART_INF_F);
-            qn.w[3 * c + a] = q_planes(lo, hi, frame->lo[a], frame->ext[a], &q_over);
+            if (qnodes) qn.w[3 * c + a] = q_planes(lo, hi, frame->lo[a], frame->ext[a], &q_over);
         }
     }
-    qn.ref0 = refs[0]; qn.ref1 = refs[1];
-    {
+    if (qnodes) {      // the quantised copy of the node: only when a kernel that walks it is enabled (want_qnodes)
+        qn.ref0 = refs[0]; qn.ref1 = refs[1];
         uint4 *qd = reinterpret_cast<uint4 *>(qnodes + i);
         const uint4 *qs = reinterpret_cast<const uint4 *>(&qn);
         qd[0] = qs[0]; qd[1] = qs[1];
+        if (q_over && !only_on_overflow) atomicOr(&frame->overflow, 1u);
     }
-    if (q_over && !only_on_overflow) atomicOr(&frame->overflow, 1u);
     if (only_on_overflow) return;          // the fp32 nodes and the SAH sum are already in place
     nd.c0x = cc[0][0]; nd.c0y = cc[0][1]; nd.h0x = hh[0][0]; nd.h0y = hh[0][1];
     nd.c1x = cc[1][0]; nd.c1y = cc[1][1]; nd.h1x = hh[1][0]; nd.h1y = hh[1][1];
@@ -354,6 +354,10 @@ __global__ void k_pack(const int2 *__restrict__ children, const int2 *__restrict
     const float4 *s4 = reinterpret_cast<const float4 *>(&nd);
     dst[0] = s4[0]; dst[1] = s4[1]; dst[2] = s4[2]; dst[3] = s4[3];
 }
+
+// The quantised node copy (QNode) is maintained only when something walks it: the split form of the later waves
+// (k_traverse, option no_split = 0) or a tuning build with RTS_QNODES = 1.
+static bool want_qnodes(const rts_engine *e) { return RTS_QNODES != 0 || !e->knobs.no_split; }
 
 // ---- partial refit set-up (run when the set of moving targets changes) ----
 // Elements owned by a moving target, appended in arbitrary order (one atomic per warp).
@@ -575,11 +579,13 @@ static int fit_and_pack(rts_engine *e)
                                                       e->d_fit_flags, n, n, nullptr, nullptr, nullptr); e->launches++; }
         RTS_CUDA(cudaMemsetAsync(e->d_fit_flags, 0, sizeof(uint32_t) * (size_t)n, e->stream));   // armed for partial refits
         RTS_CUDA(cudaMemsetAsync(e->d_sah, 0, sizeof(double), e->stream));
-        RTS_CUDA(cudaMemsetAsync(&e->d_qframe->overflow, 0, sizeof(uint32_t), e->stream));
-        { k_qframe<<<1, 32, 0, e->stream>>>((const unsigned *)e->d_scene_box, e->d_qframe, 0); e->launches++; }
+        if (want_qnodes(e)) {
+            RTS_CUDA(cudaMemsetAsync(&e->d_qframe->overflow, 0, sizeof(uint32_t), e->stream));
+            { k_qframe<<<1, 32, 0, e->stream>>>((const unsigned *)e->d_scene_box, e->d_qframe, 0); e->launches++; }
+        }
         { k_pack<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_children, e->d_range, e->d_order, e->d_tri_box,
                                                            e->d_node_box, e->d_nodes, n, e->d_sah, e->leaf_max, n - 1, nullptr,
-                                                           nullptr, e->d_qnodes, e->d_qframe, 0); e->launches++; }
+                                                           nullptr, want_qnodes(e) ? e->d_qnodes : nullptr, e->d_qframe, 0); e->launches++; }
     }
     RTS_CUDA(cudaGetLastError());
     e->root_ref = n <= e->leaf_max ? ~((0 << 3) | (n - 1)) : 0;
@@ -633,14 +639,18 @@ static int partial_update(rts_engine *e)
         { k_fit<<<blocks_for(e->n_dt, bs), bs, 0, e->stream>>>(e->d_children, e->d_parent, e->d_order, e->d_tri_box, e->d_node_box, e->d_fit_flags, n, (int)e->n_dt, e->d_tlist, e->d_leaf_of_tri, e->d_mark); e->launches++; }
     }
     if (e->n_dnode) {
-        k_pack<<<blocks_for(e->n_dnode, bs), bs, 0, e->stream>>>(e->d_children, e->d_range, e->d_order, e->d_tri_box, e->d_node_box, e->d_nodes, n, e->d_sah, e->leaf_max, (int)e->n_dnode, e->d_nodelist, e->d_fit_flags, e->d_qnodes, e->d_qframe, 0);
+        const bool wq = want_qnodes(e);
+        k_pack<<<blocks_for(e->n_dnode, bs), bs, 0, e->stream>>>(e->d_children, e->d_range, e->d_order, e->d_tri_box, e->d_node_box, e->d_nodes, n, e->d_sah, e->leaf_max, (int)e->n_dnode, e->d_nodelist, e->d_fit_flags, wq ? e->d_qnodes : nullptr, e->d_qframe, 0);
+        e->launches++;
+        if (wq) {
         // a moving target has left the frame of the quantised nodes (rare: the frame has a margin of 1/16 of the scene):
         // new frame from this pulse's scene box, every node quantised again.  Both launches return at once otherwise —
         // decided on the device, no host synchronisation.
         k_qframe<<<1, 32, 0, e->stream>>>((const unsigned *)e->d_scene_box, e->d_qframe, 1);
         k_pack<<<blocks_for(n - 1, bs), bs, 0, e->stream>>>(e->d_children, e->d_range, e->d_order, e->d_tri_box, e->d_node_box, e->d_nodes, n, e->d_sah, e->leaf_max, n - 1, nullptr, nullptr, e->d_qnodes, e->d_qframe, 1);
         k_qframe_done<<<1, 32, 0, e->stream>>>(e->d_qframe);
-        e->launches += 4;
+        e->launches += 3;
+        }
     }
     { k_scene_abs<<<1, 32, 0, e->stream>>>((const unsigned *)e->d_scene_box, e->d_scene_abs, e->n_tris); e->launches++; }
     RTS_CUDA(cudaGetLastError());

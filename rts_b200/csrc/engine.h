@@ -7,6 +7,9 @@
 
 #include "../../include/rts_b200.h"
 
+#ifndef RTS_QNODES
+#define RTS_QNODES 0            // 1: later waves walk the quantised 32-byte nodes (measured slower: 1.61 vs 1.37 ms; kept as a tuning build)
+#endif
 #define RTS_LEAF_MAX 2          // triangles per BVH leaf (collapsed LBVH subtrees); measured best of 1/2/4 on B200
 #define RTS_STACK_DEPTH 96      // traversal stack entries per thread
 #define RTS_WAVE_BLOCK 128      // threads per CTA of the bounce-wave kernel

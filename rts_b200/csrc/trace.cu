@@ -313,9 +313,6 @@ __device__ __forceinline__ bool traverse(const WaveParams &P, const d3 &o, const
 // on a triangle), under one cell for r <= 64; beyond that (and for |d| < 1e-20) the axis is ignored: near = -inf, far =
 // 3e38.  The one-cell widening of the boxes therefore makes the test conservative with respect to the exact slab
 // interval of the fp64 ray, like traverse()'s.  The sign of inv picks which half word is the near plane (PRMT selector).
-#ifndef RTS_QNODES
-#define RTS_QNODES 0           // 1: later waves walk the quantised 32-byte nodes (measured slower: 1.61 vs 1.37 ms; kept as a tuning build)
-#endif
 struct QRay {
     u64 a[3], b[3];            // (A, A), (B, B): lanes = child 0, child 1
     uint32_t sn[3], sf[3];     // PRMT selectors of the near / far plane

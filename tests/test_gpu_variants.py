@@ -1,0 +1,63 @@
+"""The alternative forms of the bounce waves kept behind options (rts_set_option) give the same answers as the default:
+split later waves (k_traverse + k_shade_wave over the quantised nodes), primary shading without the in-place first
+reflection (no_follow), global-atomics-only bins (no_smem_bins), BVH primary wave (no_raster).  Records bit-equal, bins
+equal in the exact fields and to 1e-12 in the sums (fp64 atomics commute, their rounding order does not)."""
+import numpy as np
+import pytest
+
+from rts_b200 import lib as L, scenes
+
+pytestmark = pytest.mark.gpu
+
+EXACT = ("rx", "path", "npath", "min_slot", "own_min_slot", "direct")
+SUMS = ("sum_sqrt_power", "sum_delay", "sum_phase", "sum_doppler", "power", "delay", "phase", "doppler")
+
+
+def _run(engine, spec, flags):
+    st = engine.trace(spec, flags | L.RTS_NO_REUSE)
+    return st, engine.bins().copy()
+
+
+@pytest.mark.parametrize("option,value", [("no_split", 0), ("no_follow", 1), ("no_smem_bins", 1), ("no_raster", 1)])
+@pytest.mark.parametrize("scene", ["terrain", "trihedral", "slab"])
+def test_option_gives_the_default_answers(engine, option, value, scene):
+    if scene == "terrain":
+        ms = scenes.terrain_scene(n=512, cells_x=96, cells_y=48, movers=6, n_rx=2)
+        targets, spec, poses = ms.base, ms.spec_for(3), ms.poses(3)
+    elif scene == "trihedral":
+        (targets, spec), poses = scenes.trihedral(n=400), None
+    else:
+        (targets, spec), poses = scenes.slab(n=160), None          # refraction: both ends of the queue in use
+    engine.set_targets(targets)
+    if poses is not None:
+        engine.set_poses(*poses)
+    st0, bins0 = _run(engine, spec, L.RTS_OUT_BINS)
+    engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_NO_REUSE)
+    rec0 = engine.records()
+    default = {"no_split": 1, "no_follow": 0, "no_smem_bins": 0, "no_raster": 0}[option]
+    try:
+        engine.set_option(option, value)
+        if option == "no_split":
+            engine.set_option("split_below", 1024)                  # the test scenes are small
+            if poses is not None:
+                engine.set_poses(*poses)                            # enabling the split form rebuilt the tree at the current poses
+        st1, bins1 = _run(engine, spec, L.RTS_OUT_BINS)
+        engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_NO_REUSE)
+        rec1 = engine.records()
+    finally:
+        engine.set_option(option, default)
+        if option == "no_split":
+            engine.set_option("split_below", 1 << 18)
+    for k in ("segments", "hits", "shaded_hits", "captured", "refracted"):
+        assert st0[k] == st1[k], k
+    assert len(bins0) == len(bins1) > 0
+    for f in EXACT:
+        assert np.array_equal(bins0[f], bins1[f]), f
+    for f in SUMS:
+        assert np.allclose(bins0[f], bins1[f], rtol=1e-12, atol=0), f
+    for a, b in zip(rec0, rec1):
+        if a.dtype.names:
+            for f in a.dtype.names:
+                assert a[f].tobytes() == b[f].tobytes(), f
+        else:
+            assert a.tobytes() == b.tobytes()
