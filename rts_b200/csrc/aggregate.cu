@@ -464,6 +464,58 @@ int agg_hash_load(rts_engine *e, const void *keys, const void *sums, const void 
     return RTS_OK;
 }
 
+// Everything a pulse starts from, cleared by ONE launch instead of eight cudaMemsetAsync calls (each a few microseconds of
+// stream time that nothing overlaps): the dense bin table (sums = 0, representative slots = 0x7f..7f, see api.cu), the
+// counters, the per-wave segment counts, the first batch's queue / work counters, and what the emission at the end of
+// the pulse accumulates into (receiver totals, emitted-bin count).
+struct ClearArgs {
+    unsigned long long *sums; unsigned long long n_sums;      // fp64 zeros as words
+    unsigned long long *mins; unsigned long long n_mins;
+    unsigned long long *zero[4]; unsigned n_zero[4];          // counters, wave_segs, counts, rx_sums: words to zero
+    unsigned long long *rx_mins; unsigned n_rx_mins;           // ~0
+    uint32_t *bins_out_count;
+};
+__global__ void k_pulse_clear(const ClearArgs A)
+{
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, step = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = tid; i < A.n_sums; i += step) A.sums[i] = 0ull;
+    for (unsigned long long i = tid; i < A.n_mins; i += step) A.mins[i] = 0x7f7f7f7f7f7f7f7full;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        for (unsigned long long i = tid; i < A.n_zero[k]; i += step) A.zero[k][i] = 0ull;
+    for (unsigned long long i = tid; i < A.n_rx_mins; i += step) A.rx_mins[i] = ~0ull;
+    if (tid == 0 && A.bins_out_count) *A.bins_out_count = 0u;
+}
+
+// dense: also clear the bin table (the sparse table is cleared through its list of occupied slots, agg_hash_prepare)
+int agg_pulse_clear(rts_engine *e, bool dense_bins, uint64_t n_bins, uint32_t n_rx)
+{
+    if (!e->d_rx_sums) {
+        RTS_CUDA(cudaMalloc(&e->d_rx_sums, sizeof(double) * 5 * RTS_MAX_RX));
+        RTS_CUDA(cudaMalloc(&e->d_rx_mins, sizeof(unsigned long long) * RTS_MAX_RX));
+    }
+    if (!e->d_bins_out_count) RTS_CUDA(cudaMalloc(&e->d_bins_out_count, sizeof(uint32_t)));
+    ClearArgs A;
+    memset(&A, 0, sizeof(A));
+    if (dense_bins) {
+        A.sums = reinterpret_cast<unsigned long long *>(e->d_bin_sums); A.n_sums = n_bins * 5ull;
+        A.mins = e->d_bin_mins; A.n_mins = n_bins;
+    }
+    A.zero[0] = reinterpret_cast<unsigned long long *>(e->d_counters); A.n_zero[0] = (unsigned)(sizeof(Counters) / 8);
+    A.zero[1] = e->d_wave_segs; A.n_zero[1] = 32;
+    A.zero[2] = e->d_counts; A.n_zero[2] = 96;
+    A.zero[3] = reinterpret_cast<unsigned long long *>(e->d_rx_sums); A.n_zero[3] = 5u * n_rx;
+    A.rx_mins = e->d_rx_mins; A.n_rx_mins = n_rx;
+    A.bins_out_count = e->d_bins_out_count;
+    const unsigned long long words = std::max<unsigned long long>(A.n_sums, 256ull);
+    const unsigned grid = (unsigned)std::min<unsigned long long>((words + 255ull) / 256ull, (unsigned long long)e->num_sms * 8ull);
+    k_pulse_clear<<<grid, 256, 0, e->stream>>>(A);
+    RTS_CUDA(cudaGetLastError());
+    e->launches++;
+    e->emit_precleared = true;
+    return RTS_OK;
+}
+
 // receiver totals (direct-ray rule) + myKernel2 + compaction of the non-empty bins into d_bins_out, enqueued
 static int enqueue_emit(rts_engine *e, uint32_t cap)
 {
@@ -474,8 +526,12 @@ static int enqueue_emit(rts_engine *e, uint32_t cap)
         RTS_CUDA(cudaMalloc(&e->d_rx_sums, sizeof(double) * 5 * RTS_MAX_RX));
         RTS_CUDA(cudaMalloc(&e->d_rx_mins, sizeof(unsigned long long) * RTS_MAX_RX));
     }
-    RTS_CUDA(cudaMemsetAsync(e->d_rx_sums, 0, sizeof(double) * 5 * n_rx, e->stream));
-    RTS_CUDA(cudaMemsetAsync(e->d_rx_mins, 0xff, sizeof(unsigned long long) * n_rx, e->stream));
+    const bool precleared = e->emit_precleared;      // the pulse's clear kernel did it (first emission of the pulse only)
+    e->emit_precleared = false;
+    if (!precleared) {
+        RTS_CUDA(cudaMemsetAsync(e->d_rx_sums, 0, sizeof(double) * 5 * n_rx, e->stream));
+        RTS_CUDA(cudaMemsetAsync(e->d_rx_mins, 0xff, sizeof(unsigned long long) * n_rx, e->stream));
+    }
     if (e->bins_hashed) {
         k_hash_rx_totals<<<64, 256, 0, e->stream>>>(e->d_hash_keys, e->d_bin_sums, e->d_bin_mins, e->d_hash_used, e->d_hash_count, per_rx, n_rx,
                                                     e->d_rx_sums, e->d_rx_mins);
@@ -493,7 +549,7 @@ static int enqueue_emit(rts_engine *e, uint32_t cap)
         e->bins_out_alloc = want;
     }
     if (!e->d_bins_out_count) RTS_CUDA(cudaMalloc(&e->d_bins_out_count, sizeof(uint32_t)));
-    RTS_CUDA(cudaMemsetAsync(e->d_bins_out_count, 0, sizeof(uint32_t), e->stream));
+    if (!precleared) RTS_CUDA(cudaMemsetAsync(e->d_bins_out_count, 0, sizeof(uint32_t), e->stream));
     if (e->bins_hashed) {
         k_hash_emit<<<64, 256, 0, e->stream>>>(e->d_hash_keys, e->d_bin_sums, e->d_bin_mins, e->d_hash_used, e->d_hash_count, per_rx, B, D,
                                                e->d_rx_sums, e->d_rx_mins, e->d_bins_out, e->d_bins_out_count, cap);

@@ -583,9 +583,8 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
             if (rc) return rc;
             P.hash_keys = e->d_hash_keys; P.hash_used = e->d_hash_used; P.hash_count = e->d_hash_count;
         } else {
-            e->hash_ready = false;   // the dense table shares the arrays
-            RTS_CUDA(cudaMemsetAsync(e->d_bin_sums, 0, sizeof(double) * 5 * nb, st));
-            RTS_CUDA(cudaMemsetAsync(e->d_bin_mins, 0x7f, sizeof(unsigned long long) * nb, st)); // empty = 0x7f7f…7f: positive as int64, so a signed MIN all-reduce keeps it last
+            e->hash_ready = false;   // the dense table shares the arrays; cleared below by agg_pulse_clear (sums 0, slots 0x7f7f…7f:
+                                     // positive as int64, so a signed MIN all-reduce keeps it last)
         }
         P.bin_sums = e->d_bin_sums; P.bin_mins = e->d_bin_mins; P.n_bins = e->n_bins_dense;
         // small dense tables are pre-reduced per CTA in shared memory (trace.cu: bins_smem_*); not in the split form of the waves
@@ -627,7 +626,11 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     }
     P.out_capacity = e->q_capacity;
     P.counters = e->d_counters;
-    RTS_CUDA(cudaMemsetAsync(e->d_counters, 0, sizeof(Counters), st));
+    {   // counters, per-wave counts, the first batch's queue counters, the dense bin table, the emission's accumulators: one launch
+        const bool dense = (flags & RTS_OUT_BINS) && !e->bins_hashed && e->n_bins_dense;
+        int rc = agg_pulse_clear(e, dense, e->n_bins_dense, p->n_rx);
+        if (rc) return rc;
+    }
 
     e->split_timed = false;
     e->follow_timed = false;
@@ -640,7 +643,6 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     const uint32_t max_waves = p->max_refl + 1 + (rMax ? 2 : 0); // longest chain: see DESIGN.md (wave count)
     uint64_t waves = 0;
     P.wave_segs = e->d_wave_segs;
-    RTS_CUDA(cudaMemsetAsync(e->d_wave_segs, 0, sizeof(unsigned long long) * 32, st));
     for (int w = 0; w < 32; w++) e->wave_ms[w] = 0.f;
     e->n_waves = std::min<uint32_t>(max_waves, 31);
     const bool single_batch = n_primary_total <= batch;
@@ -660,7 +662,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     for (uint64_t done = 0; done < n_primary_total; done += batch) {
         const uint64_t nb = std::min<uint64_t>(batch, n_primary_total - done);
         // d_counts: [0..31] queue counts per wave, [32..63] work counters per wave, [64..95] queue counts from the far end
-        RTS_CUDA(cudaMemsetAsync(e->d_counts, 0, sizeof(unsigned long long) * 96, st));
+        if (done) RTS_CUDA(cudaMemsetAsync(e->d_counts, 0, sizeof(unsigned long long) * 96, st));   // (the first batch's: agg_pulse_clear)
         for (uint32_t w = 0; w < max_waves && w < 31; w++) {
             WaveParams Q = P;
             Q.ray_begin = begin; Q.ray_stride = stride; Q.n_primary = nb; Q.batch_base = done;

@@ -379,6 +379,7 @@ struct rts_engine {
     uint64_t compact_alloc = 0;
     rts_bin *d_bins_out = nullptr, *h_bins = nullptr;   // h_bins: pinned
     bool bins_eager = false;
+    bool emit_precleared = false;      // the receiver totals / emitted-bin count were zeroed by the pulse's clear kernel
     double *d_rx_sums = nullptr;
     unsigned long long *d_rx_mins = nullptr;
     uint32_t *d_bins_out_count = nullptr;
@@ -463,6 +464,7 @@ int agg_hash_prepare(rts_engine *e, uint64_t slots);   // allocate / clear the s
 int agg_hash_compact(rts_engine *e, void **keys, void **sums, void **mins, uint32_t *n);
 int agg_hash_load(rts_engine *e, const void *keys, const void *sums, const void *mins, uint32_t n);
 int agg_emit_bins_async(rts_engine *e);
+int agg_pulse_clear(rts_engine *e, bool dense_bins, uint64_t n_bins, uint32_t n_rx);   // one launch for everything a pulse starts from
 int agg_fill_records(rts_engine *e, uint64_t ray_total, uint32_t D, uint32_t W);
 int agg_get_received(rts_engine *e, uint64_t cap, uint64_t *n, uint64_t *slots, rts_ray_record *results, int32_t *targ_intersect,
                      double *rcs_angle);

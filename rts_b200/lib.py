@@ -216,7 +216,9 @@ class Engine:
         self._scene = CScene(targets)
         _check(self._lib.rts_scene_set_targets(self._h, self._scene.array, self._scene.n))
 
-    def set_poses(self, rotations: Sequence[Optional[np.ndarray]], translations: Sequence[Sequence[float]]):
+    @staticmethod
+    def pack_poses(rotations: Sequence[Optional[np.ndarray]], translations: Sequence[Sequence[float]]):
+        """The rts_pose array of a pulse as the C-ABI takes it (a host loop that knows its poses ahead prepares them once)."""
         n = len(translations)
         arr = (RtsPose * max(1, n))()
         for k in range(n):
@@ -225,6 +227,12 @@ class Engine:
             Rm = np.eye(3) if R is None else np.asarray(R, dtype=np.float64).reshape(3, 3)
             arr[k].R = (C.c_double * 9)(*Rm.reshape(-1))
             arr[k].t = (C.c_double * 3)(*[float(v) for v in translations[k]])
+        return arr, n
+
+    def set_poses(self, rotations: Sequence[Optional[np.ndarray]], translations: Sequence[Sequence[float]]):
+        self.set_poses_packed(*self.pack_poses(rotations, translations))
+
+    def set_poses_packed(self, arr, n: int):
         _check(self._lib.rts_scene_set_poses(self._h, arr, n))
 
     def rebuild(self):
@@ -254,8 +262,15 @@ class Engine:
     def trace(self, spec: PulseSpec, flags: int = RTS_OUT_BINS) -> Optional[dict]:
         """One pulse.  With RTS_ASYNC the call returns as soon as the pulse is enqueued (None); stats() / bins() /
         sync() wait for it."""
-        self._pulse = CPulse(spec, self._scene.n if self._scene else 0)
-        _check(self._lib.rts_trace_pulse(self._h, C.byref(self._pulse.c), int(flags)))
+        return self.trace_prepared(self.prepare(spec), flags)
+
+    def prepare(self, spec: PulseSpec) -> "CPulse":
+        """The rts_pulse struct (and the host arrays it points to) of a pulse, built once for trace_prepared."""
+        return CPulse(spec, self._scene.n if self._scene else 0)
+
+    def trace_prepared(self, pulse: "CPulse", flags: int = RTS_OUT_BINS) -> Optional[dict]:
+        self._pulse = pulse
+        _check(self._lib.rts_trace_pulse(self._h, C.byref(pulse.c), int(flags)))
         if flags & RTS_ASYNC:
             return None
         return self.stats()
