@@ -12,7 +12,9 @@
 #endif
 #define RTS_LEAF_MAX 2          // triangles per BVH leaf (collapsed LBVH subtrees); measured best of 1/2/4 on B200
 #define RTS_STACK_DEPTH 96      // traversal stack entries per thread
+#ifndef RTS_WAVE_BLOCK
 #define RTS_WAVE_BLOCK 128      // threads per CTA of the bounce-wave kernel
+#endif
 #ifndef RTS_WAVE_MIN_BLOCKS
 #define RTS_WAVE_MIN_BLOCKS 6           // resident CTAs per SM the register allocation must allow (later waves)
 #endif
