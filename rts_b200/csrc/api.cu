@@ -80,6 +80,8 @@ static int set_option(rts_engine *e, const char *name, long long v)
     else if (!strcmp(name, "no_graph")) k.no_graph = v != 0;
     else if (!strcmp(name, "no_follow")) k.no_follow = v != 0;
     else if (!strcmp(name, "no_smem_bins")) k.no_smem_bins = v != 0;
+    else if (!strcmp(name, "debug_timeline")) { k.debug_timeline = v != 0; e->tl_n = 0; }
+    else if (!strcmp(name, "no_overlap")) { bvh_join(e); k.no_overlap = v != 0; }
     else if (!strcmp(name, "hash_bins")) k.hash_bins = v != 0;
     else if (!strcmp(name, "hash_log2")) { if (v < 4 || v > 28) return rts_fail(RTS_ERR_ARG, "hash_log2 must be 4..28"); k.hash_log2 = (uint32_t)v; e->hash_ready = false; }
     else if (!strcmp(name, "batch")) { if (v != 0 && (v < 32 || v > (1ll << 24))) return rts_fail(RTS_ERR_ARG, "batch must be 0 or 32..2^24"); k.batch = v; }
@@ -119,7 +121,7 @@ extern "C" int rts_create(int device, rts_engine **out)
     e->stream = e->own_stream;
     // tuning / test switches: the environment is read here, once; afterwards only rts_set_option changes them
     for (const char *name : {"bvh", "leaf_max", "no_chain", "no_raster", "no_tiles", "one_ended_queue", "debug_raster", "no_static_hits",
-                             "no_kept_reflections", "no_split", "split_below", "no_graph", "no_follow", "no_smem_bins", "batch", "hash_bins", "hash_log2"}) {
+                             "no_kept_reflections", "no_split", "split_below", "no_graph", "no_follow", "no_smem_bins", "no_overlap", "debug_timeline", "batch", "hash_bins", "hash_log2"}) {
         std::string env = "RTS_";
         for (const char *c = name; *c; c++) env += (char)toupper(*c);
         if (const char *v = getenv(env.c_str())) {
@@ -133,6 +135,14 @@ extern "C" int rts_create(int device, rts_engine **out)
     for (auto &ev : e->follow_ev) cudaEventCreate(&ev);
     for (auto &s : e->stage) cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&e->sah_ev, cudaEventDisableTiming);
+    {   // side streams (engine.h); the refit's is the more urgent one: the kernel that walks the tree waits for it
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&e->side_bvh, cudaStreamNonBlocking, hi) != cudaSuccess) e->side_bvh = nullptr;
+        if (cudaStreamCreateWithFlags(&e->side_dirs, cudaStreamNonBlocking) != cudaSuccess) e->side_dirs = nullptr;
+        for (cudaEvent_t *ev : {&e->ev_dirs_free, &e->ev_dirs_done, &e->ev_bvh_fork, &e->ev_bvh_done}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+        cudaGetLastError();
+    }
     if (cudaMallocHost((void **)&e->h_rb, sizeof(Readback)) != cudaSuccess) {
         rts_destroy(e);
         return rts_fail(RTS_ERR_CUDA, "cudaMallocHost failed");
@@ -179,6 +189,9 @@ extern "C" void rts_destroy(rts_engine *e)
     for (auto &ev : e->follow_ev) if (ev) cudaEventDestroy(ev);
     for (auto &s : e->stage) { if (s.done) cudaEventDestroy(s.done); if (s.host) cudaFreeHost(s.host); }
     if (e->sah_ev) cudaEventDestroy(e->sah_ev);
+    for (auto &row : e->tl_ev) for (auto &ev : row) if (ev) cudaEventDestroy(ev);
+    for (cudaStream_t sd : {e->side_dirs, e->side_bvh}) if (sd) { cudaStreamSynchronize(sd); cudaStreamDestroy(sd); }
+    for (cudaEvent_t ev : {e->ev_dirs_free, e->ev_dirs_done, e->ev_bvh_fork, e->ev_bvh_done}) if (ev) cudaEventDestroy(ev);
     if (e->h_rb) cudaFreeHost(e->h_rb);
     if (e->h_bins) cudaFreeHost(e->h_bins);
     if (e->d_wave_segs) cudaFree(e->d_wave_segs);
@@ -212,7 +225,10 @@ void stage_release(rts_engine *e)
 extern "C" int rts_set_stream(rts_engine *e, void *cuda_stream)
 {
     if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    bvh_join(e);
     cudaStreamSynchronize(e->stream);
+    if (e->side_dirs) cudaStreamSynchronize(e->side_dirs);
+    e->dirs_free_valid = false;      // ev_dirs_free belongs to the stream that is being left
     e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
     return RTS_OK;
 }
@@ -331,7 +347,7 @@ extern "C" int rts_scene_set_poses(rts_engine *e, const rts_pose *poses, uint32_
     stage_release(e);
     int rc = bvh_refit(e);
     if (rc) return rc;
-    cudaEventRecord(e->ev[5], e->stream);
+    cudaEventRecord(e->ev[5], e->bvh_join_pending ? e->side_bvh : e->stream);   // where the refit's last kernel went
     e->refit_timed = true;
     return RTS_OK;   // nothing waited for: the transform and refit run on the engine's stream
 }
@@ -682,6 +698,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
                 kept = e->coh_on;
                 kept_params = Q;
             }
+            if (w == 1 && e->knobs.debug_timeline && e->tl_n && e->tl_ev[e->tl_n - 1][5]) cudaEventRecord(e->tl_ev[e->tl_n - 1][5], st);
             if (w == 1 && kept) {         // first reflections served from the kept hits (coherent.cuh)
                 Q.w1_static = kept_params.w1_static; Q.hits_static = kept_params.hits_static; Q.moving_flags = kept_params.moving_flags;
                 trace_wave_grid(e);
@@ -698,6 +715,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
             waves++;
         }
         if (single_batch) cudaEventRecord(e->wave_ev[e->n_waves], st);
+        if (e->knobs.debug_timeline && e->tl_n && e->tl_ev[e->tl_n - 1][6]) cudaEventRecord(e->tl_ev[e->tl_n - 1][6], st);
     }
     cudaEventRecord(e->ev[1], st);
     // read-back of the counters into pinned memory; folded into the stats by pulse_collect()
@@ -864,9 +882,19 @@ extern "C" int rts_sync(rts_engine *e)
 {
     if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
     RTS_CUDA(cudaSetDevice(e->device));
-    if (e->pulse_pending) return pulse_collect(e);
-    RTS_CUDA(cudaStreamSynchronize(e->stream));
-    return RTS_OK;
+    int rc = RTS_OK;
+    if (e->pulse_pending) rc = pulse_collect(e);
+    else RTS_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->knobs.debug_timeline && e->tl_n) {   // when each of the last pulses' direction pass / footprints / shading pass ran
+        if (e->side_dirs) cudaStreamSynchronize(e->side_dirs);
+        for (int i = 0; i < e->tl_n; i++) {
+            float t[7] = {0, 0, 0, 0, 0, 0, 0};
+            for (int k = 0; k < 7; k++) cudaEventElapsedTime(&t[k], e->tl_ev[0][0], e->tl_ev[i][k]);
+            fprintf(stderr, "[timeline] pulse %2d: dirs %8.3f .. %8.3f   footprints from %8.3f   shading pass %8.3f .. %8.3f   later waves %8.3f .. %8.3f ms\n", i, t[0], t[1], t[2], t[3], t[4], t[5], t[6]);
+        }
+        e->tl_n = 0;
+    }
+    return rc;
 }
 
 extern "C" int rts_get_stats(rts_engine *e, rts_stats *out)

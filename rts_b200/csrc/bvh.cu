@@ -624,6 +624,8 @@ static int prepare_partial(rts_engine *e)
     return RTS_OK;
 }
 
+static void collect_sah(rts_engine *e, bool wait);
+
 // Only the moving targets: their vertices, normals, leaf boxes and triangle records, then the tree paths above them.
 static int partial_update(rts_engine *e)
 {
@@ -632,10 +634,24 @@ static int partial_update(rts_engine *e)
     if (e->n_dv) { k_transform<<<blocks_for(e->n_dv, bs), bs, 0, e->stream>>>(e->d_base_verts, e->d_world_verts, e->d_vert_target, e->d_poses, e->n_dv, 1, e->d_vlist); e->launches++; }
     if (e->n_dn) { k_transform<<<blocks_for(e->n_dn, bs), bs, 0, e->stream>>>(e->d_base_normals, e->d_world_normals, e->d_norm_target, e->d_poses, e->n_dn, 0, e->d_nlist); e->launches++; }
     RTS_CUDA(cudaMemcpyAsync(e->d_scene_box, e->d_static_box, sizeof(unsigned) * 6, cudaMemcpyDeviceToDevice, e->stream));
-    RTS_CUDA(cudaMemcpyAsync(e->d_sah, e->d_sah_static, sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
     if (e->n_dt) {
         { k_tri_boxes<<<blocks_for(e->n_dt, bs), bs, 0, e->stream>>>(e->d_world_verts, e->d_tris, e->d_tri_target, e->d_t_vert_off, e->d_tri_box, (unsigned *)e->d_scene_box, e->n_dt, e->d_tlist); e->launches++; }
         { k_tri_records<<<blocks_for(e->n_dt, bs), bs, 0, e->stream>>>(e->d_world_verts, e->d_tris, e->d_tri_target, e->d_t_vert_off, e->d_order, e->d_trirec, e->n_dt, e->d_tlist, e->d_leaf_of_tri); e->launches++; }
+    }
+    // Vertices, normals, leaf boxes and triangle records are what the projected primary wave reads; everything from here
+    // on — node boxes, packed nodes, scene_abs, the SAH cost — is read by traversal only.  It runs on side_bvh, beside the
+    // footprint kernels of the pulse that follows; the first kernel that walks the tree waits for it (bvh_join).  The fork
+    // is behind this stream's earlier work, so the previous pulse's last waves are done with the nodes.
+    const cudaStream_t main_stream = e->stream;
+    const bool side = e->side_bvh && !e->knobs.no_overlap;
+    struct Restore { rts_engine *e; cudaStream_t s; ~Restore() { e->stream = s; } } restore{e, main_stream};   // also on the error returns
+    if (side) {
+        cudaEventRecord(e->ev_bvh_fork, main_stream);
+        cudaStreamWaitEvent(e->side_bvh, e->ev_bvh_fork, 0);
+        e->stream = e->side_bvh;
+    }
+    RTS_CUDA(cudaMemcpyAsync(e->d_sah, e->d_sah_static, sizeof(double), cudaMemcpyDeviceToDevice, e->stream));
+    if (e->n_dt) {
         { k_fit<<<blocks_for(e->n_dt, bs), bs, 0, e->stream>>>(e->d_children, e->d_parent, e->d_order, e->d_tri_box, e->d_node_box, e->d_fit_flags, n, (int)e->n_dt, e->d_tlist, e->d_leaf_of_tri, e->d_mark); e->launches++; }
     }
     if (e->n_dnode) {
@@ -653,8 +669,29 @@ static int partial_update(rts_engine *e)
         }
     }
     { k_scene_abs<<<1, 32, 0, e->stream>>>((const unsigned *)e->d_scene_box, e->d_scene_abs, e->n_tris); e->launches++; }
+    if (side) {
+        // the SAH cost's read-back belongs behind k_pack: on the side stream too
+        if (n >= 2) {
+            collect_sah(e, true);   // one read-back slot: the previous one has long arrived
+            cudaMemcpyAsync(&e->h_rb->sah, e->d_sah, sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+            cudaEventRecord(e->sah_ev, e->stream);
+            e->sah_pending = true;
+        }
+        cudaEventRecord(e->ev_bvh_done, e->side_bvh);
+        e->bvh_join_pending = true;
+        e->stream = main_stream;
+    }
     RTS_CUDA(cudaGetLastError());
     return RTS_OK;
+}
+
+// The engine's stream waits for the refit that may still be running on side_bvh.  Called ahead of everything that reads or
+// writes the tree: the wave kernels (trace.cu), the next update, a rebuild, the diagnostics.
+void bvh_join(rts_engine *e)
+{
+    if (!e->bvh_join_pending) return;
+    cudaStreamWaitEvent(e->stream, e->ev_bvh_done, 0);
+    e->bvh_join_pending = false;
 }
 
 // Scene box of the current geometry into bvh_info (synchronises; diagnostics only — the kernels read d_scene_abs).
@@ -797,6 +834,7 @@ static int build_once(rts_engine *e, bool ploc, double *sah_out)
 int bvh_build(rts_engine *e)
 {
     const int n = (int)e->n_tris;
+    bvh_join(e);
     e->partial_ready = false;
     e->sah_pending = false;
     cudaEventRecord(e->ev[4], e->stream);
@@ -852,6 +890,7 @@ static void collect_sah(rts_engine *e, bool wait)
 int bvh_refit(rts_engine *e)
 {
     int rc;
+    bvh_join(e);
     collect_sah(e, false);
     if (e->n_tris >= 2 && e->sah_at_build > 0 && e->bvh_info.sah_cost > RTS_REBUILD_RATIO * e->sah_at_build) return bvh_build(e);
     uint32_t n_moving = 0;
@@ -865,10 +904,12 @@ int bvh_refit(rts_engine *e)
         if ((rc = partial_update(e))) return rc;
     }
     if (e->n_tris >= 2) {
+        if (!e->bvh_join_pending) {   // (a refit that went to side_bvh has enqueued its read-back there)
         collect_sah(e, true);   // one read-back slot: the previous one has long arrived
         RTS_CUDA(cudaMemcpyAsync(&e->h_rb->sah, e->d_sah, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
         cudaEventRecord(e->sah_ev, e->stream);
         e->sah_pending = true;
+        }
         // The first refits after a build are examined at once: committing base meshes and then placing the
         // targets (the usual first call) can move them arbitrarily far from where the topology clustered them.
         if (e->refits_since_build < 2) {
@@ -890,6 +931,7 @@ int bvh_check(rts_engine *e, uint64_t *violations)
 {
     const int n = (int)e->n_tris;
     unsigned long long v = 0;
+    bvh_join(e);
     if (n >= 2) {
         RTS_CUDA(cudaMemsetAsync(e->d_violations, 0, sizeof(unsigned long long), e->stream));
         { k_check<<<blocks_for(n, 256), 256, 0, e->stream>>>(e->d_parent, e->d_order, e->d_tri_box, e->d_node_box, n,

@@ -257,7 +257,7 @@ struct Comm {
 // Tuning / test switches: read from the environment once in rts_create, changed afterwards only through rts_set_option.
 struct Knobs {
     int no_chain = 0, no_raster = 0, no_tiles = 0, one_ended_queue = 0, debug_raster = 0, no_static_hits = 0,
-        no_kept_reflections = 0, no_split = 1, no_graph = 0, no_follow = 0, no_smem_bins = 0;
+        no_kept_reflections = 0, no_split = 1, no_graph = 0, no_follow = 0, no_smem_bins = 0, no_overlap = 0, debug_timeline = 0;
     long long batch = 0;           // 0 = default 2^24 primaries per batch
     int hash_bins = 0;             // 1: sparse (hashed) bins also where a dense table would fit
     uint32_t hash_log2 = 22;       // slots of the sparse bin table
@@ -269,6 +269,21 @@ struct rts_engine {
     Knobs knobs;
     int num_sms = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
+    // Work of a pulse that does not depend on the rest of the stream runs beside it (knob no_overlap turns both off):
+    //   side_dirs  k_primary_dirs needs the launch geometry only and two buffers that are free as soon as the previous
+    //              pulse's shading pass is done (ev_dirs_free) — it runs beside that pulse's last waves / bin emission and
+    //              this pulse's pose update; the footprint kernels wait for ev_dirs_done.  (Measured and not kept, DESIGN
+    //              §6: a second set of buffers so that it can run beside the previous pulse's footprint kernels or shading
+    //              pass — those need the fp64 pipe / the issue slots as much as it does, the sum stays the same.)
+    //   side_bvh   the refit above the moving triangles (k_fit, k_pack, scene_abs, SAH read-back) forks behind the leaf
+    //              boxes / triangle records (ev_bvh_fork); only traversal needs the nodes, so the footprint kernels run
+    //              beside it and the first kernel that walks the tree waits for ev_bvh_done (bvh_join).
+    cudaStream_t side_dirs = nullptr, side_bvh = nullptr;
+    cudaEvent_t ev_dirs_free = nullptr, ev_dirs_done = nullptr, ev_bvh_fork = nullptr, ev_bvh_done = nullptr;
+    bool dirs_free_valid = false, bvh_join_pending = false;
+    // knob debug_timeline: timestamps of up to 16 pulses' direction pass / footprint kernels / shading pass, printed by rts_sync
+    cudaEvent_t tl_ev[16][7] = {};   // + start and end of the later waves
+    int tl_n = 0;
     cudaEvent_t ev[6] = {};
     cudaEvent_t wave_ev[34] = {};
     cudaEvent_t split_ev[3] = {};      // around k_traverse and k_shade_wave of the second wave
@@ -443,6 +458,7 @@ int bvh_update_world(rts_engine *e);          // transform + tri boxes (+ tri re
 int bvh_build(rts_engine *e);                 // full LBVH build at current world geometry
 int bvh_refit(rts_engine *e);                 // bottom-up refit + repack
 int bvh_check(rts_engine *e, uint64_t *violations);
+void bvh_join(rts_engine *e);                // the engine's stream waits for a refit still running on side_bvh
 int bvh_read_scene_box(rts_engine *e);        // fills bvh_info.scene_lo/hi (synchronises)
 void bvh_sync_info(rts_engine *e);            // waits for the last refit's SAH cost
 

@@ -1067,6 +1067,7 @@ static int ensure_coop(rts_engine *e, int ctas)
 int trace_launch_wave(rts_engine *e, const WaveParams &p_in, bool primary, bool records)
 {
     trace_wave_grid(e);
+    bvh_join(e);
     const int grid = primary ? e->wave_grid_primary : e->wave_grid;   // persistent: resident CTAs per SM x SMs
     const WaveParams &p = p_in;
     const bool count = (p.flags & RTS_COUNT_NODES) != 0;
@@ -1093,6 +1094,7 @@ int trace_launch_split(rts_engine *e, WaveParams &p, bool records)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_traverse<false>, RTS_WAVE_BLOCK, 0);
         e->trav_grid = e->num_sms * (occ > 0 ? occ : 1);
     }
+    bvh_join(e);
     p.trav_hits = e->d_trav_hits;
     p.split_on = 1;
     // p.split_below: set by the caller (knob; default 2^18 rays)
@@ -1117,10 +1119,11 @@ int trace_raster_alloc(rts_engine *e, uint64_t batch)
     if (e->raster_alloc >= batch) return RTS_OK;
     void **ptrs[] = {(void **)&e->d_dirs, (void **)&e->d_hits, (void **)&e->d_hits_static, &e->d_raster_ctl, &e->d_raster_ctl_static,
                      &e->d_raster_items};
-    for (void **p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+    for (void **p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }   // (cudaFree waits for the device: nothing of the side streams is in flight)
     e->raster_alloc = 0;
     RTS_CUDA(cudaMalloc(&e->d_dirs, sizeof(double) * 3 * batch));
     RTS_CUDA(cudaMalloc(&e->d_hits, sizeof(unsigned long long) * batch));
+    e->dirs_free_valid = false;
     RTS_CUDA(cudaMalloc(&e->d_hits_static, sizeof(unsigned long long) * batch));
     if (e->d_w1_static) { cudaFree(e->d_w1_static); e->d_w1_static = nullptr; }
     RTS_CUDA(cudaMalloc(&e->d_w1_static, sizeof(unsigned long long) * batch));
@@ -1149,8 +1152,6 @@ static void launch_footprints(rts_engine *e, const WaveParams &p, unsigned count
 int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_batch)
 {
     cudaStream_t st = e->stream;
-    for (int a = 0; a < 3; a++) p.dirs[a] = e->d_dirs + (size_t)a * e->raster_alloc;
-    p.hits = e->d_hits;
     p.raster_ctl = (RasterCtl *)e->d_raster_ctl;
     p.raster_items = (RasterItem *)e->d_raster_items;
     p.raster_item_cap = RTS_RASTER_ITEM_CAP;
@@ -1166,10 +1167,33 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     memcpy(key.c, p.origin, sizeof(double) * 3); memcpy(key.c + 3, p.beamStart, sizeof(double) * 3);
     memcpy(key.c + 6, p.slope, sizeof(double) * 3); memcpy(key.c + 9, p.Rot, sizeof(double) * 9);
     memcpy(key.c + 18, p.Rot1, sizeof(double) * 9); memcpy(key.c + 27, p.boresight, sizeof(double) * 3);
+    cudaEvent_t *tl = nullptr;       // knob debug_timeline
+    if (e->knobs.debug_timeline && e->tl_n < 16 && (p.flags & RTS_NO_REUSE)) {
+        tl = e->tl_ev[e->tl_n++];
+        for (int k = 0; k < 7; k++) if (!tl[k]) cudaEventCreate(&tl[k]);
+    }
     const bool reuse = !(p.flags & RTS_NO_REUSE);
     const bool same_launch = reuse && e->dirs_valid && memcmp(&key, &e->dirs_key, sizeof(key)) == 0;
+    for (int a = 0; a < 3; a++) p.dirs[a] = e->d_dirs + (size_t)a * e->raster_alloc;
+    p.hits = e->d_hits;
     if (!same_launch) {
-        k_primary_dirs<<<e->num_sms * 16, 256, 0, st>>>(p);   // also resets the hit words
+        // on its own stream (engine.h: side_dirs): the two buffers are free once the previous shading pass is done, and
+        // nothing else of this stream — the previous pulse's thin waves and bin emission, this pulse's pose update — has to
+        // be waited for; the footprint kernels below wait for the directions
+        const bool side = e->side_dirs && !e->knobs.no_overlap;
+        if (side) {
+            if (!e->dirs_free_valid) cudaEventRecord(e->ev_dirs_free, st);
+            cudaStreamWaitEvent(e->side_dirs, e->ev_dirs_free, 0);
+        }
+        for (int a = 0; a < 3; a++) p.dirs[a] = e->d_dirs + (size_t)a * e->raster_alloc;
+        p.hits = e->d_hits;
+        if (tl) cudaEventRecord(tl[0], side ? e->side_dirs : st);
+        k_primary_dirs<<<e->num_sms * 32, RTS_DIRS_BLOCK, 0, side ? e->side_dirs : st>>>(p);   // also resets the hit words
+        if (tl) cudaEventRecord(tl[1], side ? e->side_dirs : st);
+        if (side) {
+            cudaEventRecord(e->ev_dirs_done, e->side_dirs);
+            cudaStreamWaitEvent(st, e->ev_dirs_done, 0);
+        }
         e->dirs_key = key;
         e->dirs_valid = true;
         e->static_valid = false;
@@ -1178,6 +1202,7 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     // The closest hits among the triangles that never move are the same from pulse to pulse as long as the launch, the
     // scene and the set of moving targets are: they are kept (static pass once), and a pulse only projects the
     // triangles of the moving targets on top of a copy.  Needs the moving-target lists of the partial refit (bvh.cu).
+    if (tl) cudaEventRecord(tl[2], st);
     uint32_t n_moving = 0;
     for (uint32_t k = 0; k < e->n_targets; k++) n_moving += e->moving[k] ? 1u : 0u;
     const bool cacheable = reuse && single_batch && !e->knobs.no_static_hits && (n_moving == 0 || e->partial_ready);
@@ -1227,6 +1252,8 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     // Without kept first-reflection hits the shading pass follows each reflection in place (follow.cuh): the second wave's
     // queue round trip (88 bytes written and read back per lit pixel) disappears, and the next launch is a thin one.
     e->followed = !e->coh_on && !e->knobs.no_follow && p.dMax >= 2;
+    bvh_join(e);      // the shading pass below is the first kernel of the pulse that may walk the tree
+    if (tl) cudaEventRecord(tl[3], st);
     if (e->followed) {
         if (!e->follow_grid) {
             int occ = 0;
@@ -1250,6 +1277,9 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     else k_primary_shade<false><<<e->num_sms * RTS_SHADE_MIN_BLOCKS, RTS_WAVE_BLOCK, bins_smem_bytes(p), st>>>(p);
     RTS_CUDA(cudaGetLastError());
     e->launches += 1;
+    if (tl) cudaEventRecord(tl[4], st);
+    // the shading pass is the last reader of the direction / hit-word buffers
+    if (e->side_dirs) { cudaEventRecord(e->ev_dirs_free, st); e->dirs_free_valid = true; }
     return RTS_OK;
 }
 
@@ -1258,6 +1288,7 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
 int trace_launch_kept(rts_engine *e, WaveParams &p, bool records)
 {
     cudaStream_t st = e->stream;
+    bvh_join(e);
     MoverIds M;
     memset(&M, 0, sizeof(M));
     for (uint32_t k = 0; k < e->n_targets && M.n < 32; k++)
