@@ -174,6 +174,7 @@ struct WaveParams {
     RasterCtl *raster_ctl;
     RasterItem *raster_items;
     uint32_t raster_item_cap;
+    uint32_t raster_chunk;          // candidates per row chunk of a large footprint (k_raster_big: one warp per chunk)
     const uint32_t *leaf_of_tri;
     uint32_t hits_resolved;         // k_raster_resolve ran: hit words carry leaf positions (and the kept flag), not triangle ids
     // the shard's columns as a lattice of the image (nx == 1, stride divides ny): y = lat_c0 + k * stride,

@@ -25,7 +25,7 @@
 #define RTS_SHADE_MIN_BLOCKS 6
 #endif
 #define RTS_RASTER_SMALL 160u          // footprints up to this many candidates are walked by their own thread
-#define RTS_RASTER_CHUNK 2048u         // candidates per row chunk of a large footprint
+#define RTS_RASTER_CHUNK 2048u         // candidates per row chunk of a large footprint, at most (WaveParams::raster_chunk: fewer in small launches)
 #define RTS_RASTER_LIMIT 16ull         // candidates per primary ray beyond which the BVH primary wave is used
 
 __device__ __forceinline__ bool raster_on(const WaveParams &P)
@@ -177,8 +177,11 @@ __device__ __forceinline__ bool tri_footprint(const WaveParams &P, unsigned pos,
             for (int k = 0; k < 3; k++) {
                 const int a = k, b = (k + 1) % 3;
                 const double A = -(ys[b] - ys[a]) * sg, B = (xs[b] - xs[a]) * sg;
-                // slack: 0.05 pixel along the edge normal plus the fp32 evaluation error of the edge function
-                const double C = -(A * xs[a] + B * ys[a]) + 0.05 * (fabs(A) + fabs(B)) + 1e-5 * (fabs(A * xs[a]) + fabs(B * ys[a]) + (fabs(A) + fabs(B)) * 64.0);
+                // slack: 0.05 pixel along the edge normal plus the fp32 evaluation error of the edge function; the last term
+                // covers k_raster_small's incremental evaluation along a row (at most 160 fp32 additions to a value below
+                // 322 (|A| + |B|): 160 * 2^-24 * 322 = 3.1e-3)
+                const double C = -(A * xs[a] + B * ys[a]) + 0.05 * (fabs(A) + fabs(B)) + 1e-5 * (fabs(A * xs[a]) + fabs(B * ys[a]) + (fabs(A) + fabs(B)) * 64.0) +
+                                 4e-3 * (fabs(A) + fabs(B));
                 F.ea[k] = (float)A; F.eb[k] = (float)B; F.ec[k] = (float)C;
             }
             F.use2d = true;
@@ -222,7 +225,10 @@ __device__ __forceinline__ void foot_test(const WaveParams &P, const TriFoot &F,
 __global__ void k_raster_setup(const __grid_constant__ WaveParams P)
 {
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
     unsigned long long area = 0;
+    unsigned c_pos = 0, c_n = 0, c_at = 0, c_rows = 0;    // this lane's large footprint: leaf position, chunks, first item, rows per chunk
+    int c_z0 = 0, c_z1 = 0;
     if (idx < raster_count(P)) {
         const unsigned pos = raster_pos(P, idx);
         TriFoot F;
@@ -230,21 +236,28 @@ __global__ void k_raster_setup(const __grid_constant__ WaveParams P)
             area = foot_area(F);
             if (area > RTS_RASTER_SMALL) {
                 const unsigned per_row = (unsigned)((F.y1 - F.y0) / F.ystep + 1);
-                const unsigned rows = max(1u, RTS_RASTER_CHUNK / per_row);
+                const unsigned rows = max(1u, P.raster_chunk / per_row);
                 // one reservation for all of the footprint's chunks (a triangle that fills the image has thousands:
-                // an atomic per chunk would serialise them on one thread), then independent stores
+                // an atomic per chunk would serialise them on one thread); the warp writes them together below
                 const unsigned n_chunks = (unsigned)(F.z1 - F.z0) / rows + 1u;
                 const unsigned at = atomicAdd(&P.raster_ctl->n_items, n_chunks);
                 if (at < P.raster_item_cap && n_chunks <= P.raster_item_cap - at) {
-                    for (unsigned c = 0; c < n_chunks; c++) {
-                        const int z = F.z0 + (int)(c * rows);
-                        RasterItem it; it.pos = pos; it.z0 = (unsigned)z; it.z1 = (unsigned)min(F.z1, z + (int)rows - 1); it.pad = 0;
-                        P.raster_items[at + c] = it;
-                    }
+                    c_pos = pos; c_n = n_chunks; c_at = at; c_rows = rows; c_z0 = F.z0; c_z1 = F.z1;
                 } else {
                     area = 1ull << 56;   // too many chunks: turn the path off
                 }
             }
+        }
+    }
+    for (unsigned todo = __ballot_sync(0xffffffffu, c_n != 0); todo; todo &= todo - 1u) {
+        const int src = __ffs(todo) - 1;
+        const unsigned pos = __shfl_sync(0xffffffffu, c_pos, src), n = __shfl_sync(0xffffffffu, c_n, src), at = __shfl_sync(0xffffffffu, c_at, src);
+        const unsigned rows = __shfl_sync(0xffffffffu, c_rows, src);
+        const int z0 = __shfl_sync(0xffffffffu, c_z0, src), z1 = __shfl_sync(0xffffffffu, c_z1, src);
+        for (unsigned c = lane; c < n; c += 32u) {
+            const int z = z0 + (int)(c * rows);
+            RasterItem it; it.pos = pos; it.z0 = (unsigned)z; it.z1 = (unsigned)min(z1, z + (int)rows - 1); it.pad = 0;
+            P.raster_items[at + c] = it;
         }
     }
 #pragma unroll
@@ -262,13 +275,25 @@ __global__ void k_raster_small(const __grid_constant__ WaveParams P)
     bool have = idx < raster_count(P) && tri_footprint(P, raster_pos(P, idx), F) && foot_area(F) <= RTS_RASTER_SMALL;
     int y = have ? F.y0 : 0, z = have ? F.z0 : 1, k = have ? F.k0 : 0;
     const int z1 = have ? F.z1 : 0;
+    // the three edge functions at the lane's current pixel: set at the start of a row, then one addition per step (the
+    // slack of tri_footprint covers the rounding of up to 160 of them); without edge functions every pixel of the box passes
+    const bool use2d = have && F.use2d;
+    const float da0 = use2d ? F.ea[0] * (float)F.ystep : 0.f, da1 = use2d ? F.ea[1] * (float)F.ystep : 0.f, da2 = use2d ? F.ea[2] * (float)F.ystep : 0.f;
+    float ex0 = use2d ? F.ec[0] : 0.f, ex1 = use2d ? F.ec[1] : 0.f, ex2 = use2d ? F.ec[2] : 0.f;      // (y0, z0): fy = fz = 0
     while (__any_sync(0xffffffffu, z <= z1)) {
         unsigned rel = 0;
         bool found = false;
         while (z <= z1) {
-            const bool ok = foot_inside2d(F, y, z) && pixel_local(P, (unsigned)y, (unsigned)z, k, rel);
+            const bool ok = fminf(fminf(ex0, ex1), ex2) >= 0.f && pixel_local(P, (unsigned)y, (unsigned)z, k, rel);
             y += F.ystep; k++;
-            if (y > F.y1) { y = F.y0; k = F.k0; z++; }
+            ex0 += da0; ex1 += da1; ex2 += da2;
+            if (y > F.y1) {
+                y = F.y0; k = F.k0; z++;
+                if (use2d) {
+                    const float fz = (float)(z - F.z0);
+                    ex0 = fmaf(F.eb[0], fz, F.ec[0]); ex1 = fmaf(F.eb[1], fz, F.ec[1]); ex2 = fmaf(F.eb[2], fz, F.ec[2]);
+                }
+            }
             if (ok) { found = true; break; }
         }
         if (found) foot_test(P, F, rel);

@@ -1155,6 +1155,10 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     p.raster_ctl = (RasterCtl *)e->d_raster_ctl;
     p.raster_items = (RasterItem *)e->d_raster_items;
     p.raster_item_cap = RTS_RASTER_ITEM_CAP;
+    // a warp walks a chunk 32 candidates at a time: 2048 per chunk in large launches, but a small launch whose few
+    // triangles fill the image (flat plate, 65 k rays: 64 chunks = 64 warps x 64 rounds, 0.06 ms) needs more, shorter ones
+    p.raster_chunk = 128u;
+    while (p.raster_chunk < RTS_RASTER_CHUNK && (uint64_t)p.raster_chunk * 2048u < p.n_primary) p.raster_chunk *= 2u;
     p.leaf_of_tri = e->d_leaf_of_tri;
     p.raster_list = nullptr; p.raster_list_count = 0; p.raster_skip = nullptr; p.raster_static = nullptr;
     RTS_CUDA(cudaMemsetAsync(e->d_raster_ctl, 0, sizeof(RasterCtl), st));
