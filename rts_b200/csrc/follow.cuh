@@ -151,7 +151,10 @@ __device__ __noinline__ void finish_stragglers(const WaveParams &P, int *stk, co
 }
 
 template <bool RECORDS, bool TABLES = false>
-__global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_WAVE_MIN_BLOCKS) k_primary_follow(const __grid_constant__ WaveParams P)
+#ifndef RTS_FOLLOW_MIN_BLOCKS
+#define RTS_FOLLOW_MIN_BLOCKS 7      // 72 registers (400 B of spills, outside the walk): 6 / 7 / 8 CTAs per SM: 1.631 / 1.601 / 1.615 ms
+#endif
+__global__ void __launch_bounds__(RTS_WAVE_BLOCK, RTS_FOLLOW_MIN_BLOCKS) k_primary_follow(const __grid_constant__ WaveParams P)
 {
     if (!raster_on(P)) return;
     constexpr unsigned FULL = 0xffffffffu;

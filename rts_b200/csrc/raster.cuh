@@ -267,7 +267,10 @@ __global__ void k_raster_setup(const __grid_constant__ WaveParams P)
 
 // Pass 2a: one thread per triangle with a small footprint.  Each lane first scans forward to its next candidate
 // that passes the cheap 2D test, then the warp runs the fp64 test together.
-__global__ void k_raster_small(const __grid_constant__ WaveParams P)
+#ifndef RTS_RASTER_MIN_BLOCKS
+#define RTS_RASTER_MIN_BLOCKS 7      // 72 registers: the kernel is latency-bound (scattered direction loads, hit-word atomics); 5 / 6 / 7 / 8 CTAs: wave 0 2.199 / 2.170 / 2.145 / 2.156 ms
+#endif
+__global__ void __launch_bounds__(128, RTS_RASTER_MIN_BLOCKS) k_raster_small(const __grid_constant__ WaveParams P)
 {
     if (!raster_on(P)) return;
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
