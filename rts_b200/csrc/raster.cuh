@@ -221,61 +221,63 @@ __device__ __forceinline__ void foot_test(const WaveParams &P, const TriFoot &F,
     atomicMin(P.hits + rel, ((unsigned long long)__float_as_uint(tf) << 32) | (unsigned long long)F.id);
 }
 
-// Pass 1: summed footprint (the guard) and the row chunks of the large footprints.
-__global__ void k_raster_setup(const __grid_constant__ WaveParams P)
+// Pass 1 (part of k_raster_small): summed footprint (the guard) and the row chunks of the large footprints.  Called by every
+// thread of the block with its triangle's footprint (ok: it has one).
+__device__ __forceinline__ void raster_setup(const WaveParams &P, bool ok, unsigned pos, const TriFoot &F)
 {
-    const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long area = 0;
     unsigned c_pos = 0, c_n = 0, c_at = 0, c_rows = 0;    // this lane's large footprint: leaf position, chunks, first item, rows per chunk
     int c_z0 = 0, c_z1 = 0;
-    if (idx < raster_count(P)) {
-        const unsigned pos = raster_pos(P, idx);
-        TriFoot F;
-        if (tri_footprint(P, pos, F)) {
-            area = foot_area(F);
-            if (area > RTS_RASTER_SMALL) {
-                const unsigned per_row = (unsigned)((F.y1 - F.y0) / F.ystep + 1);
-                const unsigned rows = max(1u, P.raster_chunk / per_row);
-                // one reservation for all of the footprint's chunks (a triangle that fills the image has thousands:
-                // an atomic per chunk would serialise them on one thread); the warp writes them together below
-                const unsigned n_chunks = (unsigned)(F.z1 - F.z0) / rows + 1u;
-                const unsigned at = atomicAdd(&P.raster_ctl->n_items, n_chunks);
-                if (at < P.raster_item_cap && n_chunks <= P.raster_item_cap - at) {
-                    c_pos = pos; c_n = n_chunks; c_at = at; c_rows = rows; c_z0 = F.z0; c_z1 = F.z1;
-                } else {
-                    area = 1ull << 56;   // too many chunks: turn the path off
-                }
+    if (ok) {
+        area = foot_area(F);
+        if (area > RTS_RASTER_SMALL) {
+            const unsigned per_row = (unsigned)((F.y1 - F.y0) / F.ystep + 1);
+            const unsigned rows = max(1u, P.raster_chunk / per_row);
+            // one reservation for all of the footprint's chunks (a triangle that fills the image has thousands:
+            // an atomic per chunk would serialise them on one thread); the warp writes them together below
+            const unsigned n_chunks = (unsigned)(F.z1 - F.z0) / rows + 1u;
+            const unsigned at = atomicAdd(&P.raster_ctl->n_items, n_chunks);
+            if (at < P.raster_item_cap && n_chunks <= P.raster_item_cap - at) {
+                c_pos = pos; c_n = n_chunks; c_at = at; c_rows = rows; c_z0 = F.z0; c_z1 = F.z1;
+            } else {
+                area = 1ull << 56;   // too many chunks: turn the path off
             }
         }
     }
     for (unsigned todo = __ballot_sync(0xffffffffu, c_n != 0); todo; todo &= todo - 1u) {
         const int src = __ffs(todo) - 1;
-        const unsigned pos = __shfl_sync(0xffffffffu, c_pos, src), n = __shfl_sync(0xffffffffu, c_n, src), at = __shfl_sync(0xffffffffu, c_at, src);
+        const unsigned spos = __shfl_sync(0xffffffffu, c_pos, src), n = __shfl_sync(0xffffffffu, c_n, src), at = __shfl_sync(0xffffffffu, c_at, src);
         const unsigned rows = __shfl_sync(0xffffffffu, c_rows, src);
         const int z0 = __shfl_sync(0xffffffffu, c_z0, src), z1 = __shfl_sync(0xffffffffu, c_z1, src);
         for (unsigned c = lane; c < n; c += 32u) {
             const int z = z0 + (int)(c * rows);
-            RasterItem it; it.pos = pos; it.z0 = (unsigned)z; it.z1 = (unsigned)min(z1, z + (int)rows - 1); it.pad = 0;
+            RasterItem it; it.pos = spos; it.z0 = (unsigned)z; it.z1 = (unsigned)min(z1, z + (int)rows - 1); it.pad = 0;
             P.raster_items[at + c] = it;
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) area += __shfl_xor_sync(0xffffffffu, area, o);
-    if ((threadIdx.x & 31) == 0 && area) atomicAdd(&P.raster_ctl->area, area);
+    if (lane == 0 && area) atomicAdd(&P.raster_ctl->area, area);
 }
 
-// Pass 2a: one thread per triangle with a small footprint.  Each lane first scans forward to its next candidate
-// that passes the cheap 2D test, then the warp runs the fp64 test together.
+// Passes 1 + 2a: one thread per triangle — its footprint (summed for the guard; cut into row chunks for k_raster_big when
+// large), then the small footprints are walked: each lane first scans forward to its next candidate that passes the
+// cheap 2D test, then the warp runs the fp64 test together.  (One kernel since round 2: a separate set-up pass computed
+// every footprint a second time, 0.03 ms per million triangles.)
 #ifndef RTS_RASTER_MIN_BLOCKS
 #define RTS_RASTER_MIN_BLOCKS 7      // 72 registers: the kernel is latency-bound (scattered direction loads, hit-word atomics); 5 / 6 / 7 / 8 CTAs: wave 0 2.199 / 2.170 / 2.145 / 2.156 ms
 #endif
 __global__ void __launch_bounds__(128, RTS_RASTER_MIN_BLOCKS) k_raster_small(const __grid_constant__ WaveParams P)
 {
-    if (!raster_on(P)) return;
+    // (no guard here: the guard is the sum this very kernel forms, and a small footprint is at most 160 candidates — what
+    // can explode is the large footprints' work, and k_raster_big and the shading pass do look at the guard)
     const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
     TriFoot F;
-    bool have = idx < raster_count(P) && tri_footprint(P, raster_pos(P, idx), F) && foot_area(F) <= RTS_RASTER_SMALL;
+    const unsigned pos = idx < raster_count(P) ? raster_pos(P, idx) : 0u;
+    bool have = idx < raster_count(P) && tri_footprint(P, pos, F);
+    raster_setup(P, have, pos, F);
+    have = have && foot_area(F) <= RTS_RASTER_SMALL;
     int y = have ? F.y0 : 0, z = have ? F.z0 : 1, k = have ? F.k0 : 0;
     const int z1 = have ? F.z1 : 0;
     // the three edge functions at the lane's current pixel: set at the start of a row, then one addition per step (the

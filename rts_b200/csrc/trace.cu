@@ -1143,10 +1143,9 @@ static void launch_footprints(rts_engine *e, const WaveParams &p, unsigned count
     const unsigned bs = 128;
     const unsigned blocks = (count + bs - 1) / bs;
     if (!blocks) return;
-    k_raster_setup<<<blocks, bs, 0, e->stream>>>(p);
-    k_raster_small<<<blocks, bs, 0, e->stream>>>(p);
+    k_raster_small<<<blocks, bs, 0, e->stream>>>(p);       // footprints + guard + the small footprints' candidates
     k_raster_big<<<e->num_sms * 8, bs, 0, e->stream>>>(p);
-    e->launches += 3;
+    e->launches += 2;
 }
 
 int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_batch)

@@ -13,9 +13,9 @@ tail -c 1500 gpurun_out/bench_n1.json
 python bench.py --steps 2 --warmup 1 --quick > gpurun_out/plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --quick > gpurun_out/ncu1.log 2>&1
-# one whole step's wave / projection kernels (9 launches per from-scratch step: directions, 3 footprint kernels, k_primary_follow,
+# one whole step's wave / projection kernels (8 launches per from-scratch step: directions, 2 footprint kernels, k_primary_follow,
 # the BVH primary wave that returns at once, 3 later waves): skip the warm-up step and the first timed step of the value leg
-ncu --set full --clock-control none --import-source on -k 'regex:k_wave|k_raster|k_primary|k_traverse|k_shade' -s 18 -c 9 -f -o gpurun_out/prof -- \
+ncu --set full --clock-control none --import-source on -k 'regex:k_wave|k_raster|k_primary|k_traverse|k_shade' -s 16 -c 8 -f -o gpurun_out/prof -- \
     python bench.py --steps 2 --warmup 1 --quick > gpurun_out/ncu2.log 2>&1
 python tools/config_probe.py > gpurun_out/config_probe.jsonl 2> gpurun_out/config_probe.err
 cut -c1-100 gpurun_out/config_probe.jsonl
