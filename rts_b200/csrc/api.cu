@@ -114,7 +114,11 @@ extern "C" int rts_create(int device, rts_engine **out)
     rts_engine *e = new rts_engine();
     e->device = device;
     e->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    // the engine's own stream outranks side_dirs (created below at the lowest priority): the direction pass should take what
+    // the thin last waves of the previous pulse leave, not the other way round (a caller's stream: see INTEGRATION.md)
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&e->own_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
         delete e;
         return rts_fail(RTS_ERR_CUDA, "cudaStreamCreate failed");
     }
@@ -139,7 +143,7 @@ extern "C" int rts_create(int device, rts_engine **out)
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
         if (cudaStreamCreateWithPriority(&e->side_bvh, cudaStreamNonBlocking, hi) != cudaSuccess) e->side_bvh = nullptr;
-        if (cudaStreamCreateWithFlags(&e->side_dirs, cudaStreamNonBlocking) != cudaSuccess) e->side_dirs = nullptr;
+        if (cudaStreamCreateWithPriority(&e->side_dirs, cudaStreamNonBlocking, lo) != cudaSuccess) e->side_dirs = nullptr;
         for (cudaEvent_t *ev : {&e->ev_dirs_free, &e->ev_dirs_done, &e->ev_bvh_fork, &e->ev_bvh_done}) cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
         cudaGetLastError();
     }

@@ -176,3 +176,14 @@ def bins_excluding(engine, world_targets, spec, flagged_k, gpu_flags=0, use_bvh=
         g.append(engine.bins().copy())
         o.append(O.trace_bins(world_targets, sub, use_bvh=use_bvh)[0])
     return merge_bins(g), merge_bins(o), len(list(flagged_k))
+
+
+def assert_bins_match(engine, world_targets, spec, orc, use_bvh=True, gpu_flags=0, max_flagged=64):
+    """Bins of the whole launch against the oracle's with the oracle's window-edge rays left out of BOTH sides (sub-shards
+    around them): nothing is skipped, and the number of rays left out is bounded.  Returns that number."""
+    flagged = np.nonzero((np.asarray(orc["edge"]) & O.EDGE_WINDOW) != 0)[0]
+    assert len(flagged) <= max_flagged, f"{len(flagged)} window-edge rays"
+    gb, ob, n_out = bins_excluding(engine, world_targets, spec, flagged, gpu_flags=gpu_flags, use_bvh=use_bvh)
+    assert_bins_close(compare_bins(gb, ob))
+    assert len(gb) == len(ob)
+    return n_out

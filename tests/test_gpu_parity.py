@@ -43,10 +43,8 @@ def test_records_and_bins_match_oracle(engine, name):
     parity.assert_records_equal(cmp)
     for k in ("segments", "hits", "shaded_hits", "refracted"):
         assert st[k] == orc["stats"][k], k
-    if cmp["window_edge_rays"] == 0:
-        assert st["captured"] == orc["stats"]["captured"]
-        obins, _ = O.trace_bins(targets, spec, use_bvh=False)
-        parity.assert_bins_close(parity.compare_bins(gbins, obins))
+    n_out = parity.assert_bins_match(engine, targets, spec, orc, use_bvh=False)      # window-edge rays left out of both sides
+    assert abs(int(st["captured"]) - int(orc["stats"]["captured"])) <= n_out
     assert engine.check_bvh() == 0
 
 
@@ -194,9 +192,7 @@ def test_C3_ship_100k_triangles_refraction(engine):
     for k in ("segments", "hits", "shaded_hits", "refracted"):
         assert st[k] == orc["stats"][k], k
     assert st["refracted"] > 10000
-    if cmp["window_edge_rays"] == 0:
-        obins, _ = O.trace_bins(targets, spec, use_bvh=True)
-        parity.assert_bins_close(parity.compare_bins(engine.bins(), obins))
+    parity.assert_bins_match(engine, targets, spec, orc, use_bvh=True)
 
 
 def test_C4_terrain_1M_triangles(engine):
@@ -208,14 +204,15 @@ def test_C4_terrain_1M_triangles(engine):
     assert engine.check_bvh() == 0
     spec = ms.spec_for(pulse)
     st = engine.trace(spec, L.RTS_OUT_BINS)
-    gbins = engine.bins()
-    obins, ost = O.trace_bins(ms.world_targets(pulse), spec, use_bvh=True)
-    for k in ("primary_rays", "segments", "hits", "shaded_hits"):
+    world = ms.world_targets(pulse)
+    orc = O.trace_shard(world, spec, use_bvh=True, arrays=False)      # counters + per-ray edge flags, no records
+    ost = orc["stats"]
+    assert st["primary_rays"] == orc["n_shard"] == 1024 * 1024
+    for k in ("segments", "hits", "shaded_hits"):
         assert st[k] == ost[k], k
-    # window-edge rays cannot be identified without per-ray records here: allow a handful of capture flips
-    assert abs(int(st["captured"]) - int(ost["captured"])) <= 2
-    if st["captured"] == ost["captured"]:
-        parity.assert_bins_close(parity.compare_bins(gbins, obins))
+    # the oracle's window-edge rays (fp32 atan2f, libdevice vs glibc) are left out of both sides' bins; only they may flip a capture
+    n_out = parity.assert_bins_match(engine, world, spec, orc, use_bvh=True, max_flagged=16)
+    assert abs(int(st["captured"]) - int(ost["captured"])) <= n_out
     # size-independent properties at the full 16.7M-ray grid
     spec_full = scenes.terrain_scene(n=4096, cells_x=8, cells_y=4, movers=0).spec
     spec_full.rx, spec_full.targ_vel = spec.rx, spec.targ_vel
@@ -505,9 +502,17 @@ def test_kept_hits_over_consecutive_pulses_match_the_oracle(engine):
         parity.assert_records_equal(cmp)
         for key in ("segments", "hits", "shaded_hits"):
             assert st[key] == orc["stats"][key], (pulse, key)
-        if cmp["window_edge_rays"] == 0:
+        flagged = np.nonzero((np.asarray(orc["edge"]) & O.EDGE_WINDOW) != 0)[0]
+        if len(flagged) == 0:       # the bins of the very pulse that used the kept hits
             obins, _ = O.trace_bins(world, spec, use_bvh=True)
             parity.assert_bins_close(parity.compare_bins(engine.bins(), obins))
+        else:                       # window-edge rays left out of both sides — on a second engine: sub-shard launches would reset what this one keeps
+            aux = L.Engine(0)
+            try:
+                aux.set_targets(world)
+                parity.assert_bins_match(aux, world, spec, orc, use_bvh=True)
+            finally:
+                aux.close()
         seen_kept += 1 if st["kept_reflections"] > 0 else 0
         if k in (1, 2, 3, 5, 6, 7):
             assert 0 < st["kept_reflections"] < st["segments"] - st["primary_rays"]   # most, but not all: movers in the way
