@@ -79,13 +79,19 @@ const char *rts_version(void);
  * [0] rts_ray_record [1] rts_target_mesh [2] rts_rx_sphere [3] rts_rx_desc [4] rts_pulse
  * [5] rts_bin [6] rts_stats [7] rts_pose [8] rts_response [9] rts_sizes */
 int         rts_abi_sizes(uint32_t sizes[10]);
-/* Run subsequent work of this engine on a caller-provided cudaStream_t (NULL = engine's own). */
+/* Run subsequent work of this engine on a caller-provided cudaStream_t (NULL = engine's own).  The engine keeps two side
+ * streams of its own, ordered against this one by events (the direction pass of the projected primary wave, at the lowest
+ * stream priority, and the BVH refit above the moving triangles); a caller's stream created above the lowest priority
+ * (cudaStreamCreateWithPriority) lets the direction pass of the next pulse fill what the last waves of the previous pulse
+ * leave instead of competing with them.  Waits for the engine's earlier work. */
 int         rts_set_stream(rts_engine *e, void *cuda_stream);
 /* Tuning / test switches (no counterpart in the reference, whose only knobs are MaxThreads / MaxBlocks,
  * ray_tracer.cpp:512).  The environment variable RTS_<NAME> gives an option its initial value when the engine is created;
  * the environment is never read again afterwards.  Names: "bvh" (0 = choose by SAH cost, 1 = Morton radix tree, 2 = PLOC),
  * "leaf_max" (1..8), "no_chain", "no_raster", "no_tiles", "one_ended_queue", "debug_raster", "no_static_hits",
- * "no_kept_reflections", "no_split", "split_below" (rays), "no_graph", "batch" (primaries per batch, 0 = 2^24),
+ * "no_kept_reflections", "no_split", "split_below" (rays), "no_graph", "no_follow", "no_smem_bins", "no_overlap" (1 = no
+ * side streams: every kernel of a pulse on the engine's stream), "debug_timeline" (rts_sync prints when the direction pass,
+ * the footprint kernels, the shading pass and the later waves of the last pulses ran), "batch" (primaries per batch, 0 = 2^24),
  * "hash_bins" (1 = sparse bin table also where a dense one would fit), "hash_log2" (log2 of its slots, default 22). */
 int         rts_set_option(rts_engine *e, const char *name, int64_t value);
 
