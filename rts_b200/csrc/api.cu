@@ -80,6 +80,7 @@ static int set_option(rts_engine *e, const char *name, long long v)
     else if (!strcmp(name, "no_graph")) k.no_graph = v != 0;
     else if (!strcmp(name, "no_follow")) k.no_follow = v != 0;
     else if (!strcmp(name, "no_smem_bins")) k.no_smem_bins = v != 0;
+    else if (!strcmp(name, "no_split_raster")) k.no_split_raster = v < 0 ? -1 : (v != 0);   // -1: split even when nothing is in flight (tests)
     else if (!strcmp(name, "debug_timeline")) { k.debug_timeline = v != 0; e->tl_n = 0; }
     else if (!strcmp(name, "no_overlap")) { bvh_join(e); k.no_overlap = v != 0; }
     else if (!strcmp(name, "hash_bins")) k.hash_bins = v != 0;
@@ -125,7 +126,7 @@ extern "C" int rts_create(int device, rts_engine **out)
     e->stream = e->own_stream;
     // tuning / test switches: the environment is read here, once; afterwards only rts_set_option changes them
     for (const char *name : {"bvh", "leaf_max", "no_chain", "no_raster", "no_tiles", "one_ended_queue", "debug_raster", "no_static_hits",
-                             "no_kept_reflections", "no_split", "split_below", "no_graph", "no_follow", "no_smem_bins", "no_overlap", "debug_timeline", "batch", "hash_bins", "hash_log2"}) {
+                             "no_kept_reflections", "no_split", "split_below", "no_graph", "no_follow", "no_smem_bins", "no_overlap", "debug_timeline", "no_split_raster", "batch", "hash_bins", "hash_log2"}) {
         std::string env = "RTS_";
         for (const char *c = name; *c; c++) env += (char)toupper(*c);
         if (const char *v = getenv(env.c_str())) {
@@ -716,6 +717,10 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
             }
             int rc = trace_launch_wave(e, Q, w == 0, records);
             if (rc) return rc;
+            // the shading pass is the last reader of the direction / hit-word buffers, the BVH primary wave behind it (which
+            // returns at once unless the guard tripped) the last reader of the footprint passes' control blocks: from here on
+            // the next batch's or pulse's direction pass and static footprints may run on side_dirs
+            if (w == 0 && use_raster && e->side_dirs) { cudaEventRecord(e->ev_dirs_free, st); e->dirs_free_valid = true; }
             waves++;
         }
         if (single_batch) cudaEventRecord(e->wave_ev[e->n_waves], st);
@@ -729,7 +734,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     if (use_raster) {
         RTS_CUDA(cudaMemcpyAsync(&e->h_rb->raster, e->d_raster_ctl, sizeof(RasterCtl), cudaMemcpyDeviceToHost, st));
         e->h_rb->raster_static.area = 0;
-        if (e->static_valid)
+        if (e->static_valid || e->split_static)
             RTS_CUDA(cudaMemcpyAsync(&e->h_rb->raster_static, e->d_raster_ctl_static, sizeof(RasterCtl), cudaMemcpyDeviceToHost, st));
     }
     e->pulse_pending = true;

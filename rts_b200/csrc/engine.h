@@ -258,7 +258,7 @@ struct Comm {
 // Tuning / test switches: read from the environment once in rts_create, changed afterwards only through rts_set_option.
 struct Knobs {
     int no_chain = 0, no_raster = 0, no_tiles = 0, one_ended_queue = 0, debug_raster = 0, no_static_hits = 0,
-        no_kept_reflections = 0, no_split = 1, no_graph = 0, no_follow = 0, no_smem_bins = 0, no_overlap = 0, debug_timeline = 0;
+        no_kept_reflections = 0, no_split = 1, no_graph = 0, no_follow = 0, no_smem_bins = 0, no_overlap = 0, debug_timeline = 0, no_split_raster = 0;
     long long batch = 0;           // 0 = default 2^24 primaries per batch
     int hash_bins = 0;             // 1: sparse (hashed) bins also where a dense table would fit
     uint32_t hash_log2 = 22;       // slots of the sparse bin table
@@ -282,6 +282,7 @@ struct rts_engine {
     cudaStream_t side_dirs = nullptr, side_bvh = nullptr;
     cudaEvent_t ev_dirs_free = nullptr, ev_dirs_done = nullptr, ev_bvh_fork = nullptr, ev_bvh_done = nullptr;
     bool dirs_free_valid = false, bvh_join_pending = false;
+    bool split_static = false;     // this pulse projected the never-moving triangles on side_dirs (its own RasterCtl: d_raster_ctl_static)
     // knob debug_timeline: timestamps of up to 16 pulses' direction pass / footprint kernels / shading pass, printed by rts_sync
     cudaEvent_t tl_ev[16][7] = {};   // + start and end of the later waves
     int tl_n = 0;

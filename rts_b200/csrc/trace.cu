@@ -1138,13 +1138,14 @@ int trace_raster_alloc(rts_engine *e, uint64_t batch)
 }
 
 // One footprint pass (setup + small + large footprints) over the triangles p selects.
-static void launch_footprints(rts_engine *e, const WaveParams &p, unsigned count)
+static void launch_footprints(rts_engine *e, const WaveParams &p, unsigned count, cudaStream_t stream = nullptr)
 {
+    const cudaStream_t fs = stream ? stream : e->stream;
     const unsigned bs = 128;
     const unsigned blocks = (count + bs - 1) / bs;
     if (!blocks) return;
-    k_raster_small<<<blocks, bs, 0, e->stream>>>(p);       // footprints + guard + the small footprints' candidates
-    k_raster_big<<<e->num_sms * 8, bs, 0, e->stream>>>(p);
+    k_raster_small<<<blocks, bs, 0, fs>>>(p);       // footprints + guard + the small footprints' candidates
+    k_raster_big<<<e->num_sms * 8, bs, 0, fs>>>(p);
     e->launches += 2;
 }
 
@@ -1179,6 +1180,14 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     const bool same_launch = reuse && e->dirs_valid && memcmp(&key, &e->dirs_key, sizeof(key)) == 0;
     for (int a = 0; a < 3; a++) p.dirs[a] = e->d_dirs + (size_t)a * e->raster_alloc;
     p.hits = e->d_hits;
+    // head_open: work of this batch is in flight on side_dirs that the engine's stream has not been told to wait for yet
+    bool head_open = false;
+    auto join_head = [&]() {
+        if (!head_open) return;
+        cudaEventRecord(e->ev_dirs_done, e->side_dirs);
+        cudaStreamWaitEvent(st, e->ev_dirs_done, 0);
+        head_open = false;
+    };
     if (!same_launch) {
         // on its own stream (engine.h: side_dirs): the two buffers are free once the previous shading pass is done, and
         // nothing else of this stream — the previous pulse's thin waves and bin emission, this pulse's pose update — has to
@@ -1193,10 +1202,7 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
         if (tl) cudaEventRecord(tl[0], side ? e->side_dirs : st);
         k_primary_dirs<<<e->num_sms * 32, RTS_DIRS_BLOCK, 0, side ? e->side_dirs : st>>>(p);   // also resets the hit words
         if (tl) cudaEventRecord(tl[1], side ? e->side_dirs : st);
-        if (side) {
-            cudaEventRecord(e->ev_dirs_done, e->side_dirs);
-            cudaStreamWaitEvent(st, e->ev_dirs_done, 0);
-        }
+        head_open = side;
         e->dirs_key = key;
         e->dirs_valid = true;
         e->static_valid = false;
@@ -1205,12 +1211,38 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     // The closest hits among the triangles that never move are the same from pulse to pulse as long as the launch, the
     // scene and the set of moving targets are: they are kept (static pass once), and a pulse only projects the
     // triangles of the moving targets on top of a copy.  Needs the moving-target lists of the partial refit (bvh.cu).
-    if (tl) cudaEventRecord(tl[2], st);
     uint32_t n_moving = 0;
     for (uint32_t k = 0; k < e->n_targets; k++) n_moving += e->moving[k] ? 1u : 0u;
     const bool cacheable = reuse && single_batch && !e->knobs.no_static_hits && (n_moving == 0 || e->partial_ready);
     e->coh_on = false;
-    if (cacheable) {
+    e->split_static = false;
+    // From scratch with moving targets: the triangles that never move are projected on side_dirs, behind the direction pass
+    // — their records are not touched by the pose update, so nothing of this stream has to be waited for, and the pass
+    // (most of the footprint work) runs beside the previous pulse's thin last waves, its bin emission and this pulse's
+    // pose update; only the moving targets' triangles are projected here, behind the update.  (A moving triangle's record
+    // may be rewritten while the static pass looks at its target id to skip it: the id is the same before and after.)
+    // Only when there is something to run beside: an earlier batch of this launch, or a previous pulse still in flight (a
+    // host that reads every pulse's bins before it enqueues the next gains nothing, and would pay the second pass's launch
+    // latency: 0.07 ms).
+    const bool in_flight = p.batch_base > 0 || (e->have_pulse && cudaEventQuery(e->ev[1]) == cudaErrorNotReady);
+    const bool split = head_open && !cacheable && n_moving > 0 && e->partial_ready && e->n_dt > 0 && !e->knobs.no_split_raster &&
+                       (in_flight || e->knobs.no_split_raster < 0);
+    if (tl && !split) cudaEventRecord(tl[2], head_open && !cacheable && n_moving == 0 ? e->side_dirs : st);   // (approximate when the engine's stream still has to wait for the directions)
+    if (split) {
+        RTS_CUDA(cudaMemsetAsync(e->d_raster_ctl_static, 0, sizeof(RasterCtl), e->side_dirs));
+        WaveParams q = p;
+        q.raster_ctl = (RasterCtl *)e->d_raster_ctl_static;
+        q.raster_skip = e->d_moving;
+        if (tl) cudaEventRecord(tl[2], e->side_dirs);
+        launch_footprints(e, q, p.n_tris, e->side_dirs);
+        join_head();
+        p.raster_static = (const RasterCtl *)e->d_raster_ctl_static;
+        p.raster_list = e->d_tlist; p.raster_list_count = e->n_dt;
+        launch_footprints(e, p, e->n_dt);
+        e->static_valid = false;
+        e->split_static = true;
+    } else if (cacheable) {
+        join_head();
         const bool valid = e->static_valid && same_launch && e->static_scene_version == e->scene_version &&
                            e->static_moving_version == e->moving_version;
         if (!valid) {
@@ -1243,11 +1275,24 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
             p.raster_list = e->d_tlist; p.raster_list_count = e->n_dt;
             launch_footprints(e, p, e->n_dt);
         }
+    } else if (head_open && n_moving == 0) {
+        // nothing moves: the whole pass behind the direction pass, beside the previous pulse's last waves (with the control
+        // block that is cleared on that stream; the one of this stream stays empty)
+        RTS_CUDA(cudaMemsetAsync(e->d_raster_ctl_static, 0, sizeof(RasterCtl), e->side_dirs));
+        WaveParams q = p;
+        q.raster_ctl = (RasterCtl *)e->d_raster_ctl_static;
+        launch_footprints(e, q, p.n_tris, e->side_dirs);
+        join_head();
+        p.raster_static = (const RasterCtl *)e->d_raster_ctl_static;
+        e->static_valid = false;
+        e->split_static = true;
     } else {
+        join_head();
         if (same_launch) RTS_CUDA(cudaMemsetAsync(e->d_hits, 0xff, sizeof(unsigned long long) * p.n_primary, st));
         e->static_valid = false;
         launch_footprints(e, p, p.n_tris);
     }
+    join_head();
     // the resolve pass exists to flag the rays whose first reflection can be answered from kept hits; without that the
     // shading pass looks the leaf position up itself
     p.hits_resolved = e->coh_on ? 1u : 0u;
@@ -1281,8 +1326,6 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     RTS_CUDA(cudaGetLastError());
     e->launches += 1;
     if (tl) cudaEventRecord(tl[4], st);
-    // the shading pass is the last reader of the direction / hit-word buffers
-    if (e->side_dirs) { cudaEventRecord(e->ev_dirs_free, st); e->dirs_free_valid = true; }
     return RTS_OK;
 }
 

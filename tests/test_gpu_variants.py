@@ -1,7 +1,8 @@
 """The alternative forms of the bounce waves kept behind options (rts_set_option) give the same answers as the default:
 split later waves (k_traverse + k_shade_wave over the quantised nodes), primary shading without the in-place first
 reflection (no_follow), global-atomics-only bins (no_smem_bins), BVH primary wave (no_raster), everything on one stream
-(no_overlap: no side streams for the direction pass and the refit).  Records bit-equal, bins
+(no_overlap: no side streams for the direction pass and the refit), never-moving and moving triangles projected in one
+pass (no_split_raster 1) or always in two (-1; by default in two only while an earlier pulse or batch is in flight).  Records bit-equal, bins
 equal in the exact fields and to 1e-12 in the sums (fp64 atomics commute, their rounding order does not)."""
 import numpy as np
 import pytest
@@ -19,7 +20,7 @@ def _run(engine, spec, flags):
     return st, engine.bins().copy()
 
 
-@pytest.mark.parametrize("option,value", [("no_split", 0), ("no_follow", 1), ("no_smem_bins", 1), ("no_raster", 1), ("no_overlap", 1)])
+@pytest.mark.parametrize("option,value", [("no_split", 0), ("no_follow", 1), ("no_smem_bins", 1), ("no_raster", 1), ("no_overlap", 1), ("no_split_raster", 1), ("no_split_raster", -1)])
 @pytest.mark.parametrize("scene", ["terrain", "trihedral", "slab"])
 def test_option_gives_the_default_answers(engine, option, value, scene):
     if scene == "terrain":
@@ -35,7 +36,7 @@ def test_option_gives_the_default_answers(engine, option, value, scene):
     st0, bins0 = _run(engine, spec, L.RTS_OUT_BINS)
     engine.trace(spec, L.RTS_OUT_RECORDS | L.RTS_NO_REUSE)
     rec0 = engine.records()
-    default = {"no_split": 1, "no_follow": 0, "no_smem_bins": 0, "no_raster": 0, "no_overlap": 0}[option]
+    default = {"no_split": 1, "no_follow": 0, "no_smem_bins": 0, "no_raster": 0, "no_overlap": 0, "no_split_raster": 0}[option]
     try:
         engine.set_option(option, value)
         if option == "no_split":
