@@ -63,3 +63,37 @@ def test_option_gives_the_default_answers(engine, option, value, scene):
                 assert a[f].tobytes() == b[f].tobytes(), f
         else:
             assert a.tobytes() == b.tobytes()
+
+
+@pytest.mark.parametrize("reuse", [False, True])
+def test_pulses_enqueued_back_to_back_equal_pulses_traced_alone(engine, reuse):
+    """Pulses of a moving scene enqueued without waiting (RTS_ASYNC): the next pulse's direction pass and static footprints
+    run on the library's side stream beside the previous pulse's last waves, its refit beside the footprint kernels.  The
+    bins of the last pulse of every prefix equal the bins of that pulse traced with nothing in flight, on one stream."""
+    ms = scenes.terrain_scene(n=384, cells_x=96, cells_y=48, movers=6, n_rx=2)
+    engine.set_targets(ms.base)
+    flags = L.RTS_OUT_BINS | (0 if reuse else L.RTS_NO_REUSE)
+    pulses = [0, 3, 1, 7, 2, 5]
+    alone = {}
+    engine.set_option("no_overlap", 1)
+    try:
+        for p in pulses:
+            engine.set_poses(*ms.poses(p))
+            st = engine.trace(ms.spec_for(p), flags | L.RTS_NO_REUSE)
+            alone[p] = (st, engine.bins().copy())
+    finally:
+        engine.set_option("no_overlap", 0)
+    for last in range(1, len(pulses) + 1):
+        for p in pulses[:last]:
+            engine.set_poses(*ms.poses(p))
+            engine.trace(ms.spec_for(p), flags | L.RTS_ASYNC)
+        st = engine.stats()                     # waits for the last pulse
+        bins = engine.bins().copy()
+        st0, bins0 = alone[pulses[last - 1]]
+        for k in ("segments", "hits", "shaded_hits", "captured"):
+            assert st[k] == st0[k], (last, k)
+        assert len(bins) == len(bins0) > 0
+        for f in EXACT:
+            assert np.array_equal(bins[f], bins0[f]), (last, f)
+        for f in SUMS:
+            assert np.allclose(bins[f], bins0[f], rtol=1e-12, atol=0), (last, f)
