@@ -271,11 +271,14 @@ struct rts_engine {
     int num_sms = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     // Work of a pulse that does not depend on the rest of the stream runs beside it (knob no_overlap turns both off):
-    //   side_dirs  k_primary_dirs needs the launch geometry only and two buffers that are free as soon as the previous
-    //              pulse's shading pass is done (ev_dirs_free) — it runs beside that pulse's last waves / bin emission and
-    //              this pulse's pose update; the footprint kernels wait for ev_dirs_done.  (Measured and not kept, DESIGN
-    //              §6: a second set of buffers so that it can run beside the previous pulse's footprint kernels or shading
-    //              pass — those need the fp64 pipe / the issue slots as much as it does, the sum stays the same.)
+    //   side_dirs  (lowest stream priority) k_primary_dirs needs the launch geometry only and two buffers whose last readers
+    //              are the previous batch's / pulse's shading pass and the BVH primary wave behind it (ev_dirs_free); in a
+    //              from-scratch pulse with moving targets the footprints of the triangles that never move follow it on this
+    //              stream (their records are not touched by the pose update), otherwise the engine's stream waits for the
+    //              directions (ev_dirs_done) and projects everything itself.  So this work runs beside the previous pulse's
+    //              last waves and bin emission and this pulse's pose update.  (Measured and not kept, DESIGN §6: a second
+    //              set of buffers so that the direction pass can run beside the previous pulse's footprint kernels or
+    //              shading pass — those need the fp64 pipe / the issue slots as much as it does, the sum stays the same.)
     //   side_bvh   the refit above the moving triangles (k_fit, k_pack, scene_abs, SAH read-back) forks behind the leaf
     //              boxes / triangle records (ev_bvh_fork); only traversal needs the nodes, so the footprint kernels run
     //              beside it and the first kernel that walks the tree waits for ev_bvh_done (bvh_join).

@@ -1189,9 +1189,10 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
         head_open = false;
     };
     if (!same_launch) {
-        // on its own stream (engine.h: side_dirs): the two buffers are free once the previous shading pass is done, and
-        // nothing else of this stream — the previous pulse's thin waves and bin emission, this pulse's pose update — has to
-        // be waited for; the footprint kernels below wait for the directions
+        // on its own stream (engine.h: side_dirs): the two buffers are free once the previous shading pass and the BVH
+        // primary wave behind it are done (ev_dirs_free, recorded in api.cu), and nothing else of this stream — the previous
+        // pulse's thin waves and bin emission, this pulse's pose update — has to be waited for; whatever of the footprint
+        // work stays on this stream waits for the directions (join_head)
         const bool side = e->side_dirs && !e->knobs.no_overlap;
         if (side) {
             if (!e->dirs_free_valid) cudaEventRecord(e->ev_dirs_free, st);
