@@ -296,6 +296,29 @@ def run_ours(args):
         return dict(ms=float(t[0]), own_ms=ms_dev, wall_ms=float(t[1]), waves=waves, split=split, follow=follow, segments=segs, captured=caps, d2h=d2h,
                     launches=eng.kernel_launches() - launches0)
 
+    def timed_pipelined(k0, k):
+        """The e2e loop of a host that keeps one pulse in flight: step i's inputs go to the device and pulse i is enqueued,
+        then pulse i-1's bins are read (rts_get_bins_previous: waits for pulse i-1's own read-back only).  Every step's
+        inputs are copied in and every step's bins are read back inside the timed region, the last one behind the loop."""
+        for i in range(k):
+            prepare((k0 + i) * world + rank if mode == "pulse" else k0 + i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        n_read = 0
+        for i in range(k):
+            step(k0 + i, False)
+            if i > 0:
+                n_read += 1 if len(eng.bins_previous()) >= 0 else 0
+        n_read += 1 if len(eng.bins()) >= 0 else 0
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        assert n_read == k
+        return dict(ms=float(t[0]))
+
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()          # nvidia-smi needs ~0.5 s to start sampling: begin before the warm-up
@@ -319,6 +342,16 @@ def run_ours(args):
     comm_mark("value leg")
     r_e2e = timed(k0, args.steps, read_back=True)
     comm_mark("e2e leg")
+    r_pipe = None
+    try:
+        r_pipe = timed_pipelined(k0, args.steps)
+    except Exception as ex:  # noqa: BLE001  (e.g. more than 256 non-empty bins: the pipelined read needs the eager block)
+        log(f"[bench] rank {rank}: pipelined e2e leg not run ({ex})")
+    ok_pipe = torch.tensor([1 if r_pipe is not None else 0], device=dev)
+    if world > 1:
+        torch.distributed.all_reduce(ok_pipe, op=torch.distributed.ReduceOp.MIN)
+    if int(ok_pipe) == 0:
+        r_pipe = None
     # the sustained leg: the same loop for at least --sustain seconds (same K on every rank)
     r_sus = None
     if args.sustain > 0 and not args.quick:
@@ -452,7 +485,10 @@ def run_ours(args):
                        "l2_policy": "per-step working set (BVH 64 MB + triangle records 81 MB + 0.4 GB of ray directions and 0.13 GB of hit words written and re-read) exceeds the 126 MB L2; no flush needed",
                        "parallelism": f"{'pulse' if mode == 'pulse' else 'ray'}-shard x{world}", "sharding": mode, "bin_exchange": exchange},
             "e2e": {"value": round(e2e, 2), "unit": "Mrays/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(r_e2e["d2h"] / args.steps),
-                    "ms_per_step": round(r_e2e["ms"] / args.steps, 4)},
+                    "ms_per_step": round(r_e2e["ms"] / args.steps, 4),
+                    "note": "every step waits for its own bins before the next pulse is enqueued (the reference's host loop); 'pipelined' = the same copies with one pulse in flight: pulse i is enqueued, then pulse i-1's bins are read (rts_get_bins_previous)",
+                    "pipelined": None if r_pipe is None else {"value": round(rays_per_step_total * args.steps / (r_pipe["ms"] * 1e-3) / 1e6, 2), "unit": "Mrays/s",
+                                                               "ms_per_step": round(r_pipe["ms"] / args.steps, 4)}},
             "gpu_launches": int(r_dev["launches"]),
             "roofline": roof,
             "clocks": clk,

@@ -166,6 +166,13 @@ int rts_kernel_launches(rts_engine *e, uint64_t *out);
 int rts_probe_read_bandwidth(rts_engine *e, uint64_t bytes, uint32_t reps, double *gbs);
 /* RTS_OUT_BINS: non-empty bins sorted by (rx, path). *n is the total even when cap is smaller. */
 int rts_get_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n);
+/* Pipelined host loops: the bins of the pulse BEFORE the last one enqueued.  A host that traces with RTS_ASYNC can enqueue
+ * pulse p+1 and then collect pulse p here — it waits only for pulse p's own read-back (two pinned blocks are used in turn),
+ * so the GPU never idles while the host consumes a pulse; pulses are independent (ray_tracer.cpp:843), the order of the
+ * responses a simulator receives is unchanged.  Needs pulse p traced with RTS_OUT_BINS, finalised (by the pulse itself,
+ * rts_finalise_bins or rts_comm_allreduce_bins) and at most 256 non-empty bins; RTS_ERR_STATE / RTS_ERR_CAPACITY otherwise.
+ * Counters and wave profile (rts_get_stats ...) always describe the last pulse. */
+int rts_get_bins_previous(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n);
 /* RTS_OUT_BINS: the responses the reference would emit for this pulse (ray_tracer.cpp:1289-1320): one per
  * unique d_pathMatch value, i.e. one per non-direct bin plus one for a receiver's direct bin when a direct
  * ray is that receiver's first received ray; sorted by representative slot like sort+unique(:1291-1292).

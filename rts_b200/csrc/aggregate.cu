@@ -567,14 +567,30 @@ static int enqueue_emit(rts_engine *e, uint32_t cap)
 // rest of the read-back, so that rts_get_bins costs one wait instead of three.  Small tables only.
 int agg_emit_bins_async(rts_engine *e)
 {
+    const bool again = e->bins_eager;   // this pulse's bins are being emitted a second time (rts_finalise_bins after a reduction): same block
     e->bins_eager = false;
     const uint64_t nb = e->n_bins_dense;
     if (!nb || !e->last_nrx || (!e->bins_hashed && nb > (1ull << 18))) return RTS_OK;
-    if (!e->h_bins && cudaMallocHost((void **)&e->h_bins, sizeof(rts_bin) * RTS_EAGER_BINS) != cudaSuccess) { e->h_bins = nullptr; return RTS_OK; }
+    if (!e->h_bins_buf[0]) {   // two pinned blocks, their counts and events (engine.h)
+        bool ok = cudaMallocHost((void **)&e->h_bins_count, sizeof(uint32_t) * 2) == cudaSuccess;
+        for (int k = 0; k < 2 && ok; k++)
+            ok = cudaMallocHost((void **)&e->h_bins_buf[k], sizeof(rts_bin) * RTS_EAGER_BINS) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&e->bins_ev[k], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) {
+            for (int k = 0; k < 2; k++) { if (e->h_bins_buf[k]) cudaFreeHost(e->h_bins_buf[k]); e->h_bins_buf[k] = nullptr; }
+            if (e->h_bins_count) cudaFreeHost(e->h_bins_count);
+            e->h_bins_count = nullptr; e->h_bins = nullptr;
+            cudaGetLastError();
+            return RTS_OK;
+        }
+    }
+    if (!again) e->bins_slot ^= 1;   // the other block: the previous pulse's may not have been read yet (rts_get_bins_previous)
+    e->h_bins = e->h_bins_buf[e->bins_slot];
     int rc = enqueue_emit(e, RTS_EAGER_BINS);
     if (rc) return rc;
-    RTS_CUDA(cudaMemcpyAsync(&e->h_rb->bins_count, e->d_bins_out_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+    RTS_CUDA(cudaMemcpyAsync(e->h_bins_count + e->bins_slot, e->d_bins_out_count, sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
     RTS_CUDA(cudaMemcpyAsync(e->h_bins, e->d_bins_out, sizeof(rts_bin) * RTS_EAGER_BINS, cudaMemcpyDeviceToHost, e->stream));
+    cudaEventRecord(e->bins_ev[e->bins_slot], e->stream);
     e->bins_eager = true;
     return RTS_OK;
 }
@@ -585,7 +601,7 @@ int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
     if (!nb || !e->last_nrx) { if (n) *n = 0; return RTS_OK; }
     if (e->bins_eager) {   // already in pinned memory (the caller has waited for the stream)
         RTS_CUDA(cudaStreamSynchronize(e->stream));
-        const uint32_t count = e->h_rb->bins_count;
+        const uint32_t count = e->h_bins_count[e->bins_slot];
         if (count <= RTS_EAGER_BINS) {
             const uint32_t got = std::min(count, cap);
             if (out && got) {
@@ -610,6 +626,25 @@ int agg_collect_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
     }
     if (n) *n = count;
     e->stats.n_bins = count;
+    return RTS_OK;
+}
+
+// The bins of the pulse before the last one, from the pinned block that pulse filled (engine.h: h_bins_buf).
+int agg_collect_bins_previous(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
+{
+    if (!e->prev_bins_eager || !e->h_bins_buf[0])
+        return rts_fail(RTS_ERR_STATE, "the pulse before the last one left no bins in pinned memory (it must have been traced with RTS_OUT_BINS, finalised, with a small bin table)");
+    RTS_CUDA(cudaEventSynchronize(e->bins_ev[e->prev_bins_slot]));
+    const uint32_t count = e->h_bins_count[e->prev_bins_slot];
+    if (count > RTS_EAGER_BINS)
+        return rts_fail(RTS_ERR_CAPACITY, "the pulse before the last one produced %u bins, more than the %u kept in pinned memory: read them with rts_get_bins before enqueuing the next pulse", count, RTS_EAGER_BINS);
+    const uint32_t got = std::min(count, cap);
+    if (out && got) {
+        std::vector<rts_bin> all(e->h_bins_buf[e->prev_bins_slot], e->h_bins_buf[e->prev_bins_slot] + count);
+        sort_bins(all.data(), count);
+        memcpy(out, all.data(), sizeof(rts_bin) * got);
+    }
+    if (n) *n = count;
     return RTS_OK;
 }
 

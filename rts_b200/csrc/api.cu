@@ -198,7 +198,8 @@ extern "C" void rts_destroy(rts_engine *e)
     for (cudaStream_t sd : {e->side_dirs, e->side_bvh}) if (sd) { cudaStreamSynchronize(sd); cudaStreamDestroy(sd); }
     for (cudaEvent_t ev : {e->ev_dirs_free, e->ev_dirs_done, e->ev_bvh_fork, e->ev_bvh_done}) if (ev) cudaEventDestroy(ev);
     if (e->h_rb) cudaFreeHost(e->h_rb);
-    if (e->h_bins) cudaFreeHost(e->h_bins);
+    for (int k = 0; k < 2; k++) { if (e->h_bins_buf[k]) cudaFreeHost(e->h_bins_buf[k]); if (e->bins_ev[k]) cudaEventDestroy(e->bins_ev[k]); }
+    if (e->h_bins_count) cudaFreeHost(e->h_bins_count);
     if (e->d_wave_segs) cudaFree(e->d_wave_segs);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -744,6 +745,7 @@ extern "C" int rts_trace_pulse(rts_engine *e, const rts_pulse *p, uint32_t flags
     e->last_B = (uint32_t)B; e->last_D = sz.depth_total; e->last_nrx = p->n_rx;
     e->last_begin = begin; e->last_stride = stride; e->last_n_primary = n_primary_total;
     e->bins_finalised = !(flags & RTS_NO_FINALISE);
+    e->prev_bins_eager = e->bins_eager; e->prev_bins_slot = e->bins_slot;   // what rts_get_bins_previous will read
     e->bins_eager = false;
     if ((flags & RTS_OUT_BINS) && e->bins_finalised) {
         int rc = agg_emit_bins_async(e);
@@ -1010,6 +1012,14 @@ extern "C" int rts_get_bins(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t 
     int rc = pulse_collect(e);
     if (rc) return rc;
     return agg_collect_bins(e, out, cap, n);
+}
+
+extern "C" int rts_get_bins_previous(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n)
+{
+    NvtxRange nvtx_range("rts:get_bins_previous");
+    if (!e) return rts_fail(RTS_ERR_ARG, "engine is NULL");
+    RTS_CUDA(cudaSetDevice(e->device));
+    return agg_collect_bins_previous(e, out, cap, n);
 }
 
 // ray_tracer.cpp:1289-1320 on the fused bins.  d_pathMatch of a ray = smallest received-list index among the

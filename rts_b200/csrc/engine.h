@@ -399,8 +399,16 @@ struct rts_engine {
     unsigned long long *d_ckeys = nullptr, *d_cmins = nullptr;   // compact copies of the occupied bins (multi-GPU exchange)
     double *d_csums = nullptr;
     uint64_t compact_alloc = 0;
-    rts_bin *d_bins_out = nullptr, *h_bins = nullptr;   // h_bins: pinned
+    rts_bin *d_bins_out = nullptr, *h_bins = nullptr;   // h_bins: pinned; the current one of h_bins_buf
     bool bins_eager = false;
+    // Two pinned blocks, used in turn by the pulses whose bins are brought to the host right behind them: a host that has
+    // enqueued pulse p+1 (RTS_ASYNC) can still read pulse p's bins (rts_get_bins_previous) — one wait for an event that
+    // was recorded behind pulse p's copies, while pulse p+1 runs.
+    rts_bin *h_bins_buf[2] = {nullptr, nullptr};
+    uint32_t *h_bins_count = nullptr;                   // pinned, [2]
+    cudaEvent_t bins_ev[2] = {nullptr, nullptr};
+    int bins_slot = 0, prev_bins_slot = 0;
+    bool prev_bins_eager = false;
     bool emit_precleared = false;      // the receiver totals / emitted-bin count were zeroed by the pulse's clear kernel
     double *d_rx_sums = nullptr;
     unsigned long long *d_rx_mins = nullptr;
@@ -487,6 +495,7 @@ int agg_hash_prepare(rts_engine *e, uint64_t slots);   // allocate / clear the s
 int agg_hash_compact(rts_engine *e, void **keys, void **sums, void **mins, uint32_t *n);
 int agg_hash_load(rts_engine *e, const void *keys, const void *sums, const void *mins, uint32_t n);
 int agg_emit_bins_async(rts_engine *e);
+int agg_collect_bins_previous(rts_engine *e, rts_bin *out, uint32_t cap, uint32_t *n);
 int agg_pulse_clear(rts_engine *e, bool dense_bins, uint64_t n_bins, uint32_t n_rx);   // one launch for everything a pulse starts from
 int agg_fill_records(rts_engine *e, uint64_t ray_total, uint32_t D, uint32_t W);
 int agg_get_received(rts_engine *e, uint64_t cap, uint64_t *n, uint64_t *slots, rts_ray_record *results, int32_t *targ_intersect,

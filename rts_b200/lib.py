@@ -52,7 +52,7 @@ EXPORTS = [
     "rts_rx_sphere_from_desc", "rts_result_sizes", "rts_rect_mesh", "rts_sphere_mesh", "rts_file_mesh",
     "rts_rotation_matrix", "rts_scene_set_targets", "rts_scene_set_poses", "rts_scene_rebuild", "rts_scene_bvh_info",
     "rts_scene_get_world_vertices", "rts_scene_get_tri_bounds", "rts_scene_check_bvh", "rts_trace_pulse",
-    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_get_split_profile", "rts_get_follow_profile", "rts_kernel_launches", "rts_probe_read_bandwidth", "rts_get_bins", "rts_get_responses", "rts_get_records", "rts_get_records_shard", "rts_get_received", "rts_bins_device", "rts_bins_compact_device", "rts_bins_load_compact", "rts_finalise_bins", "rts_aggregate", "rts_set_rcs_tables", "rts_set_antennas", "rts_comm_create", "rts_comm_ipc_handle", "rts_comm_local_ptr", "rts_comm_connect_ipc", "rts_comm_connect_ptrs", "rts_comm_allreduce_bins", "rts_comm_stats", "rts_comm_destroy",
+    "rts_sync", "rts_get_stats", "rts_get_wave_profile", "rts_get_split_profile", "rts_get_follow_profile", "rts_kernel_launches", "rts_probe_read_bandwidth", "rts_get_bins", "rts_get_bins_previous", "rts_get_responses", "rts_get_records", "rts_get_records_shard", "rts_get_received", "rts_bins_device", "rts_bins_compact_device", "rts_bins_load_compact", "rts_finalise_bins", "rts_aggregate", "rts_set_rcs_tables", "rts_set_antennas", "rts_comm_create", "rts_comm_ipc_handle", "rts_comm_local_ptr", "rts_comm_connect_ipc", "rts_comm_connect_ptrs", "rts_comm_allreduce_bins", "rts_comm_stats", "rts_comm_destroy",
 ]
 
 _lib = None
@@ -111,6 +111,7 @@ def load() -> C.CDLL:
     lib.rts_kernel_launches.argtypes = [vp, P(u64)]
     lib.rts_probe_read_bandwidth.argtypes = [vp, u64, u32, P(dbl)]
     lib.rts_get_bins.argtypes = [vp, P(RtsBin), u32, P(u32)]
+    lib.rts_get_bins_previous.argtypes = [vp, P(RtsBin), u32, P(u32)]
     lib.rts_get_responses.argtypes = [vp, P(RtsResponse), u32, P(u32)]
     lib.rts_get_records.argtypes = [vp, vp, P(i32), P(dbl), P(i32)]
     lib.rts_get_records_shard.argtypes = [vp, P(u64), vp, P(i32), P(dbl), P(i32)]
@@ -320,6 +321,13 @@ class Engine:
         if n.value > cap:
             out = np.zeros(n.value, dtype=BIN_DTYPE)
             _check(self._lib.rts_get_bins(self._h, out.ctypes.data_as(C.POINTER(RtsBin)), n.value, C.byref(n)))
+        return out[: n.value]
+
+    def bins_previous(self) -> np.ndarray:
+        """Bins of the pulse before the last one enqueued (pipelined host loops: rts_get_bins_previous)."""
+        n = C.c_uint32()
+        out = np.zeros(256, dtype=BIN_DTYPE)
+        _check(self._lib.rts_get_bins_previous(self._h, out.ctypes.data_as(C.POINTER(RtsBin)), 256, C.byref(n)))
         return out[: n.value]
 
     def responses(self) -> np.ndarray:

@@ -97,3 +97,34 @@ def test_pulses_enqueued_back_to_back_equal_pulses_traced_alone(engine, reuse):
             assert np.array_equal(bins[f], bins0[f]), (last, f)
         for f in SUMS:
             assert np.allclose(bins[f], bins0[f], rtol=1e-12, atol=0), (last, f)
+
+
+def test_bins_of_the_previous_pulse_while_the_next_one_runs(engine):
+    """rts_get_bins_previous: with pulse p+1 enqueued (RTS_ASYNC), pulse p's bins come from the pinned block pulse p filled;
+    equal to the bins of pulse p traced alone.  Without a previous pulse's bins the call fails, it does not guess."""
+    ms = scenes.terrain_scene(n=384, cells_x=96, cells_y=48, movers=6, n_rx=2)
+    engine.set_targets(ms.base)
+    flags = L.RTS_OUT_BINS | L.RTS_NO_REUSE
+    pulses = [0, 3, 1, 7]
+    alone = {}
+    for p in pulses:
+        engine.set_poses(*ms.poses(p))
+        engine.trace(ms.spec_for(p), flags)
+        alone[p] = engine.bins().copy()
+    engine.trace(ms.spec_for(pulses[-1]), L.RTS_OUT_RECORDS)          # a pulse that leaves no bins
+    engine.set_poses(*ms.poses(pulses[0]))
+    engine.trace(ms.spec_for(pulses[0]), flags | L.RTS_ASYNC)
+    with pytest.raises(RuntimeError):
+        engine.bins_previous()
+    got = []
+    for i, p in enumerate(pulses[1:], 1):
+        engine.set_poses(*ms.poses(p))
+        engine.trace(ms.spec_for(p), flags | L.RTS_ASYNC)
+        got.append((pulses[i - 1], engine.bins_previous().copy()))
+    got.append((pulses[-1], engine.bins().copy()))
+    for p, bins in got:
+        assert len(bins) == len(alone[p]) > 0
+        for f in EXACT:
+            assert np.array_equal(bins[f], alone[p][f]), (p, f)
+        for f in SUMS:
+            assert np.allclose(bins[f], alone[p][f], rtol=1e-12, atol=0), (p, f)
