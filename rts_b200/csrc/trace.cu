@@ -1231,15 +1231,23 @@ int trace_launch_raster(rts_engine *e, WaveParams &p, bool records, bool single_
     if (tl && !split) cudaEventRecord(tl[2], head_open && !cacheable && n_moving == 0 ? e->side_dirs : st);   // (approximate when the engine's stream still has to wait for the directions)
     if (split) {
         RTS_CUDA(cudaMemsetAsync(e->d_raster_ctl_static, 0, sizeof(RasterCtl), e->side_dirs));
+        // the movers' pass needs the directions, the cleared hit words and the cleared control block — not the static pass,
+        // beside which it runs (both passes only ever lower hit words; the chunk list is shared out between them)
+        cudaEventRecord(e->ev_dirs_done, e->side_dirs);
+        const uint32_t mov_items = 1u << 16;
         WaveParams q = p;
         q.raster_ctl = (RasterCtl *)e->d_raster_ctl_static;
         q.raster_skip = e->d_moving;
+        q.raster_item_cap = RTS_RASTER_ITEM_CAP - mov_items;
         if (tl) cudaEventRecord(tl[2], e->side_dirs);
         launch_footprints(e, q, p.n_tris, e->side_dirs);
-        join_head();
+        cudaStreamWaitEvent(st, e->ev_dirs_done, 0);
         p.raster_static = (const RasterCtl *)e->d_raster_ctl_static;
         p.raster_list = e->d_tlist; p.raster_list_count = e->n_dt;
+        p.raster_items = (RasterItem *)e->d_raster_items + (RTS_RASTER_ITEM_CAP - mov_items);
+        p.raster_item_cap = mov_items;
         launch_footprints(e, p, e->n_dt);
+        join_head();          // the shading pass needs both
         e->static_valid = false;
         e->split_static = true;
     } else if (cacheable) {
