@@ -89,7 +89,7 @@ int         rts_set_stream(rts_engine *e, void *cuda_stream);
  * ray_tracer.cpp:512).  The environment variable RTS_<NAME> gives an option its initial value when the engine is created;
  * the environment is never read again afterwards.  Names: "bvh" (0 = choose by SAH cost, 1 = Morton radix tree, 2 = PLOC),
  * "leaf_max" (1..8), "no_chain", "no_raster", "no_tiles", "one_ended_queue", "debug_raster", "no_static_hits",
- * "no_kept_reflections", "no_split", "split_below" (rays), "no_graph", "no_follow", "no_smem_bins", "no_overlap" (1 = no
+ * "no_kept_reflections", "no_split", "split_below" (rays), "no_follow", "no_smem_bins", "no_split_raster", "no_overlap" (1 = no
  * side streams: every kernel of a pulse on the engine's stream), "debug_timeline" (rts_sync prints when the direction pass,
  * the footprint kernels, the shading pass and the later waves of the last pulses ran), "batch" (primaries per batch, 0 = 2^24),
  * "hash_bins" (1 = sparse bin table also where a dense one would fit), "hash_log2" (log2 of its slots, default 22). */

@@ -77,7 +77,6 @@ static int set_option(rts_engine *e, const char *name, long long v)
         if (was && !k.no_split && e->scene_ready) { int rc = bvh_build(e); if (rc) return rc; }
     }
     else if (!strcmp(name, "split_below")) { if (v < 0 || v > (1ll << 30)) return rts_fail(RTS_ERR_ARG, "split_below out of range"); k.split_below = (uint32_t)v; }
-    else if (!strcmp(name, "no_graph")) k.no_graph = v != 0;
     else if (!strcmp(name, "no_follow")) k.no_follow = v != 0;
     else if (!strcmp(name, "no_smem_bins")) k.no_smem_bins = v != 0;
     else if (!strcmp(name, "no_split_raster")) k.no_split_raster = v < 0 ? -1 : (v != 0);   // -1: split even when nothing is in flight (tests)
@@ -126,7 +125,7 @@ extern "C" int rts_create(int device, rts_engine **out)
     e->stream = e->own_stream;
     // tuning / test switches: the environment is read here, once; afterwards only rts_set_option changes them
     for (const char *name : {"bvh", "leaf_max", "no_chain", "no_raster", "no_tiles", "one_ended_queue", "debug_raster", "no_static_hits",
-                             "no_kept_reflections", "no_split", "split_below", "no_graph", "no_follow", "no_smem_bins", "no_overlap", "debug_timeline", "no_split_raster", "batch", "hash_bins", "hash_log2"}) {
+                             "no_kept_reflections", "no_split", "split_below", "no_follow", "no_smem_bins", "no_overlap", "debug_timeline", "no_split_raster", "batch", "hash_bins", "hash_log2"}) {
         std::string env = "RTS_";
         for (const char *c = name; *c; c++) env += (char)toupper(*c);
         if (const char *v = getenv(env.c_str())) {

@@ -258,7 +258,7 @@ struct Comm {
 // Tuning / test switches: read from the environment once in rts_create, changed afterwards only through rts_set_option.
 struct Knobs {
     int no_chain = 0, no_raster = 0, no_tiles = 0, one_ended_queue = 0, debug_raster = 0, no_static_hits = 0,
-        no_kept_reflections = 0, no_split = 1, no_graph = 0, no_follow = 0, no_smem_bins = 0, no_overlap = 0, debug_timeline = 0, no_split_raster = 0;
+        no_kept_reflections = 0, no_split = 1, no_follow = 0, no_smem_bins = 0, no_overlap = 0, debug_timeline = 0, no_split_raster = 0;
     long long batch = 0;           // 0 = default 2^24 primaries per batch
     int hash_bins = 0;             // 1: sparse (hashed) bins also where a dense table would fit
     uint32_t hash_log2 = 22;       // slots of the sparse bin table
