@@ -192,7 +192,8 @@ def run_ours(args):
     info = eng.bvh_info()
     log(f"[bench] rank {rank}: BVH built in {info.ms_build:.2f} ms ({info.n_nodes} nodes)")
     # all of the engine's work and torch's events on one stream
-    stream = torch.cuda.Stream(dev, priority=-1)      # above the library's low-priority side stream (direction pass of the next pulse)
+    # above the library's low-priority side stream (direction pass and static footprints of the next pulse)
+    stream = torch.cuda.Stream(dev, priority=int(os.environ.get("RTS_BENCH_STREAM_PRIORITY", "-1")))
     torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
     # weak:   the launch grid is (1, 4096*N, 4096) — N x denser in azimuth — and rank r traces rays r, r+N, r+2N, ... of it,
