@@ -24,7 +24,9 @@
 #ifndef RTS_SHADE_MIN_BLOCKS
 #define RTS_SHADE_MIN_BLOCKS 6
 #endif
-#define RTS_RASTER_SMALL 160u          // footprints up to this many candidates are walked by their own thread
+#ifndef RTS_RASTER_SMALL
+#define RTS_RASTER_SMALL 160u          // footprints up to this many candidates are walked by their own thread (the slack of the edge functions assumes <= 160)
+#endif
 #define RTS_RASTER_CHUNK 2048u         // candidates per row chunk of a large footprint, at most (WaveParams::raster_chunk: fewer in small launches)
 #define RTS_RASTER_LIMIT 16ull         // candidates per primary ray beyond which the BVH primary wave is used
 
