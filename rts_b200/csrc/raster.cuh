@@ -63,9 +63,9 @@ __device__ __forceinline__ bool pixel_local(const WaveParams &P, unsigned iy, un
 }
 
 // ray directions of the batch, exactly as the wave kernel generates them, and the empty hit buffer
-// 128 threads in 32 registers: small blocks that fit beside whatever else is resident (the pass runs on engine.h's side_dirs).
+// 128 threads in at most 40 registers: small blocks that fit beside whatever else is resident (the pass runs on engine.h's side_dirs).
 #define RTS_DIRS_BLOCK 128
-__global__ void __launch_bounds__(RTS_DIRS_BLOCK, 16) k_primary_dirs(const __grid_constant__ WaveParams P)
+__global__ void __launch_bounds__(RTS_DIRS_BLOCK, 12) k_primary_dirs(const __grid_constant__ WaveParams P)
 {
     for (unsigned long long rel = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; rel < P.n_primary;
          rel += (unsigned long long)gridDim.x * blockDim.x) {

@@ -116,12 +116,12 @@ __device__ __forceinline__ d3 primary_direction(const WaveParams &P, uint32_t ix
     d.x = P.nx > 1 ? P.beamStart[0] + P.slope[0] * (ix) : P.beamStart[0];
     d.y = P.ny > 1 ? P.beamStart[1] + P.slope[1] * (iy) : P.beamStart[1];
     d.z = P.nz > 1 ? P.beamStart[2] + P.slope[2] * (iz) : P.beamStart[2];
-    d = normalised3(d);
+    d = normalised3_shared_rcp(d);
     d3 r = mk3(0, 0, 0);
     r.x += P.Rot[0] * d.x + P.Rot[1] * d.y + P.Rot[2] * d.z;
     r.y += P.Rot[3] * d.x + P.Rot[4] * d.y + P.Rot[5] * d.z;
     r.z += P.Rot[6] * d.x + P.Rot[7] * d.y + P.Rot[8] * d.z;
-    d = normalised3(r);
+    d = normalised3_shared_rcp(r);
     r = mk3(0, 0, 0);
     r.x += P.Rot1[0] * d.x + P.Rot1[1] * d.y + P.Rot1[2] * d.z;
     r.y += P.Rot1[3] * d.x + P.Rot1[4] * d.y + P.Rot1[5] * d.z;
